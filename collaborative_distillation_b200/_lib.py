@@ -1,0 +1,83 @@
+"""ctypes binding of libwctb.so (the C ABI declared in include/wctb.h).
+
+The product path has no CPU fallback: if the library is missing or fails to load, importing
+any op raises.  Nothing here imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libwctb.so")
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_d = ctypes.c_double
+
+# name -> argtypes ; every function returns int except where noted
+SIGNATURES = {
+    "wctb_abi_version": [],
+    "wctb_last_cuda_error": [],
+    "wctb_nchw_to_p4": [_p, _p, _i, _i, _i, _i, _p],
+    "wctb_p4_to_nchw": [_p, _p, _i, _i, _i, _p],
+    "wctb_pack_weights_fp32": [_p, _p, _i, _i, _p],
+    "wctb_pack_weights_tf32": [_p, _p, _i, _i, _p],
+    "wctb_tf32_kgroup": [_i, _i],
+    "wctb_tf32_supported": [_i, _i],
+    "wctb_conv3x3_first": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "wctb_conv3x3_p4": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "wctb_conv3x3_last": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "wctb_channel_sum": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "wctb_centered_gram": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "wctb_eigh_jacobi": [_p, _i, _i, _p, _i, _p, _p, _p, _p, _p],
+    "wctb_wct_matrix": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p],
+    "wctb_wct_apply": [_p, _p, _p, _p, _p, _i, _ll, _i, _p],
+    "wctb_fold_wct_into_conv": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "wctb_selftest_umma": [_p, _p, _p, _i, _i, _p],
+}
+
+WCTB_OK = 0
+EPI_NONE, EPI_POOL2, EPI_UP2 = 0, 1, 2
+ENGINE_FP32, ENGINE_TF32 = 0, 1
+
+
+class WctbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libwctb.so (once).  Raises WctbError if it is missing: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WctbError("libwctb.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise WctbError("failed to load %s: %s" % (LIB_PATH, e))
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _i
+    lib.wctb_error_string.argtypes = [_i]
+    lib.wctb_error_string.restype = ctypes.c_char_p
+    if lib.wctb_abi_version() != 1:
+        raise WctbError("libwctb ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code != WCTB_OK:
+        lib = load()
+        msg = lib.wctb_error_string(code).decode()
+        if code == -4:
+            msg += " (cudaError %d)" % lib.wctb_last_cuda_error()
+        raise WctbError("%s failed: %s" % (what, msg))

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Build libwctb.so in-tree with nvcc for sm_100a (no torch headers; plain C ABI)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SOURCES = ["conv_fp32.cu", "conv_umma.cu", "wct_transform.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(verbose=False, force=False):
+    out = os.path.join(HERE, "libwctb.so")
+    hdrs = [os.path.join(HERE, "common.cuh"), os.path.join(ROOT, "include", "wctb.h")]
+    hdrs += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    objs = []
+    for src in SOURCES:
+        s = os.path.join(HERE, src)
+        o = os.path.join(HERE, src.replace(".cu", ".o"))
+        if force or _stale(o, [s] + hdrs):
+            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            subprocess.check_call(cmd)
+        objs.append(o)
+    if force or _stale(out, objs):
+        subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-lcudart"])
+    return out
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

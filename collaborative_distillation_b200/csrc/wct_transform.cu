@@ -1,0 +1,573 @@
+// libwctb: the whiten-and-colour transform of util_wct.py on the GPU.
+//   channel sums / centred Gram (fp64 accumulate)  -> util_wct.py:68-70, 94-96
+//   one-sided Jacobi eigensolver (fp64)             -> util_wct.py:74, 100 (torch.svd of a symmetric PSD matrix)
+//   whitening/colouring matrix + alpha blend        -> util_wct.py:117-126, 219
+//   apply  csF = M (cF - mean_c) + b                -> util_wct.py:120, 125, 126
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------------
+// channel sums over a rectangular region of a P4 map
+// grid (row blocks, C/4); each CTA reduces its rows of one channel chunk.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float4* __restrict__ x, int H, int W, int y0, int y1,
+                                                          int x0, int x1, int rows_per_cta, double* __restrict__ out) {
+  const int c4 = blockIdx.y;
+  const int rbeg = y0 + blockIdx.x * rows_per_cta;
+  const int rend = min(y1, rbeg + rows_per_cta);
+  const float4* plane = x + (long long)c4 * H * W;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const int wreg = x1 - x0;
+  for (int r = rbeg; r < rend; ++r) {
+    const float4* row = plane + (long long)r * W + x0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n = 0;
+    for (int c = threadIdx.x; c < wreg; c += 256) {
+      float4 v = __ldg(row + c);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      if (++n == 64) { s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w; a = make_float4(0.f, 0.f, 0.f, 0.f); n = 0; }
+    }
+    s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+  }
+  __shared__ double red[4][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; red[3][warp] = s3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    atomicAdd(out + c4 * 4 + threadIdx.x, t);
+  }
+}
+extern "C" int wctb_channel_sum(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1, double* sum_out,
+                                void* stream) {
+  if (!x || !sum_out || C <= 0 || (C & 3) || H <= 0 || W <= 0 || y0 < 0 || y1 > H || x0 < 0 || x1 > W || y0 >= y1 ||
+      x0 >= x1)
+    return WCTB_E_BADARG;
+  int rows = y1 - y0;
+  int target = max(1, (4 * wctb_num_sms()) / (C / 4));
+  int rows_per_cta = max(1, (rows + target - 1) / target);
+  dim3 grid((rows + rows_per_cta - 1) / rows_per_cta, C / 4);
+  channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, H, W, y0, y1, x0, x1, rows_per_cta, sum_out);
+  WCTB_RETURN_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// centred Gram matrix  G += sum_p (x_p - mu)(x_p - mu)^T   in fp64 (DFMA).
+// A CTA owns a GBxGB block (bi <= bj) of G and a slice of the region's pixels; pixels are staged
+// centred, as doubles, in smem [pixel][GB]; 16x16 threads each accumulate a TBxTB sub-block
+// (GB = 16*TB; TB picked from C so small channel counts do not pay for padding).
+// Flush with fp64 atomics (order-dependent only at the 1e-16 level).
+// ------------------------------------------------------------------------------------------
+constexpr int GP = 32;   // pixels per smem stage
+template <int TB>
+__global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __restrict__ x, int C, int H, int W, int y0,
+                                                            int x0, int wreg, long long npix, long long pix_per_cta,
+                                                            const double* __restrict__ mean, double* __restrict__ G) {
+  constexpr int GB = 16 * TB;
+  constexpr int NCH4 = GB / 4;            // float4 chunks per channel block
+  __shared__ double sa[GP][GB + 1];
+  __shared__ double sb[GP][GB + 1];
+  const int nb = (C + GB - 1) / GB;
+  int bi = 0, bj = 0;
+  {
+    int t = blockIdx.y;
+    for (bi = 0; bi < nb; ++bi) {
+      int cnt = nb - bi;
+      if (t < cnt) { bj = bi + t; break; }
+      t -= cnt;
+    }
+  }
+  const bool diag = (bi == bj);
+  const long long pbeg = blockIdx.x * pix_per_cta;
+  const long long pend = min(npix, pbeg + pix_per_cta);
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4, tj = tid & 15;
+  double acc[TB][TB];
+#pragma unroll
+  for (int a = 0; a < TB; ++a)
+#pragma unroll
+    for (int b = 0; b < TB; ++b) acc[a][b] = 0.0;
+  const long long HW = (long long)H * W;
+  const int chA = bi * GB, chB = bj * GB;
+
+  for (long long p0 = pbeg; p0 < pend; p0 += GP) {
+    __syncthreads();
+    {
+      const int pp = tid & 31;
+      const long long p = p0 + pp;
+      const bool ok = p < pend;
+      long long off = 0;
+      if (ok) {
+        int r = (int)(p / wreg), c = (int)(p - (long long)r * wreg);
+        off = (long long)(y0 + r) * W + (x0 + c);
+      }
+      for (int ch4 = tid >> 5; ch4 < NCH4; ch4 += 8) {
+        double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (ok && chA + ch4 * 4 < C) {
+          float4 v = __ldg(x + (long long)(chA / 4 + ch4) * HW + off);
+          const double* m = mean + chA + ch4 * 4;
+          v0 = (double)v.x - m[0]; v1 = (double)v.y - m[1]; v2 = (double)v.z - m[2]; v3 = (double)v.w - m[3];
+        }
+        sa[pp][ch4 * 4 + 0] = v0; sa[pp][ch4 * 4 + 1] = v1; sa[pp][ch4 * 4 + 2] = v2; sa[pp][ch4 * 4 + 3] = v3;
+        if (!diag) {
+          v0 = v1 = v2 = v3 = 0;
+          if (ok && chB + ch4 * 4 < C) {
+            float4 v = __ldg(x + (long long)(chB / 4 + ch4) * HW + off);
+            const double* m = mean + chB + ch4 * 4;
+            v0 = (double)v.x - m[0]; v1 = (double)v.y - m[1]; v2 = (double)v.z - m[2]; v3 = (double)v.w - m[3];
+          }
+          sb[pp][ch4 * 4 + 0] = v0; sb[pp][ch4 * 4 + 1] = v1; sb[pp][ch4 * 4 + 2] = v2; sb[pp][ch4 * 4 + 3] = v3;
+        }
+      }
+    }
+    __syncthreads();
+    const double(*B)[GB + 1] = diag ? sa : sb;
+#pragma unroll 4
+    for (int pp = 0; pp < GP; ++pp) {
+      double a[TB], b[TB];
+#pragma unroll
+      for (int k = 0; k < TB; ++k) { a[k] = sa[pp][ti * TB + k]; b[k] = B[pp][tj + 16 * k]; }
+#pragma unroll
+      for (int u = 0; u < TB; ++u)
+#pragma unroll
+        for (int v = 0; v < TB; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < TB; ++u)
+#pragma unroll
+    for (int v = 0; v < TB; ++v) {
+      int i = chA + ti * TB + u, j = chB + tj + 16 * v;
+      if (i < C && j < C) {
+        atomicAdd(G + (long long)i * C + j, acc[u][v]);
+        if (!diag) atomicAdd(G + (long long)j * C + i, acc[u][v]);
+      }
+    }
+}
+extern "C" int wctb_centered_gram(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1,
+                                  const double* mean, double* gram_out, void* stream) {
+  if (!x || !mean || !gram_out || C <= 0 || (C & 3) || H <= 0 || W <= 0 || y0 < 0 || y1 > H || x0 < 0 || x1 > W ||
+      y0 >= y1 || x0 >= x1)
+    return WCTB_E_BADARG;
+  const int TB = C <= 16 ? 1 : (C <= 32 ? 2 : 4);
+  const int GBv = 16 * TB;
+  int nb = (C + GBv - 1) / GBv;
+  int nblk = nb * (nb + 1) / 2;
+  long long npix = (long long)(y1 - y0) * (x1 - x0);
+  int target = max(1, (4 * wctb_num_sms()) / nblk);
+  long long per = (npix + target - 1) / target;
+  per = ((per + GP - 1) / GP) * GP;
+  if (per < 8 * GP) per = 8 * GP;
+  unsigned gx = (unsigned)((npix + per - 1) / per);
+  dim3 grid(gx, nblk);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4* x4 = (const float4*)x;
+  if (TB == 1) centered_gram_kernel<1><<<grid, 256, 0, st>>>(x4, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
+  else if (TB == 2) centered_gram_kernel<2><<<grid, 256, 0, st>>>(x4, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
+  else centered_gram_kernel<4><<<grid, 256, 0, st>>>(x4, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
+  WCTB_RETURN_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi on G = scale*A (+I): column pairs are rotated until mutually
+// orthogonal; then  sigma_k = ||g_k|| = eigenvalue,  g_k / sigma_k = eigenvector (A symmetric PSD).
+// Round-robin ordering: C-1 rounds of C/2 disjoint pairs per sweep.
+// Variant 1 (C <= 128): one CTA per problem, G (column-major) resident in shared memory.
+// Variant 2 (any even C): cooperative grid, G in global memory (L2), grid.sync() per round.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rr_pair(int round, int k, int n, int& p, int& q) {
+  // circle method: player n-1 fixed, the others rotate
+  const int m = n - 1;
+  if (k == 0) { p = m; q = round % m; }
+  else { p = (round + k) % m; q = (round - k + m) % m; }
+  if (p > q) { int t = p; p = q; q = t; }
+}
+
+constexpr double JACOBI_TOL = 1e-15;
+constexpr int JACOBI_MAX_SWEEPS = 40;
+
+// rotate columns gp, gq (length n) cooperatively by `lanes` lanes (a power of two <= 32) of one warp
+template <int LANES>
+__device__ __forceinline__ int jacobi_rotate(double* gp, double* gq, int n, int sub, unsigned mask, double floor2) {
+  double a = 0, b = 0, c = 0;
+  for (int i = sub; i < n; i += LANES) {
+    double x = gp[i], y = gq[i];
+    a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(mask, a, o);
+    b += __shfl_xor_sync(mask, b, o);
+    c += __shfl_xor_sync(mask, c, o);
+  }
+  // converged pair: orthogonal to working precision, or one column is numerically null
+  if (c * c <= JACOBI_TOL * JACOBI_TOL * a * b || a <= floor2 || b <= floor2) return 0;
+  double zeta = (b - a) / (2.0 * c);
+  double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  double cs = rsqrt(1.0 + t * t);
+  double sn = cs * t;
+  for (int i = sub; i < n; i += LANES) {
+    double x = gp[i], y = gq[i];
+    gp[i] = cs * x - sn * y;
+    gq[i] = sn * x + cs * y;
+  }
+  return 1;
+}
+
+__global__ void __launch_bounds__(1024) jacobi_smem_kernel(const double* __restrict__ A, int C, const double* __restrict__ scale,
+                                                           int add_identity, double* __restrict__ evals,
+                                                           double* __restrict__ evecs, int* __restrict__ sweeps_out) {
+  extern __shared__ double G[];  // column-major C x C
+  __shared__ double s_fro;
+  const int prob = blockIdx.x;
+  const double sc = scale[prob];
+  const double* Ap = A + (long long)prob * C * C;
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    int r = i / C, c = i - r * C;
+    double v = Ap[i] * sc;
+    if (add_identity && r == c) v += 1.0;
+    G[c * C + r] = v;
+  }
+  if (threadIdx.x == 0) s_fro = 0;
+  __syncthreads();
+  {
+    double f = 0;
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) f = fma(G[i], G[i], f);
+    for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_fro, f);
+  }
+  __syncthreads();
+  const double floor2 = s_fro * 1e-30;  // column norm^2 below (1e-15 ||A||_F)^2 -> numerically null
+  constexpr int LANES = 16;
+  const int group = threadIdx.x / LANES, sub = threadIdx.x % LANES;
+  const int ngroups = blockDim.x / LANES;
+  const unsigned mask = 0xffffu << ((threadIdx.x & 31) & ~(LANES - 1));
+  int sweep = 0;
+  for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+    int rotated = 0;
+    for (int round = 0; round < C - 1; ++round) {
+      for (int k = group; k < C / 2; k += ngroups) {
+        int p, q;
+        rr_pair(round, k, C, p, q);
+        rotated |= jacobi_rotate<LANES>(G + p * C, G + q * C, C, sub, mask, floor2);
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) { ++sweep; break; }
+  }
+  // eigenvalues = column norms, eigenvectors = normalised columns
+  for (int k = group; k < C; k += ngroups) {
+    double a = 0;
+    for (int i = sub; i < C; i += LANES) a = fma(G[k * C + i], G[k * C + i], a);
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
+    double sig = sqrt(a);
+    double inv = sig > 0 ? 1.0 / sig : 0.0;
+    if (sub == 0) evals[(long long)prob * C + k] = sig;
+    for (int i = sub; i < C; i += LANES) evecs[(long long)prob * C * C + (long long)k * C + i] = G[k * C + i] * inv;
+  }
+  if (sweeps_out && threadIdx.x == 0) sweeps_out[prob] = sweep;
+}
+
+__global__ void __launch_bounds__(256) jacobi_global_kernel(const double* __restrict__ A, int nprob, int C,
+                                                            const double* __restrict__ scale, int add_identity,
+                                                            double* __restrict__ evals, double* __restrict__ evecs,
+                                                            double* __restrict__ work, int* __restrict__ flags,
+                                                            int* __restrict__ sweeps_out) {
+  cg::grid_group grid = cg::this_grid();
+  const long long CC = (long long)C * C;
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long gthreads = (long long)gridDim.x * blockDim.x;
+  // flags: [0..nprob) frobenius^2 (as double bits in work tail) -> use work + nprob*CC .. for fro; flags[sweep parity] rotated
+  double* fro = work + nprob * CC;
+  if (gtid < nprob) fro[gtid] = 0;
+  if (gtid < 2) flags[gtid] = 0;
+  grid.sync();
+  for (long long i = gtid; i < nprob * CC; i += gthreads) {
+    int prob = (int)(i / CC);
+    long long e = i - prob * CC;
+    int r = (int)(e / C), c = (int)(e - (long long)r * C);
+    double v = A[i] * scale[prob];
+    if (add_identity && r == c) v += 1.0;
+    work[prob * CC + (long long)c * C + r] = v;
+    double f = v * v;  // nprob*C*C and the stride are multiples of 32: a warp stays inside one problem
+    for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(fro + prob, f);
+  }
+  grid.sync();
+  const int warps_per_cta = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * warps_per_cta;
+  const int lane = threadIdx.x & 31;
+  const int pairs_per_prob = C / 2;
+  int sweep = 0;
+  for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+    int rotated = 0;
+    for (int round = 0; round < C - 1; ++round) {
+      for (int w = gwarp; w < nprob * pairs_per_prob; w += nwarps) {
+        int prob = w / pairs_per_prob, k = w - prob * pairs_per_prob;
+        int p, q;
+        rr_pair(round, k, C, p, q);
+        double* Gp = work + prob * CC;
+        rotated |= jacobi_rotate<32>(Gp + (long long)p * C, Gp + (long long)q * C, C, lane, 0xffffffffu,
+                                     fro[prob] * 1e-30);
+      }
+      grid.sync();
+    }
+    if (rotated && lane == 0) atomicOr(flags + (sweep & 1), 1);
+    grid.sync();
+    int any = *((volatile int*)(flags + (sweep & 1)));
+    if (gtid == 0) flags[(sweep + 1) & 1] = 0;
+    if (!any) { ++sweep; break; }
+    // the next sweep's first grid.sync orders the reset above before any atomicOr of that sweep+1 parity
+  }
+  grid.sync();
+  for (int w = gwarp; w < nprob * C; w += nwarps) {
+    int prob = w / C, k = w - prob * C;
+    const double* g = work + prob * CC + (long long)k * C;
+    double a = 0;
+    for (int i = lane; i < C; i += 32) a = fma(g[i], g[i], a);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    double sig = sqrt(a), inv = sig > 0 ? 1.0 / sig : 0.0;
+    if (lane == 0) evals[(long long)prob * C + k] = sig;
+    for (int i = lane; i < C; i += 32) evecs[prob * CC + (long long)k * C + i] = g[i] * inv;
+  }
+  if (sweeps_out && gtid < nprob) sweeps_out[gtid] = sweep;
+}
+
+extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale, int add_identity, double* evals,
+                                double* evecs, double* work, int* sweeps_out, void* stream) {
+  if (!a || !scale || !evals || !evecs || !work || nprob <= 0 || C < 2 || (C & 1)) return WCTB_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 128) {
+    size_t smem = (size_t)C * C * sizeof(double);
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = C >= 128 ? 1024 : (C >= 64 ? 512 : 256);
+    jacobi_smem_kernel<<<nprob, threads, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    WCTB_RETURN_LAUNCH();
+  }
+  // cooperative variant: work must hold nprob*C*C + nprob doubles + 2 ints (caller gives nprob*C*C + 16 doubles)
+  int* flags = reinterpret_cast<int*>(work + (long long)nprob * C * C + nprob);
+  int nblk_max = 0;
+  WCTB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk_max, jacobi_global_kernel, 256, 0));
+  if (nblk_max < 1) return WCTB_E_UNSUPPORTED;
+  int want = (nprob * (C / 2) + 7) / 8;
+  int gridx = min(want, wctb_num_sms() * min(nblk_max, 2));
+  void* args[] = {(void*)&a, (void*)&nprob, (void*)&C, (void*)&scale, (void*)&add_identity, (void*)&evals,
+                  (void*)&evecs, (void*)&work, (void*)&flags, (void*)&sweeps_out};
+  WCTB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_global_kernel, dim3(gridx), dim3(256), args, 0, st));
+  return WCTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// whitening / colouring matrix (fp64), tiny: C <= 512.
+//   T1 = Vc diag(Ec^-1/4 [kept]) , W = T1 T1^T ; T2 = Vs diag(Es^+1/4 [kept]), Col = T2 T2^T ; M = Col W
+// evecs are stored column k at [k*C + i].
+// ------------------------------------------------------------------------------------------
+__global__ void eig_max_kernel(const double* __restrict__ e, int C, double* __restrict__ out) {
+  double m = 0;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) m = fmax(m, e[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ double r[32];
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (blockDim.x >> 5); ++i) m = fmax(m, r[i]);
+    *out = m;
+  }
+}
+// out[i][j] = sum_k f(e_k) v_k[i] v_k[j]   (power = -0.5 or +0.5, thresholded at tau*emax)
+__global__ void spectral_fn_kernel(const double* __restrict__ e, const double* __restrict__ v, int C, double tau,
+                                   const double* __restrict__ emax, double power, double* __restrict__ out) {
+  int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  __shared__ double vi[16][17], vj[16][17], f[16];
+  double acc = 0;
+  const double thr = tau * (*emax);
+  for (int k0 = 0; k0 < C; k0 += 16) {
+    int k = k0 + threadIdx.y;
+    vi[threadIdx.y][threadIdx.x] = (k < C && blockIdx.y * 16 + threadIdx.x < C) ? v[(long long)k * C + blockIdx.y * 16 + threadIdx.x] : 0.0;
+    vj[threadIdx.y][threadIdx.x] = (k < C && blockIdx.x * 16 + threadIdx.x < C) ? v[(long long)k * C + blockIdx.x * 16 + threadIdx.x] : 0.0;
+    if (threadIdx.y == 0) {
+      int kk = k0 + threadIdx.x;
+      double ev = kk < C ? e[kk] : 0.0;
+      f[threadIdx.x] = (kk < C && ev > thr && ev > 0) ? pow(ev, power) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) acc = fma(f[kk] * vi[kk][threadIdx.y], vj[kk][threadIdx.x], acc);
+    __syncthreads();
+  }
+  if (i < C && j < C) out[(long long)i * C + j] = acc;
+}
+// M = alpha * (Col @ W) + (1-alpha) I  -> fp32 ; also b, mean_c
+__global__ void wct_matrix_kernel(const double* __restrict__ col, const double* __restrict__ wh, int C, double alpha,
+                                  const double* __restrict__ c_mean, const double* __restrict__ s_mean,
+                                  float* __restrict__ m_out, float* __restrict__ b_out, float* __restrict__ mc_out,
+                                  double* __restrict__ m64) {
+  int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  __shared__ double a[16][17], b[16][17];
+  double acc = 0;
+  for (int k0 = 0; k0 < C; k0 += 16) {
+    a[threadIdx.y][threadIdx.x] = (i < C && k0 + threadIdx.x < C) ? col[(long long)i * C + k0 + threadIdx.x] : 0.0;
+    b[threadIdx.y][threadIdx.x] = (k0 + threadIdx.y < C && j < C) ? wh[(long long)(k0 + threadIdx.y) * C + j] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) acc = fma(a[threadIdx.y][kk], b[kk][threadIdx.x], acc);
+    __syncthreads();
+  }
+  if (i < C && j < C) {
+    double v = alpha * acc + (i == j ? (1.0 - alpha) : 0.0);
+    m_out[(long long)i * C + j] = (float)v;
+    m64[(long long)i * C + j] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && i < C) {
+    b_out[i] = (float)(alpha * s_mean[i] + (1.0 - alpha) * c_mean[i]);
+    mc_out[i] = (float)c_mean[i];
+  }
+}
+extern "C" int wctb_wct_matrix(const double* c_evals, const double* c_evecs, const double* c_mean, const double* s_evals,
+                               const double* s_evecs, const double* s_mean, int C, double tau, double alpha,
+                               float* m_out, float* b_out, float* mean_c_out, double* work, void* stream) {
+  if (!c_evals || !c_evecs || !c_mean || !s_evals || !s_evecs || !s_mean || !m_out || !b_out || !mean_c_out || !work ||
+      C <= 0 || C > 1024)
+    return WCTB_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long CC = (long long)C * C;
+  double* wh = work;            // W   (whitening)
+  double* col = work + CC;      // Col (colouring)
+  double* m64 = work + 2 * CC;  // M in fp64
+  double* emax = work + 3 * CC; // [2] largest content / style eigenvalue
+  eig_max_kernel<<<1, 256, 0, st>>>(c_evals, C, emax);
+  eig_max_kernel<<<1, 256, 0, st>>>(s_evals, C, emax + 1);
+  dim3 blk(16, 16), grd((C + 15) / 16, (C + 15) / 16);
+  spectral_fn_kernel<<<grd, blk, 0, st>>>(c_evals, c_evecs, C, tau, emax, -0.5, wh);
+  spectral_fn_kernel<<<grd, blk, 0, st>>>(s_evals, s_evecs, C, tau, emax + 1, 0.5, col);
+  wct_matrix_kernel<<<grd, blk, 0, st>>>(col, wh, C, alpha, c_mean, s_mean, m_out, b_out, mean_c_out, m64);
+  WCTB_RETURN_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// apply: y = M (x - mean_c) + b  on a P4 map.  CTA: 128 pixels x 32 output channels (blockIdx.y),
+// the [C][32] slab of M^T in smem; thread = 1 pixel x 32 outputs... 2 pixels per thread to halve LDS/FMA.
+// ------------------------------------------------------------------------------------------
+constexpr int AP_CO = 32;
+__global__ void __launch_bounds__(128) wct_apply_kernel(const float4* __restrict__ x, const float* __restrict__ m,
+                                                        const float* __restrict__ b, const float* __restrict__ mean_c,
+                                                        float4* __restrict__ y, int C, long long npix, int rnd) {
+  extern __shared__ float4 sm4[];
+  float* mt = reinterpret_cast<float*>(sm4);  // [C][AP_CO]  (input channel major)
+  float* mc = mt + (size_t)C * AP_CO;         // [C]
+  const int co0 = blockIdx.y * AP_CO;
+  const int nco = min(AP_CO, C - co0);
+  for (int i = threadIdx.x; i < C * AP_CO; i += 128) {
+    int ci = i / AP_CO, o = i - ci * AP_CO;
+    mt[i] = o < nco ? m[(long long)(co0 + o) * C + ci] : 0.f;
+  }
+  for (int i = threadIdx.x; i < C; i += 128) mc[i] = mean_c[i];
+  __syncthreads();
+  const long long p0 = (blockIdx.x * 128LL + threadIdx.x) * 2;
+  if (p0 >= npix) return;
+  const bool two = p0 + 1 < npix;
+  float acc0[AP_CO], acc1[AP_CO];
+#pragma unroll
+  for (int o = 0; o < AP_CO; ++o) { acc0[o] = 0.f; acc1[o] = 0.f; }
+  const int C4 = C >> 2;
+  for (int c4 = 0; c4 < C4; ++c4) {
+    float4 v0 = __ldg(x + (long long)c4 * npix + p0);
+    float4 v1 = two ? __ldg(x + (long long)c4 * npix + p0 + 1) : v0;
+    const float* mcc = mc + c4 * 4;
+    float a0[4] = {v0.x - mcc[0], v0.y - mcc[1], v0.z - mcc[2], v0.w - mcc[3]};
+    float a1[4] = {v1.x - mcc[0], v1.y - mcc[1], v1.z - mcc[2], v1.w - mcc[3]};
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      const float4* row = reinterpret_cast<const float4*>(mt + (size_t)(c4 * 4 + ci) * AP_CO);
+#pragma unroll
+      for (int o4 = 0; o4 < AP_CO / 4; ++o4) {
+        float4 w = row[o4];
+        acc0[o4 * 4 + 0] = fmaf(a0[ci], w.x, acc0[o4 * 4 + 0]); acc1[o4 * 4 + 0] = fmaf(a1[ci], w.x, acc1[o4 * 4 + 0]);
+        acc0[o4 * 4 + 1] = fmaf(a0[ci], w.y, acc0[o4 * 4 + 1]); acc1[o4 * 4 + 1] = fmaf(a1[ci], w.y, acc1[o4 * 4 + 1]);
+        acc0[o4 * 4 + 2] = fmaf(a0[ci], w.z, acc0[o4 * 4 + 2]); acc1[o4 * 4 + 2] = fmaf(a1[ci], w.z, acc1[o4 * 4 + 2]);
+        acc0[o4 * 4 + 3] = fmaf(a0[ci], w.w, acc0[o4 * 4 + 3]); acc1[o4 * 4 + 3] = fmaf(a1[ci], w.w, acc1[o4 * 4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o4 = 0; o4 < AP_CO / 4; ++o4) {
+    if (o4 * 4 < nco) {
+      const float* bb = b + co0 + o4 * 4;
+      long long plane = (long long)(co0 / 4 + o4) * npix;
+      float4 r0 = make_float4(acc0[o4 * 4] + bb[0], acc0[o4 * 4 + 1] + bb[1], acc0[o4 * 4 + 2] + bb[2], acc0[o4 * 4 + 3] + bb[3]);
+      float4 r1 = make_float4(acc1[o4 * 4] + bb[0], acc1[o4 * 4 + 1] + bb[1], acc1[o4 * 4 + 2] + bb[2], acc1[o4 * 4 + 3] + bb[3]);
+      if (rnd) {
+        r0.x = wctb_tf32(r0.x); r0.y = wctb_tf32(r0.y); r0.z = wctb_tf32(r0.z); r0.w = wctb_tf32(r0.w);
+        r1.x = wctb_tf32(r1.x); r1.y = wctb_tf32(r1.y); r1.z = wctb_tf32(r1.z); r1.w = wctb_tf32(r1.w);
+      }
+      y[plane + p0] = r0;
+      if (two) y[plane + p0 + 1] = r1;
+    }
+  }
+}
+extern "C" int wctb_wct_apply(const float* x, const float* m, const float* b, const float* mean_c, float* y, int C,
+                              long long npix, int round_tf32, void* stream) {
+  if (!x || !m || !b || !mean_c || !y || C <= 0 || (C & 3) || C > 512 || npix <= 0) return WCTB_E_BADARG;
+  size_t smem = ((size_t)C * AP_CO + C) * sizeof(float);
+  WCTB_CUDA_TRY(cudaFuncSetAttribute(wct_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((npix + 255) / 256), (C + AP_CO - 1) / AP_CO);
+  wct_apply_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const float4*)x, m, b, mean_c, (float4*)y, C, npix, round_tf32);
+  WCTB_RETURN_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// fold csF = M (x - mean_c) + b into the decoder's first conv (see wctb.h)
+// ------------------------------------------------------------------------------------------
+__global__ void fold_w_kernel(const float* __restrict__ w, const float* __restrict__ m, float* __restrict__ w_out,
+                              int Cin, int Cout) {
+  // one thread per (o, i, t)
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long n = (long long)Cout * Cin * 9;
+  if (idx >= n) return;
+  int t = (int)(idx % 9);
+  int i = (int)((idx / 9) % Cin);
+  int o = (int)(idx / (9LL * Cin));
+  double acc = 0;
+  for (int j = 0; j < Cin; ++j) acc = fma((double)w[((long long)o * Cin + j) * 9 + t], (double)m[(long long)j * Cin + i], acc);
+  w_out[idx] = (float)acc;
+}
+__global__ void fold_b_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ m,
+                              const float* __restrict__ b, const float* __restrict__ mean_c, float* __restrict__ b_out,
+                              int Cin, int Cout) {
+  // one warp per output channel
+  int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (o >= Cout) return;
+  double acc = 0;
+  for (int j = lane; j < Cin; j += 32) {
+    double mm = 0;
+    for (int i = 0; i < Cin; ++i) mm = fma((double)m[(long long)j * Cin + i], (double)mean_c[i], mm);
+    double d = (double)b[j] - mm;
+    double ws = 0;
+    for (int t = 0; t < 9; ++t) ws += (double)w[((long long)o * Cin + j) * 9 + t];
+    acc = fma(ws, d, acc);
+  }
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) b_out[o] = (float)((double)bias[o] + acc);
+}
+extern "C" int wctb_fold_wct_into_conv(const float* w, const float* bias, const float* m, const float* b,
+                                       const float* mean_c, float* w_out, float* b_out, int Cin, int Cout, void* stream) {
+  if (!w || !bias || !m || !b || !mean_c || !w_out || !b_out || Cin <= 0 || Cout <= 0) return WCTB_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long n = (long long)Cout * Cin * 9;
+  fold_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, m, w_out, Cin, Cout);
+  fold_b_kernel<<<(Cout + 7) / 8, 256, 0, st>>>(w, bias, m, b, mean_c, b_out, Cin, Cout);
+  WCTB_RETURN_LAUNCH();
+}

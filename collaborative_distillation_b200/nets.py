@@ -1,0 +1,192 @@
+"""Drop-in encoder / decoder modules with the reference's class names and call signatures.
+
+reference: model/model_cd.py (SmallEncoder{1..5}_16x_aux, SmallDecoder{1..5}_16x),
+model/model_kd2sd.py (SmallDecoder{1..5}_16x_aux), model/model_original.py (Encoder{1..5}, Decoder{1..5}).
+`Cls(model=None, fixed=False)`; `forward(x[1,3,H,W]) -> [1,C,h,w]` / `forward(y[1,C,h,w]) -> [1,3,H',W']`.
+state_dict keys are the reference's (`conv0`, `conv11`, ..., `conv*_aux`, `aux*`), so the shipped .pth load unchanged.
+
+Unlike the reference, forward() runs hand-written sm_100a kernels (libwctb.so) and therefore needs CUDA
+tensors; a CPU tensor raises (no silent fallback).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import arch, ops
+from ._lib import WctbError
+
+_PRECISION = "tf32"   # "tf32": tcgen05 TF32 tensor-core engine where supported; "fp32": CUDA-core fp32 everywhere
+
+
+def set_precision(p: str):
+    global _PRECISION
+    if p not in ("fp32", "tf32"):
+        raise ValueError("precision must be 'fp32' or 'tf32'")
+    _PRECISION = p
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _load_state(module: nn.Module, model):
+    """model_cd.py:72-76 / model_original.py:24-30: accept {'model': sd} or a bare state_dict."""
+    if not model:
+        return
+    ext = os.path.splitext(model)[1]
+    if ext == ".t7":
+        raise WctbError("Torch7 .t7 weights need torch.utils.serialization.load_lua (removed in torch>=1.0); "
+                        "convert them to a .pth state_dict first (see INTEGRATION.md)")
+    assert ext == ".pth", "weights must be .pth or .t7 (model_original.py:24)"
+    sd = torch.load(model, map_location="cpu")
+    if isinstance(sd, dict) and "model" in sd and not torch.is_tensor(sd["model"]):
+        sd = sd["model"]
+    module.load_state_dict(sd)
+    print("load model '%s' successfully" % model)
+
+
+class _Net(nn.Module):
+    MODE = "16x"
+    STAGE = 5
+    KIND = "enc"
+    AUX = ()
+
+    def __init__(self, model=None, fixed=False):
+        super().__init__()
+        self.fixed = fixed
+        if self.KIND == "enc":
+            self.layers = arch.encoder_layers(self.MODE, self.STAGE)
+            self.conv0 = nn.Conv2d(3, 3, 1, 1, 0)
+            if self.MODE == "original" and self.STAGE == 5:   # model_original.py:427-433
+                with torch.no_grad():
+                    self.conv0.weight.copy_(torch.tensor([[0., 0, 255], [0, 255., 0], [255., 0, 0]]).view(3, 3, 1, 1))
+                    self.conv0.bias.copy_(torch.tensor([-103.939, -116.779, -123.68]))
+        else:
+            self.layers = arch.decoder_layers(self.MODE, self.STAGE)
+        for L in self.layers:
+            setattr(self, L["name"], nn.Conv2d(L["cin"], L["cout"], 3, 1, 0))
+        for name, cin, cout in self.AUX:
+            setattr(self, name, nn.Conv2d(cin, cout, 1, 1, 0))
+        _load_state(self, model)
+        if fixed:
+            for p in self.parameters():
+                p.requires_grad = False
+        self._pack_cache = {}
+
+    # ---------------------------------------------------------------- packing
+    def _cache_key(self, precision):
+        ps = [getattr(self, L["name"]).weight for L in self.layers]
+        return (precision, ps[0].device, tuple((p._version, p.data_ptr()) for p in ps))
+
+    def _engine(self, L, precision):
+        if precision == "tf32" and ops.tf32_supported(L["cin"], L["cout"]):
+            return ops.ENGINE_TF32
+        return ops.ENGINE_FP32
+
+    def _pack_layer(self, idx, precision, w=None, b=None):
+        L = self.layers[idx]
+        conv = getattr(self, L["name"])
+        w = conv.weight.detach() if w is None else w
+        b = conv.bias.detach() if b is None else b
+        first = self.KIND == "enc" and idx == 0
+        last = self.KIND == "dec" and idx == len(self.layers) - 1
+        if first:   # fold conv0 (1x1) into conv11: exact under reflection padding (SURVEY 8(a) note 1)
+            w0 = self.conv0.weight.detach().double().view(3, 3)
+            b0 = self.conv0.bias.detach().double()
+            wd = w.double()
+            b = (b.double() + torch.einsum("ojyx,j->o", wd, b0)).float()
+            w = torch.einsum("ojyx,ji->oiyx", wd, w0).float()
+        engine = ops.ENGINE_FP32 if (first or last) else self._engine(L, precision)
+        return {"w": ops.pack_weights(w.contiguous(), engine), "b": b.contiguous().float(), "engine": engine}
+
+    def packed(self, precision=None):
+        precision = precision or _PRECISION
+        key = self._cache_key(precision)
+        if self._pack_cache.get("key") != key:
+            self._pack_cache = {"key": key, "layers": [self._pack_layer(i, precision) for i in range(len(self.layers))]}
+        return self._pack_cache["layers"]
+
+    @staticmethod
+    def _check_cuda(x):
+        if not x.is_cuda:
+            raise WctbError("this module runs sm_100a CUDA kernels: input must be a CUDA tensor (no CPU fallback)")
+
+
+class _Encoder(_Net):
+    KIND = "enc"
+
+    def forward_p4(self, x, precision=None):
+        """x [1,3,H,W] (or [3,H,W]) CUDA fp32 -> P4 feature [C/4,h,w,4]"""
+        self._check_cuda(x)
+        precision = precision or _PRECISION
+        pk = self.packed(precision)
+        x = x.detach().contiguous().float()
+        H, W = x.shape[-2:]
+        n = len(self.layers)
+        sh, sw = arch.feature_hw(self.STAGE, H, W)
+        if sh < 2 or sw < 2:
+            raise WctbError("input %dx%d too small for stage %d (ReflectionPad2d needs >=2 px at the deepest level)" % (H, W, self.STAGE))
+        nxt = lambda i: pk[i + 1]["engine"] == ops.ENGINE_TF32 if i + 1 < n else False
+        y = ops.conv3x3_first(x, pk[0]["w"], pk[0]["b"], self.layers[0]["cout"], nxt(0))
+        for i in range(1, n):
+            L = self.layers[i]
+            epi = ops.EPI_POOL2 if L["pool_after"] else ops.EPI_NONE
+            y = ops.conv3x3_p4(y, pk[i]["w"], pk[i]["b"], L["cout"], epi, nxt(i), pk[i]["engine"])
+        return y
+
+    def forward(self, x):
+        return ops.p4_to_nchw(self.forward_p4(x))
+
+
+class _Decoder(_Net):
+    KIND = "dec"
+
+    def forward_p4(self, y, precision=None, first_override=None):
+        """y P4 [C/4,h,w,4] -> image [1,3,H,W].  first_override=(w_oihw, bias) replaces the first conv's
+        parameters (used to fold the WCT matrix into it)."""
+        self._check_cuda(y)
+        precision = precision or _PRECISION
+        pk = list(self.packed(precision))
+        if first_override is not None:
+            pk[0] = self._pack_layer(0, precision, first_override[0], first_override[1])
+        n = len(self.layers)
+        if y.shape[1] < 2 or y.shape[2] < 2:
+            raise WctbError("feature map too small for ReflectionPad2d(1)")
+        nxt = lambda i: (pk[i + 1]["engine"] == ops.ENGINE_TF32) if i + 1 < n else False
+        for i in range(n - 1):
+            L = self.layers[i]
+            epi = ops.EPI_UP2 if L["up_after"] else ops.EPI_NONE
+            y = ops.conv3x3_p4(y, pk[i]["w"], pk[i]["b"], L["cout"], epi, nxt(i), pk[i]["engine"])
+        return ops.conv3x3_last(y, pk[n - 1]["w"], pk[n - 1]["b"])
+
+    def first_layer_needs_tf32_input(self, precision=None):
+        pk = self.packed(precision or _PRECISION)
+        return len(pk) > 1 and pk[0]["engine"] == ops.ENGINE_TF32
+
+    def forward(self, y):
+        self._check_cuda(y)
+        return self.forward_p4(ops.nchw_to_p4(y.detach().contiguous().float(), self.first_layer_needs_tf32_input()))
+
+
+def _make(name, base, mode, stage, aux=()):
+    return type(name, (base,), {"MODE": mode, "STAGE": stage, "AUX": tuple(aux), "__doc__":
+                                "%s stage %d, mode %s (see module docstring)" % (base.KIND, stage, mode)})
+
+
+_g = globals()
+for _k in range(1, 6):
+    _g["Encoder%d" % _k] = _make("Encoder%d" % _k, _Encoder, "original", _k)
+    _g["Decoder%d" % _k] = _make("Decoder%d" % _k, _Decoder, "original", _k)
+    _g["SmallEncoder%d_16x_aux" % _k] = _make("SmallEncoder%d_16x_aux" % _k, _Encoder, "16x", _k, arch.ENCODER_AUX["16x"][_k])
+    _g["SmallDecoder%d_16x" % _k] = _make("SmallDecoder%d_16x" % _k, _Decoder, "16x", _k)
+    _g["SmallDecoder%d_16x_aux" % _k] = _make("SmallDecoder%d_16x_aux" % _k, _Decoder, "16x_kd2sd", _k, arch.DECODER_AUX_KD2SD[_k])
+
+ENCODERS = {"original": [_g["Encoder%d" % k] for k in range(1, 6)],
+            "16x": [_g["SmallEncoder%d_16x_aux" % k] for k in range(1, 6)]}
+ENCODERS["16x_kd2sd"] = ENCODERS["16x"]
+DECODERS = {"original": [_g["Decoder%d" % k] for k in range(1, 6)],
+            "16x": [_g["SmallDecoder%d_16x" % k] for k in range(1, 6)],
+            "16x_kd2sd": [_g["SmallDecoder%d_16x_aux" % k] for k in range(1, 6)]}

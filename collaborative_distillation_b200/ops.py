@@ -1,0 +1,180 @@
+"""Tensor-level wrappers over the C ABI (include/wctb.h).  torch is used for device memory and
+streams only; all arithmetic on the path happens inside libwctb.so.  CUDA tensors only."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, ENGINE_FP32, ENGINE_TF32, check  # noqa: F401
+
+_launches = 0  # number of libwctb kernel-launching calls (bench.py reports kernels via its own table)
+KERNELS_PER_CALL = {"nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
+                    "conv_last": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
+                    "fold": 2}
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(kind):
+    global _launches
+    _launches += KERNELS_PER_CALL[kind]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: torch.Tensor, dtype=torch.float32):
+    if not t.is_cuda:
+        raise _lib.WctbError("libwctb ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise _lib.WctbError("expected contiguous %s tensor, got %s contiguous=%s" % (dtype, t.dtype, t.is_contiguous()))
+    return t.data_ptr()
+
+
+def nchw_to_p4(x: torch.Tensor, round_tf32: bool = False) -> torch.Tensor:
+    """[C,H,W] (or [1,C,H,W]) -> P4 [C/4,H,W,4]"""
+    if x.dim() == 4:
+        x = x.squeeze(0)
+    C, H, W = x.shape
+    y = torch.empty(C // 4, H, W, 4, device=x.device, dtype=torch.float32)
+    check(_lib.load().wctb_nchw_to_p4(_need(x), _need(y), C, H, W, int(round_tf32), _stream()), "nchw_to_p4")
+    _count("nchw_to_p4")
+    return y
+
+
+def p4_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """P4 [C/4,H,W,4] -> [1,C,H,W]"""
+    C4, H, W, _ = x.shape
+    y = torch.empty(1, C4 * 4, H, W, device=x.device, dtype=torch.float32)
+    check(_lib.load().wctb_p4_to_nchw(_need(x), _need(y), C4 * 4, H, W, _stream()), "p4_to_nchw")
+    _count("p4_to_nchw")
+    return y
+
+
+def tf32_supported(cin: int, cout: int) -> bool:
+    return bool(_lib.load().wctb_tf32_supported(cin, cout))
+
+
+def pack_weights(w_oihw: torch.Tensor, engine: int) -> torch.Tensor:
+    cout, cin = w_oihw.shape[:2]
+    w = w_oihw.detach().contiguous().float()
+    dst = torch.empty(9 * cin * cout, device=w.device, dtype=torch.float32)
+    lib = _lib.load()
+    if engine == ENGINE_TF32:
+        check(lib.wctb_pack_weights_tf32(_need(w), _need(dst), cin, cout, _stream()), "pack_weights_tf32")
+        _count("pack_tf32")
+    else:
+        check(lib.wctb_pack_weights_fp32(_need(w), _need(dst), cin, cout, _stream()), "pack_weights_fp32")
+        _count("pack_fp32")
+    return dst
+
+
+def conv3x3_first(x_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor, cout: int, round_tf32: bool) -> torch.Tensor:
+    """x: [1,3,H,W] or [3,H,W]; w packed [9][3][cout] -> P4 [cout/4,H,W,4]"""
+    if x_nchw.dim() == 4:
+        x_nchw = x_nchw.squeeze(0)
+    _, H, W = x_nchw.shape
+    y = torch.empty(cout // 4, H, W, 4, device=x_nchw.device, dtype=torch.float32)
+    check(_lib.load().wctb_conv3x3_first(_need(x_nchw), _need(w), _need(b), _need(y), H, W, cout, int(round_tf32), _stream()),
+          "conv3x3_first")
+    _count("conv_first")
+    return y
+
+
+def conv3x3_p4(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, cout: int, epilogue: int, round_tf32: bool,
+               engine: int) -> torch.Tensor:
+    C4, H, W, _ = x.shape
+    if epilogue == EPI_POOL2:
+        Ho, Wo = H // 2, W // 2
+    elif epilogue == EPI_UP2:
+        Ho, Wo = 2 * H, 2 * W
+    else:
+        Ho, Wo = H, W
+    y = torch.empty(cout // 4, Ho, Wo, 4, device=x.device, dtype=torch.float32)
+    check(_lib.load().wctb_conv3x3_p4(_need(x), _need(w), _need(b), _need(y), H, W, C4 * 4, cout, epilogue,
+                                      int(round_tf32), engine, _stream()), "conv3x3_p4")
+    _count("conv_p4")
+    return y
+
+
+def conv3x3_last(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    C4, H, W, _ = x.shape
+    y = torch.empty(1, 3, H, W, device=x.device, dtype=torch.float32)
+    check(_lib.load().wctb_conv3x3_last(_need(x), _need(w), _need(b), _need(y), H, W, C4 * 4, _stream()), "conv3x3_last")
+    _count("conv_last")
+    return y
+
+
+def channel_sum(x: torch.Tensor, region=None) -> torch.Tensor:
+    """P4 map -> fp64 [C] sums over region (y0,y1,x0,x1) (default: whole map)"""
+    C4, H, W, _ = x.shape
+    y0, y1, x0, x1 = region if region is not None else (0, H, 0, W)
+    out = torch.zeros(C4 * 4, device=x.device, dtype=torch.float64)
+    check(_lib.load().wctb_channel_sum(_need(x), C4 * 4, H, W, y0, y1, x0, x1, _need(out, torch.float64), _stream()),
+          "channel_sum")
+    _count("channel_sum")
+    return out
+
+
+def centered_gram(x: torch.Tensor, mean: torch.Tensor, region=None) -> torch.Tensor:
+    """P4 map, fp64 mean [C] -> fp64 [C,C] sum (x-mean)(x-mean)^T over the region"""
+    C4, H, W, _ = x.shape
+    C = C4 * 4
+    y0, y1, x0, x1 = region if region is not None else (0, H, 0, W)
+    out = torch.zeros(C, C, device=x.device, dtype=torch.float64)
+    check(_lib.load().wctb_centered_gram(_need(x), C, H, W, y0, y1, x0, x1, _need(mean, torch.float64),
+                                         _need(out, torch.float64), _stream()), "centered_gram")
+    _count("centered_gram")
+    return out
+
+
+def eigh_jacobi(a: torch.Tensor, scale: torch.Tensor, add_identity: bool = False, return_sweeps: bool = False):
+    """a: fp64 [nprob,C,C] symmetric PSD; scale fp64 [nprob].  -> evals [nprob,C], evecs [nprob,C(k),C(i)]"""
+    nprob, C, _ = a.shape
+    evals = torch.empty(nprob, C, device=a.device, dtype=torch.float64)
+    evecs = torch.empty(nprob, C, C, device=a.device, dtype=torch.float64)
+    work = torch.empty(nprob * C * C + 16, device=a.device, dtype=torch.float64)
+    sweeps = torch.zeros(nprob, device=a.device, dtype=torch.int32)
+    check(_lib.load().wctb_eigh_jacobi(_need(a, torch.float64), nprob, C, _need(scale, torch.float64), int(add_identity),
+                                       _need(evals, torch.float64), _need(evecs, torch.float64),
+                                       _need(work, torch.float64), _need(sweeps, torch.int32), _stream()), "eigh_jacobi")
+    _count("eigh")
+    return (evals, evecs, sweeps) if return_sweeps else (evals, evecs)
+
+
+def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, alpha: float):
+    """-> (M fp32 [C,C], b fp32 [C], mean_c fp32 [C])  with csF = M (cF - mean_c) + b"""
+    C = c_evals.numel()
+    dev = c_evals.device
+    m = torch.empty(C, C, device=dev, dtype=torch.float32)
+    b = torch.empty(C, device=dev, dtype=torch.float32)
+    mc = torch.empty(C, device=dev, dtype=torch.float32)
+    work = torch.empty(3 * C * C + 8, device=dev, dtype=torch.float64)
+    f64 = torch.float64
+    check(_lib.load().wctb_wct_matrix(_need(c_evals, f64), _need(c_evecs, f64), _need(c_mean, f64), _need(s_evals, f64),
+                                      _need(s_evecs, f64), _need(s_mean, f64), C, float(tau), float(alpha), _need(m),
+                                      _need(b), _need(mc), _need(work, f64), _stream()), "wct_matrix")
+    _count("wct_matrix")
+    return m, b, mc
+
+
+def wct_apply(x: torch.Tensor, m: torch.Tensor, b: torch.Tensor, mean_c: torch.Tensor, round_tf32: bool = False) -> torch.Tensor:
+    C4, H, W, _ = x.shape
+    y = torch.empty_like(x)
+    check(_lib.load().wctb_wct_apply(_need(x), _need(m), _need(b), _need(mean_c), _need(y), C4 * 4, H * W, int(round_tf32),
+                                     _stream()), "wct_apply")
+    _count("wct_apply")
+    return y
+
+
+def fold_wct_into_conv(w_oihw, bias, m, b, mean_c):
+    cout, cin = w_oihw.shape[:2]
+    w_out = torch.empty_like(w_oihw)
+    b_out = torch.empty_like(bias)
+    check(_lib.load().wctb_fold_wct_into_conv(_need(w_oihw), _need(bias), _need(m), _need(b), _need(mean_c), _need(w_out),
+                                              _need(b_out), cin, cout, _stream()), "fold_wct_into_conv")
+    _count("fold")
+    return w_out, b_out

@@ -1,0 +1,115 @@
+"""Multi-GPU sharding of the stylization path: spatial strips + halos, one process per GPU.
+
+The reference is single-GPU.  Here an ultra-resolution content image (and the style image) is cut
+along W into `world` contiguous strips whose cuts are multiples of 16 px (2^4 = total pooling factor), so no
+pool window / upsample pair straddles a seam and the floor-pool shape chain equals the single-GPU one.
+
+Per stage k (WCT.py:98-106) every rank
+  1. receives a `halo(k)`-px image halo from its neighbours (one send/recv pair per side, NCCL over NVLink),
+     halo(k) = encoder + decoder receptive field of stage k rounded up to 16 (160/64/32/16/16 px for k=5..1),
+  2. runs encoder -> statistics -> eigensolve -> apply -> decoder on the extended strip; reflection padding
+     happens only at true image borders, the seam-side error stays inside the halo and is cropped away,
+  3. all-reduces the statistics (sum x: C doubles, centred Gram: C*C doubles) over its OWN strip only,
+so the result is tile-invariant: identical convolution arithmetic per pixel, statistics equal up to fp64
+summation order.  No feature map is ever gathered.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import arch
+
+
+def stage_halo(mode: str, stage: int) -> int:
+    """image-space halo (px, multiple of 16) that makes the own strip of stage `stage` exact."""
+    h = 0
+    for L in reversed(arch.decoder_layers(mode, stage)):
+        if L["up_after"]:
+            h = (h + 1) // 2
+        h += 1
+    for L in reversed(arch.encoder_layers(mode, stage)):
+        if L["pool_after"]:
+            h *= 2
+        h += 1
+    return ((h + 15) // 16) * 16
+
+
+def strip_cuts(W: int, world: int):
+    """cut positions [c0=0, c1, ..., c_world=W]; interior cuts are multiples of 16."""
+    cuts = [0]
+    for i in range(1, world):
+        cuts.append(int(round(i * W / world / 16.0)) * 16)
+    cuts.append(W)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b <= a:
+            raise ValueError("image width %d too small for %d strips" % (W, world))
+    return cuts
+
+
+class StripGroup:
+    """Strip-parallel driver.  `stage_fn(stage, content_ext, style_ext, alpha, c_region, s_region) -> image_ext`
+    is `WCT.style_transfer_stage` in production (with `wct.dist = self`), or a CPU restatement in the gloo tests."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    # ---- collectives used by WCT._moments
+    def allreduce_(self, t: torch.Tensor):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allreduce_count(self, n: float, device) -> float:
+        t = torch.tensor([n], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+    # ---- halo exchange
+    def exchange(self, own: torch.Tensor, halo: int):
+        """own [1,3,H,w] -> extended strip [1,3,H,lh+w+rh] and (lh, rh) actually attached (0 at true borders)."""
+        if self.world == 1 or halo == 0:
+            return own, 0, 0
+        w = own.shape[-1]
+        if w < halo:
+            raise ValueError("strip width %d < halo %d: use fewer GPUs for this image" % (w, halo))
+        r, n = self.rank, self.world
+        ops, left, right = [], None, None
+        if r > 0:
+            left = torch.empty(own.shape[:-1] + (halo,), dtype=own.dtype, device=own.device)
+            ops += [dist.P2POp(dist.isend, own[..., :halo].contiguous(), r - 1, self.group),
+                    dist.P2POp(dist.irecv, left, r - 1, self.group)]
+        if r < n - 1:
+            right = torch.empty(own.shape[:-1] + (halo,), dtype=own.dtype, device=own.device)
+            ops += [dist.P2POp(dist.isend, own[..., -halo:].contiguous(), r + 1, self.group),
+                    dist.P2POp(dist.irecv, right, r + 1, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        parts = [p for p in (left, own, right) if p is not None]
+        return torch.cat(parts, dim=-1).contiguous(), (halo if left is not None else 0), (halo if right is not None else 0)
+
+    @staticmethod
+    def own_slice(full: torch.Tensor, cuts, rank: int):
+        return full[..., cuts[rank]:cuts[rank + 1]].contiguous()
+
+    def stylize(self, stage_fn, mode: str, content_own: torch.Tensor, style_own: torch.Tensor, alpha: float = 1.0,
+                stages=(5, 4, 3, 2, 1), num_run: int = 1) -> torch.Tensor:
+        """content_own / style_own: this rank's strips [1,3,H,w].  Returns this rank's strip of the stylized image."""
+        hmax = max(stage_halo(mode, s) for s in stages)
+        style_ext, s_lh, s_rh = self.exchange(style_own, hmax)
+        img = content_own
+        for _ in range(num_run):
+            for s in stages:
+                h = stage_halo(mode, s)
+                ext, lh, rh = self.exchange(img, h)
+                H, We = ext.shape[-2:]
+                c_region = (0, H, lh, We - rh)
+                st = style_ext[..., (s_lh - min(s_lh, h)):style_ext.shape[-1] - (s_rh - min(s_rh, h))]
+                sl, sr = min(s_lh, h), min(s_rh, h)
+                s_region = (0, st.shape[-2], sl, st.shape[-1] - sr)
+                out = stage_fn(s, ext, st.contiguous(), alpha, c_region, s_region)
+                # floor-pool may have dropped trailing rows/cols (global right/bottom edge only)
+                x1 = min(We - rh, out.shape[-1])
+                img = out[..., lh:x1].contiguous()
+        return img

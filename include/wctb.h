@@ -1,0 +1,149 @@
+/*
+ * wctb.h -- C ABI of libwctb.so: the B200 (sm_100a) kernels behind the WCT stylization
+ * hot path of MingSun-Tse/Collaborative-Distillation (PytorchWCT/WCT.py + util_wct.py +
+ * model/model_{cd,original,kd2sd}.py).
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); its boundary for this path is
+ * the Python call surface listed below.  Each entry point names the reference call it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the Python side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (e.g. torch Tensor.data_ptr())
+ *    unless the name ends in _host;
+ *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it:
+ *    no allocation, no synchronisation, no global state;
+ *  - return value: WCTB_OK (0) or a negative WCTB_E_* code; never throws;
+ *  - activations between layers use the "P4" layout  [C/4][H][W][4] fp32  (channel-chunk
+ *    planar: one float4 = 4 consecutive channels of one pixel).  Images and the public
+ *    feature tensors are plain NCHW fp32 (batch 1), converted at the boundary.
+ */
+#ifndef WCTB_H_
+#define WCTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WCTB_ABI_VERSION 1
+
+enum {
+  WCTB_OK = 0,
+  WCTB_E_BADARG = -1,     /* shape / alignment / enum out of range */
+  WCTB_E_UNSUPPORTED = -2,/* configuration not built (e.g. channel count) */
+  WCTB_E_WORKSPACE = -3,  /* workspace too small */
+  WCTB_E_CUDA = -4        /* a CUDA runtime call failed; see wctb_last_cuda_error() */
+};
+
+/* epilogue of a conv layer (what follows conv+bias+ReLU in the reference forward()) */
+enum {
+  WCTB_EPI_NONE = 0,
+  WCTB_EPI_POOL2 = 1, /* nn.MaxPool2d(2,2) floor mode fused on the output (model_cd.py:709,727) */
+  WCTB_EPI_UP2 = 2    /* nn.UpsamplingNearest2d(2) fused on the output   (model_cd.py:261,278) */
+};
+
+/* which arithmetic a P4->P4 conv uses */
+enum {
+  WCTB_ENGINE_FP32 = 0, /* CUDA-core FFMA, fp32 exact-order reference path            */
+  WCTB_ENGINE_TF32 = 1  /* tcgen05.mma kind::tf32, operands pre-rounded (rna) to TF32 */
+};
+
+int wctb_abi_version(void);
+const char* wctb_error_string(int code);
+int wctb_last_cuda_error(void); /* cudaError_t of the last WCTB_E_CUDA on this thread */
+
+/* ---- layout conversion at the public boundary -------------------------------------------
+ * replaces: implicit NCHW tensors flowing between nn.Modules (model_cd.py:724-743).      */
+int wctb_nchw_to_p4(const float* src_nchw, float* dst_p4, int C, int H, int W, int round_tf32, void* stream);
+int wctb_p4_to_nchw(const float* src_p4, float* dst_nchw, int C, int H, int W, void* stream);
+
+/* ---- weight packing (once, at load time) ---------------------------------------------
+ * src: OIHW fp32 [Cout][Cin][3][3] as in the reference state_dict (model_cd.py:690-702).
+ * FP32 engine layout:  [tap 9][Cin][Cout] fp32.
+ * TF32 engine layout:  [Cin/KG][tap 9][KG/4][Cout][4] fp32 rounded to TF32 (rna); KG = wctb_tf32_kgroup(Cin,Cout) */
+int wctb_pack_weights_fp32(const float* w_oihw, float* dst, int Cin, int Cout, void* stream);
+int wctb_pack_weights_tf32(const float* w_oihw, float* dst, int Cin, int Cout, void* stream);
+int wctb_tf32_kgroup(int Cin, int Cout);
+int wctb_tf32_supported(int Cin, int Cout);
+
+/* ---- convolutions: ReflectionPad2d(1) + Conv2d(3x3) + bias + ReLU (+pool / +upsample) ----
+ * replaces: `self.relu(self.convXY(self.pad(y)))` (+ `self.pool` / `self.unpool`) in
+ *   SmallEncoder{1..5}_16x_aux.forward (model_cd.py:346-349,403-409,485-494,589-603,724-743),
+ *   SmallDecoder{1..5}_16x.forward (model_cd.py:83-85,117-122,159-167,211-224,276-294),
+ *   Encoder{1..5} and Decoder{1..5} forward (model_original.py:36-39 ... 581-599).
+ * round_tf32 != 0: the stored activation is rounded to TF32 (round-to-nearest-away) so that a
+ *   following WCTB_ENGINE_TF32 layer reads exactly representable operands.                */
+
+/* first layer: x NCHW [3][H][W] -> y P4 [Cout/4][H][W][4]; conv0 (1x1, model_cd.py:725) is folded
+ * into `w` by the host (exact under reflection padding).  w: [tap][3][Cout], Cout % 4 == 0. */
+int wctb_conv3x3_first(const float* x_nchw, const float* w, const float* bias, float* y_p4,
+                       int H, int W, int Cout, int round_tf32, void* stream);
+
+/* middle layers: P4 -> P4.  Output is [Cout/4][Ho][Wo][4] with (Ho,Wo) = (H,W), (H/2,W/2) or (2H,2W). */
+int wctb_conv3x3_p4(const float* x_p4, const float* w_packed, const float* bias, float* y_p4,
+                    int H, int W, int Cin, int Cout, int epilogue, int round_tf32, int engine,
+                    void* stream);
+
+/* last decoder layer: P4 [Cin/4][H][W][4] -> NCHW [3][H][W], ReLU kept (model_cd.py:293). w: [tap][Cin][3] */
+int wctb_conv3x3_last(const float* x_p4, const float* w, const float* bias, float* y_nchw,
+                      int H, int W, int Cin, void* stream);
+
+/* ---- WCT statistics ------------------------------------------------------------------
+ * replaces: torch.mean(cF,1) / cF - mean / torch.mm(cF, cF.t()) (util_wct.py:68-70, 94-96).
+ * x is P4 [C/4][H][W][4]; the sums run over the region rows [y0,y1) x cols [x0,x1) only
+ * (the whole map for one GPU; the rank's own strip without halo when sharded).
+ * channel_sum:   sum_out[C]  (fp64)  += sum over region of x          (caller zeroes it)
+ * centered_gram: gram_out[C*C] (fp64, row-major, full symmetric) += sum (x-mean)(x-mean)^T  */
+int wctb_channel_sum(const float* x_p4, int C, int H, int W, int y0, int y1, int x0, int x1,
+                     double* sum_out, void* stream);
+int wctb_centered_gram(const float* x_p4, int C, int H, int W, int y0, int y1, int x0, int x1,
+                       const double* mean, double* gram_out, void* stream);
+
+/* ---- symmetric eigendecomposition (one-sided Jacobi, fp64) ------------------------------
+ * replaces: torch.svd(contentConv, some=False) / torch.svd(styleConv) (util_wct.py:74,100);
+ * only (E, V) are consumed there and the matrices are symmetric PSD.
+ * a: nprob matrices [C][C] fp64 (row-major symmetric), each scaled by `scale` and, if
+ * add_identity, + I (the `--numpy` variant, util_wct.py:143) before the solve.
+ * Outputs per problem: evals[C] (>= 0, unsorted), evecs[C][C] column k = unit eigenvector k
+ * stored as evecs[k*C + i] (zero vector when the eigenvalue is exactly 0).
+ * work: nprob*C*C + 16 doubles of scratch.  sweeps_out (optional, may be NULL): int[nprob].    */
+int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale, int add_identity,
+                     double* evals, double* evecs, double* work, int* sweeps_out, void* stream);
+
+/* ---- whitening / colouring matrix ----------------------------------------------------
+ * replaces: util_wct.py:117-126 + the alpha blend of transform() (util_wct.py:219):
+ *   W   = sum_{k: Ec_k > tau*max(Ec)} Ec_k^-1/2 vc_k vc_k^T        (117-119)
+ *   Col = sum_{k: Es_k > tau*max(Es)} Es_k^+1/2 vs_k vs_k^T        (124-125)
+ *   M   = alpha * Col W + (1-alpha) I ;  b = alpha*mean_s + (1-alpha)*mean_c
+ * so that  csF = M (cF - mean_c) + b.   (tau replaces EigenValueThre=1e-100)
+ * Outputs fp32: m_out [C][C] row-major (row = output channel), b_out [C], mean_c_out [C].
+ * work: 3*C*C + 8 doubles.                                                                  */
+int wctb_wct_matrix(const double* c_evals, const double* c_evecs, const double* c_mean,
+                    const double* s_evals, const double* s_evecs, const double* s_mean,
+                    int C, double tau, double alpha, float* m_out, float* b_out,
+                    float* mean_c_out, double* work, void* stream);
+
+/* csF = M (cF - mean_c) + b on a P4 map of npix pixels (whole extended strip).
+ * replaces: torch.mm(step2, cF), torch.mm(..., whiten_cF), + s_mean (util_wct.py:120,125,126). */
+int wctb_wct_apply(const float* x_p4, const float* m, const float* b, const float* mean_c,
+                   float* y_p4, int C, long long npix, int round_tf32, void* stream);
+
+/* Fold csF = M(x-mean_c)+b into the decoder's first conv (exact: the conv is linear before its
+ * ReLU and reflection padding maps constants to constants):
+ *   w_out[o][i][t] = sum_j w_oihw[o][j][t] * M[j][i]
+ *   b_out[o]       = bias[o] + sum_{j,t} w_oihw[o][j][t] * (b[j] - (M mean_c)[j])
+ * w_out is OIHW fp32 (pack it afterwards).                                                */
+int wctb_fold_wct_into_conv(const float* w_oihw, const float* bias, const float* m, const float* b,
+                            const float* mean_c, float* w_out, float* b_out, int Cin, int Cout,
+                            void* stream);
+
+/* ---- self tests (device-side descriptor / pipeline checks used by tests and smoke) ------- */
+int wctb_selftest_umma(float* out_128xN, const float* a_128xK, const float* b_NxK, int N, int K,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WCTB_H_ */
