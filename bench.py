@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/sec, end-to-end 5-stage WCT stylize (16x-pruned VGG-19, UHD) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|weak]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one full pass of the hot path over one synthetic content/style pair: 5 coarse-to-fine stages of
+encoder(style), encoder(content), whiten-and-colour transform, decoder (WCT.py:120-125).
+  value : content megapixels / second with inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the public API from pinned HOST buffers, H2D + D2H inside the timed region
+  roofline : the dominant kernel (by time) measured live with CUDA events on the launch stream
+  cpu_baseline : the CPU oracle (port of the reference path, torch-cpu fp32 convs + fp64 transform) on a bounded sample
+Default workload (N=1): BASELINE.json configs[2] = 3840x2160 content / 2000x2000 style, --mode 16x --UHD
+(the config the UHD metric is quoted on; it fits one GPU).  N>1: weak scaling, content 2160 x (3840*N) cut into
+N strips along W (halo exchange + statistic all-reduces per stage), style 2000x2000 sharded the same way.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {  # name -> (content HxW, style HxW)
+    "cfg2": ((1024, 1024), (512, 512)),
+    "cfg3": ((2160, 3840), (2000, 2000)),
+    "cfg4": ((4096, 10240), (2160, 3840)),
+}
+WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_16x.npz")
+
+
+def algorithmic_conv_flops(mode, Hc, Wc, Hs, Ws):
+    """sum over executed convs of 2*9*Cin*Cout*H_l*W_l (+conv0), encoder on content AND style."""
+    from collaborative_distillation_b200 import arch
+    total = 0.0
+    for s in range(1, 6):
+        for (H, W, with_dec) in ((Hc, Wc, True), (Hs, Ws, False)):
+            h, w = H, W
+            total += 2 * 3 * 3 * h * w
+            for L in arch.encoder_layers(mode, s):
+                total += 2 * 9 * L["cin"] * L["cout"] * h * w
+                if L["pool_after"]:
+                    h, w = h // 2, w // 2
+            if with_dec:
+                for L in arch.decoder_layers(mode, s):
+                    total += 2 * 9 * L["cin"] * L["cout"] * h * w
+                    if L["up_after"]:
+                        h, w = h * 2, w * 2
+    return total
+
+
+class ClockSampler:
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = []
+        reasons = set()
+        mx = None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(Hc, Wc, Hs, Ws, steps, warmup, threads):
+    """Time the CPU oracle (reference algorithm: torch-cpu fp32 convs, fp64 SVD transform) -> (MP/s, ms/step)."""
+    from oracle import wct_oracle as O
+    torch.set_num_threads(threads)
+    w = O.load_weights_npz(WEIGHTS)
+    g = torch.Generator().manual_seed(0)
+    content, style = torch.rand(1, 3, Hc, Wc, generator=g), torch.rand(1, 3, Hs, Ws, generator=g)
+    for _ in range(warmup):
+        O.stylize(w, "16x", content, style)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.stylize(w, "16x", content, style)
+        ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    return Hc * Wc / 1e6 / t, t * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    (Hc, Wc), (Hs, Ws) = CONFIGS["cfg2"]          # bounded sample of the workload: cfg2-sized pair per step
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    mps, ms = cpu_reference_pass(Hc, Wc, Hs, Ws, steps, warmup, threads)
+    sample = "%dx%d content / %dx%d style, 16x, 5 stages, %d timed passes" % (Wc, Hc, Ws, Hs, steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "megapixels/sec end-to-end WCT stylize (16x VGG, UHD)", "value": round(mps, 4),
+        "unit": "MP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 convs + f64 transform",
+        "data": "synthetic torch.rand images (seed 0), shipped 16x weights",
+        "config": {"workload": "CPU oracle (port of the reference torch path) on a bounded sample: " + sample,
+                   "mode": "16x", "alpha": 1.0},
+        "cpu_baseline": {"value": round(mps, 4), "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(mps, 4), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=None, help="cfg2|cfg3|cfg4|weak (default: cfg3 at N=1, weak at N>1)")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--fold", type=int, default=0, help="fold the WCT matrix into the decoder's first conv")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from types import SimpleNamespace
+
+    import collaborative_distillation_b200 as P
+    from collaborative_distillation_b200 import ops, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = world
+
+    cfg = args.config or ("cfg3" if N == 1 else "weak")
+    if cfg == "weak":
+        (Hc, Wc), (Hs, Ws) = (2160, 3840 * N), (2000, 2000)
+        wl = "weak-scaling family of configs[2]: %dx%d content (3840 px of width per GPU) / %dx%d style, --mode 16x --UHD" % (Wc, Hc, Ws, Hs)
+    else:
+        (Hc, Wc), (Hs, Ws) = CONFIGS[cfg]
+        wl = "BASELINE configs %s: %dx%d content / %dx%d style, --mode 16x%s" % (cfg, Wc, Hc, Ws, Hs, "" if cfg == "cfg2" else " --UHD")
+
+    P.set_precision(args.precision)
+    wct = P.WCT(SimpleNamespace(mode="16x", numpy=False))
+    P.weights.load_npz_into(wct, WEIGHTS)
+    wct = wct.to(dev)
+    wct.fold_into_decoder = bool(args.fold)
+
+    g = torch.Generator().manual_seed(0)
+    content_h = torch.rand(1, 3, Hc, Wc, generator=g)
+    style_h = torch.rand(1, 3, Hs, Ws, generator=g)
+    grp = None
+    if N > 1:
+        grp = parallel.StripGroup()
+        wct.dist = grp
+        content_h = grp.own_slice(content_h, parallel.strip_cuts(Wc, N), rank)
+        style_h = grp.own_slice(style_h, parallel.strip_cuts(Ws, N), rank)
+    content_h, style_h = content_h.pin_memory(), style_h.pin_memory()
+    content_d, style_d = content_h.to(dev), style_h.to(dev)
+    out_h = torch.empty(1, 3, (Hc >> 4) << 4, content_h.shape[-1], dtype=torch.float32).pin_memory()
+
+    def step(c, s):
+        if grp is None:
+            return wct.stylize(c, s, alpha=1.0)
+        return grp.stylize(wct.style_transfer_stage, "16x", c, s, alpha=1.0)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()                                          # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if N > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step(content_d, style_d)
+    l0 = ops.launches()
+    with ClockSampler(local) as cs:
+        total_ms = timed(lambda: step(content_d, style_d), args.steps)
+    launches = (ops.launches() - l0)
+    clocks = cs.summary()
+    ms_per_step = total_ms / args.steps
+    mp = Hc * Wc / 1e6
+    value = mp / (ms_per_step / 1e3)
+
+    # ---- e2e: pinned host -> device -> stylize -> host, every step
+    def e2e_step():
+        c = content_h.to(dev, non_blocking=True)
+        s = style_h.to(dev, non_blocking=True)
+        o = step(c, s)
+        out_h[..., :o.shape[-2], :o.shape[-1]].copy_(o, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_val = mp / (e2e_ms / 1e3)
+    h2d = (content_h.numel() + style_h.numel()) * 4
+    d2h = out_h.numel() * 4
+
+    # ---- roofline of the dominant kernel: one extra instrumented pass (rank 0), CUDA events around every conv launch
+    roof = None
+    if rank == 0:
+        roof = conv_roofline(P, ops, wct, step, content_d, style_d, args.precision)
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline and N == 1:
+        threads = os.cpu_count() or 1
+        (bh, bw), (sh_, sw_) = CONFIGS["cfg2"]
+        mps, _ = cpu_reference_pass(bh, bw, sh_, sw_, 2, 1, threads)
+        cpu_base = {"value": round(mps, 4), "unit": "MP/s", "cores": threads, "kind": "port",
+                    "sample": "%dx%d content / %dx%d style (BASELINE configs[1]), 16x, 5 stages, 1 warm-up + 2 timed passes of the CPU oracle" % (bw, bh, sw_, sh_)}
+
+    if rank == 0:
+        flops = algorithmic_conv_flops("16x", Hc, Wc, Hs, Ws)
+        line = {
+            "metric": "megapixels/sec end-to-end WCT stylize (16x VGG, UHD)", "value": round(value, 2), "unit": "MP/s",
+            "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 tensor-core convs (fp32 accumulate, fp32 first/last layer), f64 statistics+eigensolve" if args.precision == "tf32" else "f32 convs, f64 statistics+eigensolve",
+            "data": "synthetic torch.rand images (seed 0); shipped 16x weights (tests/golden/weights_16x.npz)",
+            "config": {"workload": wl, "mode": "16x", "alpha": 1.0, "stages": 5, "parallelism": "strips%d" % N,
+                       "l2": "256 MiB flush between timed iterations", "precision": args.precision, "fold": args.fold,
+                       "algorithmic_conv_tflop_per_step": round(flops / 1e12, 4)},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": h2d * N if N > 1 else h2d,
+                    "d2h_bytes_per_step": d2h * N if N > 1 else d2h, "ms_per_step": round(e2e_ms, 3)},
+            "gpu_launches": launches,
+            "conv_tflops_whole_step": round(flops / (ms_per_step / 1e3) / 1e12, 2),
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line))
+    if N > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
+    """Wrap ops.conv3x3_p4 with CUDA events for one pass; report the shape class with the largest time share."""
+    peaks = measured_peaks()
+    rec = {}
+    orig = ops.conv3x3_p4
+    from collaborative_distillation_b200 import nets
+
+    def wrapped(x, w, b, cout, epilogue, round_tf32, engine):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = orig(x, w, b, cout, epilogue, round_tf32, engine)
+        e1.record()
+        C4, H, W, _ = x.shape
+        rec.setdefault((C4 * 4, cout, epilogue, engine), []).append((e0, e1, H, W, y.numel()))
+        return y
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.conv3x3_p4 = wrapped
+    nets.ops.conv3x3_p4 = wrapped
+    try:
+        torch.cuda.synchronize()
+        t0.record()
+        step(content_d, style_d)
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.conv3x3_p4 = orig
+        nets.ops.conv3x3_p4 = orig
+    step_ms = t0.elapsed_time(t1)
+    rows = []
+    for (cin, cout, epi, engine), evs in rec.items():
+        ms = sum(a.elapsed_time(b) for a, b, *_ in evs)
+        fl = sum(2.0 * 9 * cin * cout * H * W for _, _, H, W, _ in evs)
+        by = sum(4.0 * (cin * H * W + yn) for _, _, H, W, yn in evs)     # algorithmic: read input once, write output once
+        rows.append({"cin": cin, "cout": cout, "epi": epi, "engine": "tf32" if engine == 1 else "fp32", "launches": len(evs),
+                     "ms": ms, "flops": fl, "bytes": by})
+    rows.sort(key=lambda r: -r["ms"])
+    conv_ms = sum(r["ms"] for r in rows)
+    top = rows[0]
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0        # TF32 dense = half the bf16 rate; no direct TF32 measurement
+    fp32_peak = 148 * 128 * 2 * 1.9e9 / 1e12                # CUDA-core FFMA peak at 1.9 GHz
+    ach_tf = top["flops"] / (top["ms"] / 1e3) / 1e12
+    ach_gb = top["bytes"] / (top["ms"] / 1e3) / 1e9
+    ai = top["flops"] / top["bytes"]
+    peak_tf = tf32_peak if top["engine"] == "tf32" else fp32_peak
+    ridge = peak_tf * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    if ai < ridge:
+        roof = {"bound": "hbm", "achieved": round(ach_gb, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(ach_gb / peaks["hbm_gbs"], 4)}
+    else:
+        roof = {"bound": "tensor", "achieved": round(ach_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
+                "frac": round(ach_tf / peak_tf, 4)}
+    roof.update({
+        "traffic": None, "peaks_source": peaks["source"],
+        "kernel": "conv3x3_p4 %s engine, Cin=%d Cout=%d epi=%d (%d launches/step, %.1f%% of step time)" % (
+            top["engine"], top["cin"], top["cout"], top["epi"], top["launches"], 100 * top["ms"] / step_ms),
+        "arith_intensity_flop_per_byte": round(ai, 1), "achieved_tflops": round(ach_tf, 2), "achieved_gbs": round(ach_gb, 1),
+        "tensor_peak_note": "TF32 peak taken as bf16_tflops_sustained/2 (%s)" % peaks["source"] if top["engine"] == "tf32" else "fp32 CUDA-core peak 148 SM x 128 FMA x 1.9 GHz",
+        "conv_share_of_step": round(conv_ms / step_ms, 4),
+        "by_shape": [{"k": "%s %d->%d epi%d" % (r["engine"], r["cin"], r["cout"], r["epi"]), "ms": round(r["ms"], 3),
+                      "tflops": round(r["flops"] / (r["ms"] / 1e3) / 1e12, 2), "gbs": round(r["bytes"] / (r["ms"] / 1e3) / 1e9, 1)}
+                     for r in rows[:8]],
+    })
+    return roof
+
+
+if __name__ == "__main__":
+    main()
