@@ -154,11 +154,131 @@ __global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __rest
       }
     }
 }
+// Large maps: same tiling, fp32 FFMA partial sums over runs of <= 32 pixels, flushed into fp64 accumulators.
+// Relative error of the Gram ~ 3.5e-7 / sqrt(npix), used only for npix >= 65536.
+// GB = 32 (C <= 32): 4 pixel groups x 64 threads; GB = 64: 1 group x 256 threads; 4x4 register tile per thread,
+// operands read as float4 (two 128-bit shared loads per 16 FMA).
+template <int GB>
+__global__ void __launch_bounds__(256) centered_gram_f32_kernel(const float4* __restrict__ x, int C, int H, int W, int y0,
+                                                                int x0, int wreg, long long npix, long long pix_per_cta,
+                                                                const double* __restrict__ mean, double* __restrict__ G) {
+  constexpr int NCH4 = GB / 4;
+  constexpr int TPG = (GB / 4) * (GB / 4);   // threads per pixel group
+  constexpr int NG = 256 / TPG;              // pixel groups per CTA
+  constexpr int GPX = 32;                    // pixels per smem stage
+  __shared__ __align__(16) float sa[GPX][GB + 4];
+  __shared__ __align__(16) float sb[GPX][GB + 4];
+  const int nb = (C + GB - 1) / GB;
+  int bi = 0, bj = 0;
+  {
+    int t = blockIdx.y;
+    for (bi = 0; bi < nb; ++bi) {
+      int cnt = nb - bi;
+      if (t < cnt) { bj = bi + t; break; }
+      t -= cnt;
+    }
+  }
+  const bool diag = (bi == bj);
+  const long long pbeg = blockIdx.x * pix_per_cta;
+  const long long pend = min(npix, pbeg + pix_per_cta);
+  const int tid = threadIdx.x;
+  const int grp = tid / TPG, tl = tid % TPG;
+  const int ti = tl / (GB / 4), tj = tl % (GB / 4);
+  float acc[4][4];
+  double dacc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { acc[u][v] = 0.f; dacc[u][v] = 0.0; }
+  const long long HW = (long long)H * W;
+  const int chA = bi * GB, chB = bj * GB;
+  int run = 0;
+  for (long long p0 = pbeg; p0 < pend; p0 += GPX) {
+    __syncthreads();
+    {
+      const int pp = tid & 31;
+      const long long p = p0 + pp;
+      const bool ok = p < pend;
+      long long off = 0;
+      if (ok) {
+        int r = (int)(p / wreg), c = (int)(p - (long long)r * wreg);
+        off = (long long)(y0 + r) * W + (x0 + c);
+      }
+      for (int ch4 = tid >> 5; ch4 < NCH4; ch4 += 8) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && chA + ch4 * 4 < C) {
+          v = __ldg(x + (long long)(chA / 4 + ch4) * HW + off);
+          const double* m = mean + chA + ch4 * 4;
+          v.x -= (float)m[0]; v.y -= (float)m[1]; v.z -= (float)m[2]; v.w -= (float)m[3];
+        }
+        *reinterpret_cast<float4*>(&sa[pp][ch4 * 4]) = v;
+        if (!diag) {
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && chB + ch4 * 4 < C) {
+            v = __ldg(x + (long long)(chB / 4 + ch4) * HW + off);
+            const double* m = mean + chB + ch4 * 4;
+            v.x -= (float)m[0]; v.y -= (float)m[1]; v.z -= (float)m[2]; v.w -= (float)m[3];
+          }
+          *reinterpret_cast<float4*>(&sb[pp][ch4 * 4]) = v;
+        }
+      }
+    }
+    __syncthreads();
+    const float(*B)[GB + 4] = diag ? sa : sb;
+#pragma unroll
+    for (int k = 0; k < GPX / NG; ++k) {
+      const int pp = grp + k * NG;
+      const float4 a4 = *reinterpret_cast<const float4*>(&sa[pp][ti * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&B[pp][tj * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+    }
+    run += GPX / NG;
+    if (run >= 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { dacc[u][v] += (double)acc[u][v]; acc[u][v] = 0.f; }
+      run = 0;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const double val = dacc[u][v] + (double)acc[u][v];
+      int i = chA + ti * 4 + u, j = chB + tj * 4 + v;
+      if (i < C && j < C) {
+        atomicAdd(G + (long long)i * C + j, val);
+        if (!diag) atomicAdd(G + (long long)j * C + i, val);
+      }
+    }
+}
+
 extern "C" int wctb_centered_gram(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1,
                                   const double* mean, double* gram_out, void* stream) {
   if (!x || !mean || !gram_out || C <= 0 || (C & 3) || H <= 0 || W <= 0 || y0 < 0 || y1 > H || x0 < 0 || x1 > W ||
       y0 >= y1 || x0 >= x1)
     return WCTB_E_BADARG;
+  {
+    const long long npix_all = (long long)(y1 - y0) * (x1 - x0);
+    if (npix_all >= 65536) {
+      const int GBv = C <= 32 ? 32 : 64;
+      const int nb = (C + GBv - 1) / GBv, nblk = nb * (nb + 1) / 2;
+      int target = max(1, (4 * wctb_num_sms()) / nblk);
+      long long per = (npix_all + target - 1) / target;
+      per = ((per + 31) / 32) * 32;
+      if (per < 1024) per = 1024;
+      dim3 grid((unsigned)((npix_all + per - 1) / per), nblk);
+      cudaStream_t st = (cudaStream_t)stream;
+      if (GBv == 32) centered_gram_f32_kernel<32><<<grid, 256, 0, st>>>((const float4*)x, C, H, W, y0, x0, x1 - x0, npix_all, per, mean, gram_out);
+      else centered_gram_f32_kernel<64><<<grid, 256, 0, st>>>((const float4*)x, C, H, W, y0, x0, x1 - x0, npix_all, per, mean, gram_out);
+      WCTB_RETURN_LAUNCH();
+    }
+  }
   const int TB = C <= 16 ? 1 : (C <= 32 ? 2 : 4);
   const int GBv = 16 * TB;
   int nb = (C + GBv - 1) / GBv;
@@ -193,10 +313,11 @@ __device__ __forceinline__ void rr_pair(int round, int k, int n, int& p, int& q)
   if (p > q) { int t = p; p = q; q = t; }
 }
 
-constexpr double JACOBI_TOL = 1e-15;
+struct JacobiScales { double v[8]; };
+constexpr double JACOBI_TOL = 1e-14;
 constexpr int JACOBI_MAX_SWEEPS = 40;
 
-// rotate columns gp, gq (length n) cooperatively by `lanes` lanes (a power of two <= 32) of one warp
+// rotate columns gp, gq (length n) cooperatively by LANES lanes (a power of two <= 32) of one warp
 template <int LANES>
 __device__ __forceinline__ int jacobi_rotate(double* gp, double* gq, int n, int sub, unsigned mask, double floor2) {
   double a = 0, b = 0, c = 0;
@@ -224,63 +345,128 @@ __device__ __forceinline__ int jacobi_rotate(double* gp, double* gq, int n, int 
   return 1;
 }
 
-__global__ void __launch_bounds__(1024) jacobi_smem_kernel(const double* __restrict__ A, int C, const double* __restrict__ scale,
-                                                           int add_identity, double* __restrict__ evals,
-                                                           double* __restrict__ evecs, int* __restrict__ sweeps_out) {
-  extern __shared__ double G[];  // column-major C x C
-  __shared__ double s_fro;
-  const int prob = blockIdx.x;
-  const double sc = scale[prob];
-  const double* Ap = A + (long long)prob * C * C;
-  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
-    int r = i / C, c = i - r * C;
-    double v = Ap[i] * sc;
-    if (add_identity && r == c) v += 1.0;
-    G[c * C + r] = v;
+// Shared-memory variant (C <= 128).  One CTA per problem.
+//  * channels whose diagonal entry is exactly 0 (structurally dead ReLU channels: the whole row/column of a PSD
+//    matrix is then 0) are compacted away first: the solve runs on the k x k live block (k even, padded with one
+//    dead channel if needed); dead channels get eigenvalue 0 and a zero eigenvector.
+//  * G is column-major with a padded pitch (k+4 doubles) so concurrent column pairs spread over the banks;
+//  * each column pair is owned by LANES lanes that keep both columns in registers between the dot products
+//    and the rotation (EPL = elements per lane).
+template <int LANES, int EPL>
+__device__ __forceinline__ int jacobi_rotate_reg(double* gp, double* gq, int n, int sub, unsigned mask, double floor2) {
+  double x[EPL], y[EPL];
+  double a = 0, b = 0, c = 0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    int i = sub + e * LANES;
+    x[e] = i < n ? gp[i] : 0.0;
+    y[e] = i < n ? gq[i] : 0.0;
+    a = fma(x[e], x[e], a); b = fma(y[e], y[e], b); c = fma(x[e], y[e], c);
   }
-  if (threadIdx.x == 0) s_fro = 0;
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(mask, a, o);
+    b += __shfl_xor_sync(mask, b, o);
+    c += __shfl_xor_sync(mask, c, o);
+  }
+  if (c * c <= JACOBI_TOL * JACOBI_TOL * a * b || a <= floor2 || b <= floor2) return 0;
+  double zeta = (b - a) / (2.0 * c);
+  double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  double cs = rsqrt(1.0 + t * t);
+  double sn = cs * t;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    int i = sub + e * LANES;
+    if (i < n) {
+      gp[i] = cs * x[e] - sn * y[e];
+      gq[i] = sn * x[e] + cs * y[e];
+    }
+  }
+  return 1;
+}
+
+template <int LANES, int EPL>
+__global__ void __launch_bounds__(64 * LANES) jacobi_smem_kernel(const double* __restrict__ A, int C,
+                                                                 const JacobiScales scale, int add_identity,
+                                                                 double* __restrict__ evals, double* __restrict__ evecs,
+                                                                 int* __restrict__ sweeps_out) {
+  extern __shared__ double G[];  // column-major k x k, pitch k+4
+  __shared__ double s_fro;
+  __shared__ int s_live[128];    // compacted index -> original channel
+  __shared__ int s_k;
+  const int prob = blockIdx.x;
+  const double sc = scale.v[prob];
+  const double* Ap = A + (long long)prob * C * C;
+  if (threadIdx.x == 0) {
+    int k = 0;
+    int first_dead = -1;
+    for (int i = 0; i < C; ++i) {
+      double d = Ap[(long long)i * C + i] * sc + (add_identity ? 1.0 : 0.0);
+      if (d > 0.0) s_live[k++] = i; else if (first_dead < 0) first_dead = i;
+    }
+    if ((k & 1) && first_dead >= 0) s_live[k++] = first_dead;   // keep k even for the round-robin pairing
+    if (k < 2) { k = 0; }
+    s_k = k;
+    s_fro = 0;
+  }
+  __syncthreads();
+  const int k = s_k;
+  const int pitch = k + 4;
+  for (int i = threadIdx.x; i < k * k; i += blockDim.x) {
+    int r = i / k, c = i - r * k;
+    int ro = s_live[r], co = s_live[c];
+    double v = Ap[(long long)ro * C + co] * sc;
+    if (add_identity && ro == co) v += 1.0;
+    G[c * pitch + r] = v;
+  }
+  // outputs default: eigenvalue 0 / zero vector (dead channels, and the k == 0 case)
+  for (int i = threadIdx.x; i < C; i += blockDim.x) evals[(long long)prob * C + i] = 0.0;
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) evecs[(long long)prob * C * C + i] = 0.0;
   __syncthreads();
   {
     double f = 0;
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) f = fma(G[i], G[i], f);
+    for (int i = threadIdx.x; i < k * k; i += blockDim.x) { int r = i / k, c = i - r * k; double v = G[c * pitch + r]; f = fma(v, v, f); }
     for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(&s_fro, f);
   }
   __syncthreads();
   const double floor2 = s_fro * 1e-30;  // column norm^2 below (1e-15 ||A||_F)^2 -> numerically null
-  constexpr int LANES = 16;
   const int group = threadIdx.x / LANES, sub = threadIdx.x % LANES;
   const int ngroups = blockDim.x / LANES;
-  const unsigned mask = 0xffffu << ((threadIdx.x & 31) & ~(LANES - 1));
+  const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
   int sweep = 0;
-  for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
-    int rotated = 0;
-    for (int round = 0; round < C - 1; ++round) {
-      for (int k = group; k < C / 2; k += ngroups) {
-        int p, q;
-        rr_pair(round, k, C, p, q);
-        rotated |= jacobi_rotate<LANES>(G + p * C, G + q * C, C, sub, mask, floor2);
+  if (k >= 2) {
+    for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+      int rotated = 0;
+      for (int round = 0; round < k - 1; ++round) {
+        for (int pi = group; pi < k / 2; pi += ngroups) {
+          int p, q;
+          rr_pair(round, pi, k, p, q);
+          rotated |= jacobi_rotate_reg<LANES, EPL>(G + p * pitch, G + q * pitch, k, sub, mask, floor2);
+        }
+        __syncthreads();
       }
-      __syncthreads();
+      if (!__syncthreads_or(rotated)) { ++sweep; break; }
     }
-    if (!__syncthreads_or(rotated)) { ++sweep; break; }
   }
-  // eigenvalues = column norms, eigenvectors = normalised columns
-  for (int k = group; k < C; k += ngroups) {
+  // eigenvalues = column norms, eigenvectors = normalised columns, scattered back to original channel indices
+  for (int j = group; j < k; j += ngroups) {
     double a = 0;
-    for (int i = sub; i < C; i += LANES) a = fma(G[k * C + i], G[k * C + i], a);
+    for (int i = sub; i < k; i += LANES) a = fma(G[j * pitch + i], G[j * pitch + i], a);
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
     double sig = sqrt(a);
     double inv = sig > 0 ? 1.0 / sig : 0.0;
-    if (sub == 0) evals[(long long)prob * C + k] = sig;
-    for (int i = sub; i < C; i += LANES) evecs[(long long)prob * C * C + (long long)k * C + i] = G[k * C + i] * inv;
+    const int jo = s_live[j];
+    if (sub == 0) evals[(long long)prob * C + jo] = sig;
+    for (int i = sub; i < k; i += LANES)
+      evecs[(long long)prob * C * C + (long long)jo * C + s_live[i]] = G[j * pitch + i] * inv;
   }
   if (sweeps_out && threadIdx.x == 0) sweeps_out[prob] = sweep;
 }
 
 __global__ void __launch_bounds__(256) jacobi_global_kernel(const double* __restrict__ A, int nprob, int C,
-                                                            const double* __restrict__ scale, int add_identity,
+                                                            const JacobiScales scale, int add_identity,
                                                             double* __restrict__ evals, double* __restrict__ evecs,
                                                             double* __restrict__ work, int* __restrict__ flags,
                                                             int* __restrict__ sweeps_out) {
@@ -297,7 +483,7 @@ __global__ void __launch_bounds__(256) jacobi_global_kernel(const double* __rest
     int prob = (int)(i / CC);
     long long e = i - prob * CC;
     int r = (int)(e / C), c = (int)(e - (long long)r * C);
-    double v = A[i] * scale[prob];
+    double v = A[i] * scale.v[prob];
     if (add_identity && r == c) v += 1.0;
     work[prob * CC + (long long)c * C + r] = v;
     double f = v * v;  // nprob*C*C and the stride are multiples of 32: a warp stays inside one problem
@@ -345,15 +531,24 @@ __global__ void __launch_bounds__(256) jacobi_global_kernel(const double* __rest
   if (sweeps_out && gtid < nprob) sweeps_out[gtid] = sweep;
 }
 
-extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale, int add_identity, double* evals,
+extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale_host, int add_identity, double* evals,
                                 double* evecs, double* work, int* sweeps_out, void* stream) {
-  if (!a || !scale || !evals || !evecs || !work || nprob <= 0 || C < 2 || (C & 1)) return WCTB_E_BADARG;
+  if (!a || !scale_host || !evals || !evecs || !work || nprob <= 0 || nprob > 8 || C < 2 || (C & 1)) return WCTB_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  JacobiScales scale;
+  for (int i = 0; i < 8; ++i) scale.v[i] = i < nprob ? scale_host[i] : 1.0;
   if (C <= 128) {
-    size_t smem = (size_t)C * C * sizeof(double);
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = C >= 128 ? 1024 : (C >= 64 ? 512 : 256);
-    jacobi_smem_kernel<<<nprob, threads, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    size_t smem = (size_t)C * (C + 4) * sizeof(double);
+    // lanes per column pair / elements per lane: (8,16) covers k <= 128, (4,16) k <= 64, (4,8) k <= 32
+    if (C > 64) {
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_smem_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jacobi_smem_kernel<8, 16><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    } else if (C > 32) {
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_smem_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jacobi_smem_kernel<4, 16><<<nprob, 256, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    } else {
+      jacobi_smem_kernel<4, 8><<<nprob, 256, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    }
     WCTB_RETURN_LAUNCH();
   }
   // cooperative variant: work must hold nprob*C*C + nprob doubles + 2 ints (caller gives nprob*C*C + 16 doubles)

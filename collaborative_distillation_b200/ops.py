@@ -119,26 +119,31 @@ def channel_sum(x: torch.Tensor, region=None) -> torch.Tensor:
     return out
 
 
-def centered_gram(x: torch.Tensor, mean: torch.Tensor, region=None) -> torch.Tensor:
-    """P4 map, fp64 mean [C] -> fp64 [C,C] sum (x-mean)(x-mean)^T over the region"""
+def centered_gram(x: torch.Tensor, mean: torch.Tensor, region=None, out: torch.Tensor = None) -> torch.Tensor:
+    """P4 map, fp64 mean [C] -> fp64 [C,C] sum (x-mean)(x-mean)^T over the region (accumulated into `out` if given)"""
     C4, H, W, _ = x.shape
     C = C4 * 4
     y0, y1, x0, x1 = region if region is not None else (0, H, 0, W)
-    out = torch.zeros(C, C, device=x.device, dtype=torch.float64)
+    if out is None:
+        out = torch.zeros(C, C, device=x.device, dtype=torch.float64)
     check(_lib.load().wctb_centered_gram(_need(x), C, H, W, y0, y1, x0, x1, _need(mean, torch.float64),
                                          _need(out, torch.float64), _stream()), "centered_gram")
     _count("centered_gram")
     return out
 
 
-def eigh_jacobi(a: torch.Tensor, scale: torch.Tensor, add_identity: bool = False, return_sweeps: bool = False):
-    """a: fp64 [nprob,C,C] symmetric PSD; scale fp64 [nprob].  -> evals [nprob,C], evecs [nprob,C(k),C(i)]"""
+def eigh_jacobi(a: torch.Tensor, scale, add_identity: bool = False, return_sweeps: bool = False):
+    """a: fp64 [nprob,C,C] symmetric PSD; scale: nprob host floats.  -> evals [nprob,C], evecs [nprob,C(k),C(i)]"""
+    import ctypes
     nprob, C, _ = a.shape
+    scale = [float(v) for v in (scale.tolist() if torch.is_tensor(scale) else scale)]
+    assert len(scale) == nprob
+    scale_host = (ctypes.c_double * nprob)(*scale)
     evals = torch.empty(nprob, C, device=a.device, dtype=torch.float64)
     evecs = torch.empty(nprob, C, C, device=a.device, dtype=torch.float64)
     work = torch.empty(nprob * C * C + 16, device=a.device, dtype=torch.float64)
     sweeps = torch.zeros(nprob, device=a.device, dtype=torch.int32)
-    check(_lib.load().wctb_eigh_jacobi(_need(a, torch.float64), nprob, C, _need(scale, torch.float64), int(add_identity),
+    check(_lib.load().wctb_eigh_jacobi(_need(a, torch.float64), nprob, C, scale_host, int(add_identity),
                                        _need(evals, torch.float64), _need(evecs, torch.float64),
                                        _need(work, torch.float64), _need(sweeps, torch.int32), _stream()), "eigh_jacobi")
     _count("eigh")

@@ -48,7 +48,7 @@ def strip_cuts(W: int, world: int):
 
 
 class StripGroup:
-    """Strip-parallel driver.  `stage_fn(stage, content_ext, style_ext, alpha, c_region, s_region) -> image_ext`
+    """Strip-parallel driver.  `stage_fn(stage, content_ext, style_ext, alpha, c_region, s_region, c_count, s_count) -> image_ext`
     is `WCT.style_transfer_stage` in production (with `wct.dist = self`), or a CPU restatement in the gloo tests."""
 
     def __init__(self, group=None):
@@ -61,10 +61,10 @@ class StripGroup:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
-    def allreduce_count(self, n: float, device) -> float:
-        t = torch.tensor([n], dtype=torch.float64, device=device)
+    def total_width(self, own_w: int, device) -> int:
+        t = torch.tensor([own_w], dtype=torch.int64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        return float(t.item())
+        return int(t.item())
 
     # ---- halo exchange
     def exchange(self, own: torch.Tensor, halo: int):
@@ -99,6 +99,10 @@ class StripGroup:
         hmax = max(stage_halo(mode, s) for s in stages)
         style_ext, s_lh, s_rh = self.exchange(style_own, hmax)
         img = content_own
+        # whole-image widths (one tiny all-reduce per call): statistics divide by GLOBAL pixel counts
+        Wc_tot = self.total_width(content_own.shape[-1], content_own.device)
+        Ws_tot = self.total_width(style_own.shape[-1], style_own.device)
+        Hs = style_own.shape[-2]
         for _ in range(num_run):
             for s in stages:
                 h = stage_halo(mode, s)
@@ -108,7 +112,11 @@ class StripGroup:
                 st = style_ext[..., (s_lh - min(s_lh, h)):style_ext.shape[-1] - (s_rh - min(s_rh, h))]
                 sl, sr = min(s_lh, h), min(s_rh, h)
                 s_region = (0, st.shape[-2], sl, st.shape[-1] - sr)
-                out = stage_fn(s, ext, st.contiguous(), alpha, c_region, s_region)
+                sh = s - 1
+                c_count = (H >> sh) * (Wc_tot >> sh)
+                s_count = (Hs >> sh) * (Ws_tot >> sh)
+                out = stage_fn(s, ext, st.contiguous(), alpha, c_region, s_region, c_count, s_count)
+                Wc_tot = (Wc_tot >> sh) << sh          # floor-pool drops trailing columns of the whole image
                 # floor-pool may have dropped trailing rows/cols (global right/bottom edge only)
                 x1 = min(We - rh, out.shape[-1])
                 img = out[..., lh:x1].contiguous()

@@ -40,34 +40,35 @@ class WCT(nn.Module):
         self.fold_into_decoder = False
 
     # ------------------------------------------------------------------ statistics -> (M, b, mean_c)
-    def _moments(self, x_p4, region=None):
-        """-> (n, mean fp64 [C], gram fp64 [C,C]) over the region; all-reduced over ranks when sharded"""
-        C4, H, W, _ = x_p4.shape
-        if region is None:
-            region = (0, H, 0, W)
-        n = float((region[1] - region[0]) * (region[3] - region[2]))
+    def _moments(self, x_p4, region, count, gram_out):
+        """mean fp64 [C] and centred Gram (into gram_out [C,C] fp64, zeroed by the caller) over the region;
+        all-reduced over ranks when sharded.  `count` = number of feature pixels of the WHOLE image (host value)."""
         s = ops.channel_sum(x_p4, region)
         if self.dist is not None:
-            n = self.dist.allreduce_count(n, x_p4.device)
             self.dist.allreduce_(s)
-        mean = s / n
-        g = ops.centered_gram(x_p4, mean, region)
-        if self.dist is not None:
-            self.dist.allreduce_(g)
-        return n, mean, g
+        mean = s / count
+        ops.centered_gram(x_p4, mean, region, out=gram_out)
+        return mean
 
-    def _wct_params(self, c_p4, s_p4, alpha, c_region=None, s_region=None):
-        nc, c_mean, c_g = self._moments(c_p4, c_region)
-        ns, s_mean, s_g = self._moments(s_p4, s_region)
-        a = torch.stack([c_g, s_g])
-        scale = torch.tensor([1.0 / (nc - 1.0), 1.0 / (ns - 1.0)], device=a.device, dtype=torch.float64)  # util_wct.py:70,96
-        # --numpy variant adds I to BOTH problems inside one launch only if requested for content; style must not
-        if getattr(self.args, "numpy", False):                                          # util_wct.py:143
-            ce, cv = ops.eigh_jacobi(a[0:1].contiguous(), scale[0:1].contiguous(), add_identity=True)
-            se, sv = ops.eigh_jacobi(a[1:2].contiguous(), scale[1:2].contiguous(), add_identity=False)
+    def _wct_params(self, c_p4, s_p4, alpha, c_region=None, s_region=None, c_count=None, s_count=None):
+        C = c_p4.shape[0] * 4
+        full = lambda t: (0, t.shape[1], 0, t.shape[2])
+        c_region = c_region or full(c_p4)
+        s_region = s_region or full(s_p4)
+        nc = float(c_count if c_count is not None else (c_region[1] - c_region[0]) * (c_region[3] - c_region[2]))
+        ns = float(s_count if s_count is not None else (s_region[1] - s_region[0]) * (s_region[3] - s_region[2]))
+        grams = torch.zeros(2, C, C, device=c_p4.device, dtype=torch.float64)
+        c_mean = self._moments(c_p4, c_region, nc, grams[0])
+        s_mean = self._moments(s_p4, s_region, ns, grams[1])
+        if self.dist is not None:
+            self.dist.allreduce_(grams)
+        scale = [1.0 / (nc - 1.0), 1.0 / (ns - 1.0)]                                   # util_wct.py:70,96
+        if getattr(self.args, "numpy", False):                                          # +I on the content covariance only (util_wct.py:143)
+            ce, cv = ops.eigh_jacobi(grams[0:1], scale[0:1], add_identity=True)
+            se, sv = ops.eigh_jacobi(grams[1:2], scale[1:2], add_identity=False)
             evals, evecs = torch.cat([ce, se]), torch.cat([cv, sv])
         else:
-            evals, evecs = ops.eigh_jacobi(a, scale)
+            evals, evecs = ops.eigh_jacobi(grams, scale)
         return ops.wct_matrix(evals[0], evecs[0], c_mean, evals[1], evecs[1], s_mean, self.tau, alpha)
 
     # ------------------------------------------------------------------ reference API
@@ -96,15 +97,17 @@ class WCT(nn.Module):
 
     # ------------------------------------------------------------------ fused device-resident path
     @torch.no_grad()
-    def style_transfer_stage(self, stage, content, style, alpha=1.0, c_region=None, s_region=None):
+    def style_transfer_stage(self, stage, content, style, alpha=1.0, c_region=None, s_region=None, c_count=None,
+                             s_count=None):
         """One styleTransfer(wct.eK, wct.dK, cImg, sImg, csF) of WCT.py:98-106, entirely on the device.
-        content/style [1,3,H,W] CUDA; regions are stage-1-resolution own strips (y0,y1,x0,x1) when sharded."""
+        content/style [1,3,H,W] CUDA; when sharded, regions are this rank's own strip (y0,y1,x0,x1) in image
+        pixels and counts are the WHOLE image's number of feature pixels at this stage."""
         enc, dec = getattr(self, "e%d" % stage), getattr(self, "d%d" % stage)
         sh = stage - 1
         s4 = enc.forward_p4(style)
         c4 = enc.forward_p4(content)
         reg = lambda r: None if r is None else tuple(v >> sh for v in r)
-        m, b, mc = self._wct_params(c4, s4, float(alpha), reg(c_region), reg(s_region))
+        m, b, mc = self._wct_params(c4, s4, float(alpha), reg(c_region), reg(s_region), c_count, s_count)
         del s4
         if self.fold_into_decoder:
             L0 = getattr(dec, dec.layers[0]["name"])

@@ -104,12 +104,12 @@ int wctb_centered_gram(const float* x_p4, int C, int H, int W, int y0, int y1, i
 /* ---- symmetric eigendecomposition (one-sided Jacobi, fp64) ------------------------------
  * replaces: torch.svd(contentConv, some=False) / torch.svd(styleConv) (util_wct.py:74,100);
  * only (E, V) are consumed there and the matrices are symmetric PSD.
- * a: nprob matrices [C][C] fp64 (row-major symmetric), each scaled by `scale` and, if
+ * a: nprob (<= 8) matrices [C][C] fp64 (row-major symmetric), each scaled by scale_host[prob] (HOST array) and, if
  * add_identity, + I (the `--numpy` variant, util_wct.py:143) before the solve.
  * Outputs per problem: evals[C] (>= 0, unsorted), evecs[C][C] column k = unit eigenvector k
  * stored as evecs[k*C + i] (zero vector when the eigenvalue is exactly 0).
  * work: nprob*C*C + 16 doubles of scratch.  sweeps_out (optional, may be NULL): int[nprob].    */
-int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale, int add_identity,
+int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale_host, int add_identity,
                      double* evals, double* evecs, double* work, int* sweeps_out, void* stream);
 
 /* ---- whitening / colouring matrix ----------------------------------------------------

@@ -83,19 +83,24 @@ def test_conv_last_fp32(H, W, cin):
 
 # ------------------------------------------------------------------ statistics
 @pytest.mark.parametrize("C,H,W,region", [(24, 31, 47, None), (128, 9, 11, None), (64, 40, 50, (3, 37, 8, 50)),
-                                          (256, 6, 7, None), (16, 5, 300, (0, 5, 16, 272))])
+                                          (256, 6, 7, None), (16, 5, 300, (0, 5, 16, 272)),
+                                          (24, 300, 310, None), (128, 260, 270, (4, 260, 0, 264)), (32, 257, 300, None)])
 def test_moments_match_fp64(C, H, W, region):
     x = (torch.randn(C, H, W, generator=torch.Generator().manual_seed(4)) * 3 + 1.5).relu()
     p4 = ops.nchw_to_p4(x.to(DEV))
     y0, y1, x0, x1 = region or (0, H, 0, W)
     xr = x[:, y0:y1, x0:x1].double().reshape(C, -1)
     s = ops.channel_sum(p4, region).cpu()
-    np.testing.assert_allclose(s.numpy(), xr.sum(1).numpy(), rtol=1e-12, atol=1e-9)
+    # fp32 partial sums of <= 64 values per thread, then fp64: ~1e-10 relative on large maps
+    np.testing.assert_allclose(s.numpy(), xr.sum(1).numpy(), rtol=2e-9, atol=1e-9)
     mean = xr.mean(1)
     g = ops.centered_gram(p4, mean.to(DEV), region).cpu()
     xc = xr - mean[:, None]
     ref = xc @ xc.t()
-    assert (g - ref).abs().max().item() <= 1e-11 * ref.abs().max().item()      # fp64 accumulation
+    npix = (y1 - y0) * (x1 - x0)
+    # < 65536 px: fp64 DFMA accumulation.  >= 65536 px: fp32 FFMA runs of 32 px flushed into fp64 (3.5e-7/sqrt(n))
+    tol = 1e-11 if npix < 65536 else 2e-8
+    assert (g - ref).abs().max().item() <= tol * ref.abs().max().item()
     assert (g - g.t()).abs().max().item() <= 1e-13 * ref.abs().max().item()   # fp64 atomics: order-dependent last bits
 
 
@@ -107,7 +112,7 @@ def test_eigh_jacobi_vs_lapack(C, rank):
     A = B @ B.t()
     A2 = torch.stack([A, 0.5 * A + 0.1 * torch.eye(C, dtype=torch.float64)])
     scale = torch.tensor([1.0, 2.0], dtype=torch.float64)
-    ev, evec, sweeps = ops.eigh_jacobi(A2.to(DEV), scale.to(DEV), return_sweeps=True)
+    ev, evec, sweeps = ops.eigh_jacobi(A2.to(DEV), scale.tolist(), return_sweeps=True)
     ev, evec = ev.cpu(), evec.cpu()
     assert int(sweeps.max()) < 40, "Jacobi did not converge"
     for p in range(2):

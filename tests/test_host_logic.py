@@ -87,3 +87,36 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES) | {"wctb_error_string"}
     assert _lib.load().wctb_abi_version() == 1
     assert _lib.load().wctb_error_string(-2) == b"unsupported configuration"
+
+
+def test_cli_flag_surface_matches_reference():
+    """WCT.py:15-34 flag names/defaults + mode->weight path tables (:36-70)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("wct_cli", os.path.join(ROOT, "PytorchWCT", "WCT.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    a = cli.parse(["--mode", "16x", "--UHD", "--alpha", "0.6", "--num_run", "2", "--debug"])
+    assert a.mode == "16x" and a.UHD and a.alpha == 0.6 and a.num_run == 2 and a.debug and not a.numpy and not a.synthesis
+    assert a.e5 == "../trained_models/wct_se_16x_new/5SE.pth" and a.d1 == "../trained_models/wct_se_16x_new_sd/1SD.pth"
+    assert (a.contentPath, a.stylePath, a.UHD_contentPath, a.UHD_stylePath, a.outf) == (
+        "content", "style", "content/UHD_content", "style/UHD_style", "stylized_results")
+    assert a.content_size == 0 and a.style_size == 0 and a.picked_content_mark == "." and a.texturePath == "style/texture"
+    d = cli.parse([])
+    assert d.mode is None and d.e3.endswith("original_wct_models/vgg_normalised_conv3_1.t7") and d.alpha == 1
+    k = cli.parse(["--mode", "16x_kd2sd"])
+    assert k.d4 == "../trained_models/wct_se_16x_new_sd_kd2sd/4SD.pth"
+
+
+def test_reference_import_paths():
+    import importlib
+    sys_path = os.path.join(ROOT, "PytorchWCT")
+    import sys
+    sys.path.insert(0, sys_path)
+    try:
+        m = importlib.import_module("model.model_cd")
+        assert hasattr(m, "SmallEncoder5_16x_aux") and hasattr(m, "SmallDecoder1_16x")
+        assert hasattr(importlib.import_module("model.model_original"), "Decoder4")
+        assert hasattr(importlib.import_module("model.model_kd2sd"), "SmallDecoder3_16x_aux")
+        assert importlib.import_module("util_wct").WCT is P.WCT
+    finally:
+        sys.path.remove(sys_path)

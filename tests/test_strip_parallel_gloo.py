@@ -30,28 +30,28 @@ def test_halos_and_cuts():
 
 
 def cpu_stage_fn(weights, mode, group):
-    def moments(F, region):
+    def moments(F, region, count):
         y0, y1, x0, x1 = region
         x = F[:, y0:y1, x0:x1].double().reshape(F.shape[0], -1)
-        n = torch.tensor([float(x.shape[1])], dtype=torch.float64)
         s = x.sum(1)
         if group is not None:
-            group.allreduce_(n), group.allreduce_(s)
+            group.allreduce_(s)
+        n = float(count if count is not None else x.shape[1])
         mean = s / n
         xc = x - mean[:, None]
         g = xc @ xc.t()
         if group is not None:
             group.allreduce_(g)
-        return n.item(), mean, g
+        return n, mean, g
 
-    def fn(stage, content, style, alpha, c_region, s_region):
+    def fn(stage, content, style, alpha, c_region, s_region, c_count=None, s_count=None):
         sh = stage - 1
         with torch.no_grad():
             cF = O.encoder_forward(weights["e%d" % stage], mode, stage, content).squeeze(0)
             sF = O.encoder_forward(weights["e%d" % stage], mode, stage, style).squeeze(0)
             reg = lambda r: tuple(v >> sh for v in r)
-            nc, cm, cg = moments(cF, reg(c_region))
-            ns, sm, sg = moments(sF, reg(s_region))
+            nc, cm, cg = moments(cF, reg(c_region), c_count)
+            ns, sm, sg = moments(sF, reg(s_region), s_count)
             ce, cv = torch.linalg.eigh(cg / (nc - 1))
             se, sv = torch.linalg.eigh(sg / (ns - 1))
             kc, ks = ce > 1e-7 * ce.max(), se > 1e-7 * se.max()
