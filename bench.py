@@ -261,9 +261,8 @@ def main():
     d2h = out_h.numel() * 4
 
     # ---- roofline of the dominant kernel: one extra instrumented pass (rank 0), CUDA events around every conv launch
-    roof = None
-    if rank == 0:
-        roof = conv_roofline(P, ops, wct, step, content_d, style_d, args.precision)
+    # (the pass contains collectives when sharded, so every rank runs it; rank 0 reports)
+    roof = conv_roofline(P, ops, wct, step, content_d, style_d, args.precision)
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline and N == 1:

@@ -29,6 +29,10 @@ SIGNATURES = {
     "wctb_conv3x3_first": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "wctb_conv3x3_p4": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "wctb_conv3x3_last": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "wctb_conv_head_supported": [_i, _i],
+    "wctb_conv_tail_supported": [_i, _i],
+    "wctb_conv_tail": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "wctb_conv_head": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "wctb_channel_sum": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "wctb_centered_gram": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "wctb_eigh_jacobi": [_p, _i, _i, ctypes.POINTER(ctypes.c_double), _i, _p, _p, _p, _p, _p],

@@ -19,71 +19,10 @@
 // source address; completion on an mbarrier), warp 1 = TMEM allocator + single-thread MMA issuer
 // (tcgen05.mma.cta_group::1.kind::tf32, tcgen05.commit frees the stage), warps 2..5 = epilogue
 // (tcgen05.ld -> bias/ReLU/TF32-round -> pool|up -> coalesced float4 stores).
-#include "common.cuh"
+#include "umma.cuh"
 
 namespace {
-
-constexpr int PW = 64;   // smem row pitch (pixels)
-constexpr int TW = 62;   // valid output columns per tile
-constexpr int KG = 8;    // channels per pipeline stage (one K=8 MMA per tap)
-
-// ---------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done, addr = smem_u32(bar);
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(NCOLS) : "memory");
-}
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-//   [0,14) start>>4 | [16,30) LBO>>4 (K-direction core-matrix stride) | [32,46) SBO>>4 (M/N-direction 8-row stride)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
+using namespace wctb_umma;
 
 // ---------------------------------------------------------------------------------- geometry
 template <int N> struct Cfg {
@@ -109,6 +48,123 @@ struct ConvArgs {
   float4* y;
   int H, W, Cin, Cout, round_tf32;
 };
+
+// single-thread MMA issue loop: nkg pipeline stages x NB accumulator blocks x 9 taps (one K=8 MMA each)
+template <int N, int NSTAGE, int STAGE_BYTES, int IN_BYTES, int P, int NB>
+__device__ __forceinline__ void mma_issue_loop(uint8_t* stages, uint64_t* full, uint64_t* empty, uint64_t* accum_full,
+                                               uint32_t tmem_base, int nkg) {
+  constexpr uint32_t idesc = umma_idesc_tf32(N);
+  for (int kg = 0; kg < nkg; ++kg) {
+    const int slot = kg % NSTAGE;
+    const uint32_t ph = (kg / NSTAGE) & 1;
+    mbar_wait(full + slot, ph);
+    tc_fence_after();
+    const uint32_t a_base = smem_u32(stages + slot * STAGE_BYTES);
+    const uint32_t w_base = a_base + IN_BYTES;
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap - dy * 3;
+        const uint64_t ad = umma_desc(a_base + (uint32_t)(128 * b + dy * PW + dx) * 16u, P * 16u, 128u);
+        const uint64_t bd = umma_desc(w_base + (uint32_t)tap * 2u * N * 16u, N * 16u, 128u);
+        umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, (kg > 0 || tap > 0) ? 1u : 0u);
+      }
+    }
+    tc_commit(empty + slot);      // frees the smem stage when these MMAs have read it
+  }
+  tc_commit(accum_full);          // accumulators complete
+}
+
+// epilogue for the 4 warps owning the TMEM lane quarters: TMEM -> bias/ReLU/TF32-round -> (pool | up) -> P4 stores
+template <int N, int NB, int EPI>
+__device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint64_t* accum_full, uint32_t tmem_base, float* poolbuf,
+                                              int warp, int lane, int x0, int y0, int nblk) {
+  const int H = a.H, W = a.W;
+  const long long HW = (long long)H * W;
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const float* bias = a.bias + nblk * N;
+    const int cplane0 = nblk * (N / 4);
+    if (EPI == WCTB_EPI_POOL2) {
+      const int Ho = H >> 1, Wo = W >> 1;
+      const long long HWo = (long long)Ho * Wo;
+      int it = 0;
+      for (int b = 0; b < NB; ++b) {
+        // block b = tile rows 2b (lanes 0..63) and 2b+1 (lanes 64..127)
+        const int cpos = (q & 1) * 32 + lane;                    // column within the 64-pitch row
+        const int oy = (y0 >> 1) + b, ox = (x0 + cpos) >> 1;
+        const bool ok = (cpos < TW) && oy < Ho && ox < Wo && ((lane & 1) == 0);
+        for (int g = 0; g < N / 16; ++g, ++it) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N + 16 * g), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = wctb_relu(v[i] + __ldg(bias + 16 * g + i));
+            v[i] = a.round_tf32 ? wctb_tf32(t) : t;
+          }
+          float* buf = poolbuf + (it & 1) * (64 * 20);
+          if (q >= 2) {
+            float4* d = reinterpret_cast<float4*>(buf + cpos * 20);
+            d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+            d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (q < 2) {
+            const float4* s = reinterpret_cast<const float4*>(buf + cpos * 20);
+            float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+            float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float m = fmaxf(v[i], o[i]);
+              v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            }
+            if (ok) {
+              const long long off = (long long)oy * Wo + ox;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                a.y[(long long)(cplane0 + 4 * g + j) * HWo + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
+      }
+    } else {
+      for (int b = 0; b < NB; ++b) {
+        const int p = 128 * b + 32 * q + lane;
+        const int r = p >> 6, c = p & 63;
+        const int gy = y0 + r, gx = x0 + c;
+        const bool ok = (c < TW) && gy < H && gx < W;
+        for (int g = 0; g < N / 16; ++g) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N + 16 * g), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = wctb_relu(v[i] + __ldg(bias + 16 * g + i));
+            v[i] = a.round_tf32 ? wctb_tf32(t) : t;
+          }
+          if (ok) {
+            if (EPI == WCTB_EPI_NONE) {
+              const long long off = (long long)gy * W + gx;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                a.y[(long long)(cplane0 + 4 * g + j) * HW + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {  // nearest x2
+              const int Wo = 2 * W;
+              const long long HWo = 4 * HW;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                float4* pl = a.y + (long long)(cplane0 + 4 * g + j) * HWo;
+                const long long off = (long long)(2 * gy) * Wo + 2 * gx;
+                pl[off] = o; pl[off + 1] = o; pl[off + Wo] = o; pl[off + Wo + 1] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+}
 
 template <int N, int EPI>
 __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const ConvArgs a) {
@@ -173,114 +229,12 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const ConvArgs a) {
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(N);
-      for (int kg = 0; kg < nkg; ++kg) {
-        const int slot = kg % C::NSTAGE;
-        const uint32_t ph = (kg / C::NSTAGE) & 1;
-        mbar_wait(full + slot, ph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(stages + slot * C::STAGE_BYTES);
-        const uint32_t w_base = a_base + C::IN_BYTES;
-#pragma unroll 1
-        for (int b = 0; b < C::NB; ++b) {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint64_t ad = umma_desc(a_base + (uint32_t)(128 * b + dy * PW + dx) * 16u, C::P * 16u, 128u);
-            const uint64_t bd = umma_desc(w_base + (uint32_t)tap * 2u * N * 16u, N * 16u, 128u);
-            umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, (kg > 0 || tap > 0) ? 1u : 0u);
-          }
-        }
-        tc_commit(empty + slot);      // frees the smem stage when these MMAs have read it
-      }
-      tc_commit(accum_full);          // accumulators complete
-    }
+    if (lane == 0)
+      mma_issue_loop<N, C::NSTAGE, C::STAGE_BYTES, C::IN_BYTES, C::P, C::NB>(stages, full, empty, accum_full, tmem_base, nkg);
     __syncwarp();
   } else {
     // =========================== epilogue ===========================
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    const float* bias = a.bias + nblk * N;
-    const int cplane0 = nblk * (N / 4);
-    if (EPI == WCTB_EPI_POOL2) {
-      const int Ho = H >> 1, Wo = W >> 1;
-      const long long HWo = (long long)Ho * Wo;
-      int it = 0;
-      for (int b = 0; b < C::NB; ++b) {
-        // block b = tile rows 2b (lanes 0..63) and 2b+1 (lanes 64..127)
-        const int cpos = (q & 1) * 32 + lane;                    // column within the 64-pitch row
-        const int oy = (y0 >> 1) + b, ox = (x0 + cpos) >> 1;
-        const bool ok = (cpos < TW) && oy < Ho && ox < Wo && ((lane & 1) == 0);
-        for (int g = 0; g < N / 16; ++g, ++it) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N + 16 * g), v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = wctb_relu(v[i] + __ldg(bias + 16 * g + i));
-            v[i] = a.round_tf32 ? wctb_tf32(t) : t;
-          }
-          float* buf = poolbuf + (it & 1) * (64 * 20);
-          if (q >= 2) {
-            float4* d = reinterpret_cast<float4*>(buf + cpos * 20);
-            d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
-            d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (q < 2) {
-            const float4* s = reinterpret_cast<const float4*>(buf + cpos * 20);
-            float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
-            float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float m = fmaxf(v[i], o[i]);
-              v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            }
-            if (ok) {
-              const long long off = (long long)oy * Wo + ox;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                a.y[(long long)(cplane0 + 4 * g + j) * HWo + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-          }
-        }
-      }
-    } else {
-      for (int b = 0; b < C::NB; ++b) {
-        const int p = 128 * b + 32 * q + lane;
-        const int r = p >> 6, c = p & 63;
-        const int gy = y0 + r, gx = x0 + c;
-        const bool ok = (c < TW) && gy < H && gx < W;
-        for (int g = 0; g < N / 16; ++g) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N + 16 * g), v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = wctb_relu(v[i] + __ldg(bias + 16 * g + i));
-            v[i] = a.round_tf32 ? wctb_tf32(t) : t;
-          }
-          if (ok) {
-            if (EPI == WCTB_EPI_NONE) {
-              const long long off = (long long)gy * W + gx;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                a.y[(long long)(cplane0 + 4 * g + j) * HW + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {  // nearest x2
-              const int Wo = 2 * W;
-              const long long HWo = 4 * HW;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                float4* pl = a.y + (long long)(cplane0 + 4 * g + j) * HWo;
-                const long long off = (long long)(2 * gy) * Wo + 2 * gx;
-                pl[off] = o; pl[off + 1] = o; pl[off + Wo] = o; pl[off + Wo + 1] = o;
-              }
-            }
-          }
-        }
-      }
-    }
+    conv_epilogue<N, C::NB, EPI>(a, accum_full, tmem_base, poolbuf, warp, lane, x0, y0, nblk);
   }
   tc_fence_before();
   __syncthreads();
@@ -312,6 +266,371 @@ inline int pick_n(int Cout) {
   if (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256) return Cout;
   if (Cout > 256 && Cout % 256 == 0) return 256;
   return 0;
+}
+
+// ---------------------------------------------------------------------------------- fused encoder head
+//   y = [pool2]( ReLU(conv12( reflect_pad( ReLU(conv11( reflect_pad(img) )) ) )) )     img NCHW 3ch -> y P4 N ch
+// conv11 (K = 27, not an MMA shape) is computed with FFMA by four producer warps straight into the tensor-core
+// operand tile in shared memory (same [chunk][row][64] float4 layout the bulk-copy producer fills), 8 channels
+// (= one pipeline stage) at a time; conv12 runs on tcgen05 from that tile.  The C1-channel full-resolution
+// activation (64 B/px for the 16x net) never goes to HBM.  conv0 is folded into conv11 by the host.
+// Reflection of the INTERMEDIATE: a halo position outside the image must hold conv11 evaluated at the mirrored
+// position, so the producer evaluates conv11 at (reflect(y), reflect(x)).
+struct HeadArgs {
+  const float* img;   // [3][H][W]
+  const float* w11;   // [27][C1]  (conv0 folded), fp32
+  const float* b11;   // [C1]
+  ConvArgs c;         // conv12: x unused, w packed tf32, bias, y, H, W, Cin = C1, Cout = N
+};
+template <int C1, int N> struct HeadCfg {
+  using C = Cfg<N>;
+  static constexpr int IMG_ROWS = C::TH + 4, IMG_PITCH = 68;
+  static constexpr int IMG_BYTES = 3 * IMG_ROWS * IMG_PITCH * 4;
+  static constexpr int W11_BYTES = (27 * C1 + C1) * 4;
+  static constexpr int NSTAGE = 2;
+  static constexpr int SMEM_BYTES = NSTAGE * C::STAGE_BYTES + IMG_BYTES + W11_BYTES + C::POOL_BYTES + 256 + 128;
+  static constexpr int MIN_CTAS = (SMEM_BYTES <= 113 * 1024 && C::TMEM_COLS <= 256) ? 2 : 1;
+};
+
+template <int C1, int N, int EPI>
+__global__ void __launch_bounds__(320, HeadCfg<C1, N>::MIN_CTAS) conv_head_kernel(const HeadArgs h) {
+  using C = Cfg<N>;
+  using HC = HeadCfg<C1, N>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* stages = smem;
+  float* img_s = reinterpret_cast<float*>(smem + HC::NSTAGE * C::STAGE_BYTES);
+  float* w11_s = reinterpret_cast<float*>(smem + HC::NSTAGE * C::STAGE_BYTES + HC::IMG_BYTES);
+  float* b11_s = w11_s + 27 * C1;
+  float* poolbuf = reinterpret_cast<float*>(smem + HC::NSTAGE * C::STAGE_BYTES + HC::IMG_BYTES + HC::W11_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(poolbuf) + C::POOL_BYTES);
+  uint64_t* empty = full + HC::NSTAGE;
+  uint64_t* accum_full = empty + HC::NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * C::TH;
+  const int H = h.c.H, W = h.c.W;
+  constexpr int nkg = C1 / KG;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HC::NSTAGE; ++s) { mbar_init(full + s, 129); mbar_init(empty + s, 1); }
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- conv12 weight loader
+    if (lane == 0) {
+      for (int kg = 0; kg < nkg; ++kg) {
+        const int slot = kg % HC::NSTAGE;
+        mbar_wait(empty + slot, ((kg / HC::NSTAGE) & 1) ^ 1);
+        mbar_expect_tx(full + slot, C::W_BYTES);
+        bulk_g2s(smem_u32(stages + slot * C::STAGE_BYTES + C::IN_BYTES), h.c.w + (size_t)kg * (C::W_BYTES / 4), C::W_BYTES,
+                 full + slot);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0)
+      mma_issue_loop<N, HC::NSTAGE, C::STAGE_BYTES, C::IN_BYTES, C::P, C::NB>(stages, full, empty, accum_full, tmem_base, nkg);
+    __syncwarp();
+  } else if (warp < 6) {
+    conv_epilogue<N, C::NB, EPI>(h.c, accum_full, tmem_base, poolbuf, warp, lane, x0, y0, 0);
+  } else {
+    // ---- conv11 producers (128 threads)
+    const int tp = threadIdx.x - 192;
+    const long long HW = (long long)H * W;
+    for (int i = tp; i < 27 * C1 + C1; i += 128) w11_s[i] = i < 27 * C1 ? h.w11[i] : h.b11[i - 27 * C1];
+    for (int i = tp; i < 3 * HC::IMG_ROWS * HC::IMG_PITCH; i += 128) {
+      const int q = i % HC::IMG_PITCH, r = (i / HC::IMG_PITCH) % HC::IMG_ROWS, c = i / (HC::IMG_PITCH * HC::IMG_ROWS);
+      const int gy = min(max(y0 - 2 + r, 0), H - 1), gx = min(max(x0 - 2 + q, 0), W - 1);
+      img_s[i] = __ldg(h.img + c * HW + (long long)gy * W + gx);
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    constexpr int NPAIR = (C::TH + 2) * PW / 2;
+    for (int kg = 0; kg < nkg; ++kg) {
+      const int slot = kg % HC::NSTAGE;
+      mbar_wait(empty + slot, ((kg / HC::NSTAGE) & 1) ^ 1);
+      float4* st0 = reinterpret_cast<float4*>(stages + slot * C::STAGE_BYTES);
+      float4* st1 = st0 + C::P;
+      for (int pr = tp; pr < NPAIR; pr += 128) {
+        const int t = 2 * pr;                       // tile positions t, t+1 (same row)
+        const int i = t / PW, j = t % PW;
+        const int gy = wctb_reflect(y0 - 1 + i, H);
+        int ry[3], cx[4];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ry[d] = min(max(wctb_reflect(gy + d - 1, H) - (y0 - 2), 0), HC::IMG_ROWS - 1) * HC::IMG_PITCH;
+        const int gx0 = wctb_reflect(x0 - 1 + j, W), gx1 = wctb_reflect(x0 + j, W);
+        float acc0[8], acc1[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { acc0[o] = b11_s[kg * 8 + o]; acc1[o] = acc0[o]; }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int c0 = min(max(wctb_reflect(gx0 + dx - 1, W) - (x0 - 2), 0), HC::IMG_PITCH - 1);
+            const int c1 = min(max(wctb_reflect(gx1 + dx - 1, W) - (x0 - 2), 0), HC::IMG_PITCH - 1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float v0 = img_s[c * HC::IMG_ROWS * HC::IMG_PITCH + ry[dy] + c0];
+              const float v1 = img_s[c * HC::IMG_ROWS * HC::IMG_PITCH + ry[dy] + c1];
+              const float4* wp = reinterpret_cast<const float4*>(w11_s + ((dy * 3 + dx) * 3 + c) * C1 + kg * 8);
+              const float4 wa = wp[0], wb = wp[1];
+              acc0[0] = fmaf(v0, wa.x, acc0[0]); acc0[1] = fmaf(v0, wa.y, acc0[1]); acc0[2] = fmaf(v0, wa.z, acc0[2]); acc0[3] = fmaf(v0, wa.w, acc0[3]);
+              acc0[4] = fmaf(v0, wb.x, acc0[4]); acc0[5] = fmaf(v0, wb.y, acc0[5]); acc0[6] = fmaf(v0, wb.z, acc0[6]); acc0[7] = fmaf(v0, wb.w, acc0[7]);
+              acc1[0] = fmaf(v1, wa.x, acc1[0]); acc1[1] = fmaf(v1, wa.y, acc1[1]); acc1[2] = fmaf(v1, wa.z, acc1[2]); acc1[3] = fmaf(v1, wa.w, acc1[3]);
+              acc1[4] = fmaf(v1, wb.x, acc1[4]); acc1[5] = fmaf(v1, wb.y, acc1[5]); acc1[6] = fmaf(v1, wb.z, acc1[6]); acc1[7] = fmaf(v1, wb.w, acc1[7]);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { acc0[o] = wctb_tf32(wctb_relu(acc0[o])); acc1[o] = wctb_tf32(wctb_relu(acc1[o])); }
+        st0[t] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        st1[t] = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+        st0[t + 1] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        st1[t + 1] = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes -> visible to tcgen05.mma
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full + slot)) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int C1, int N, int EPI>
+int launch_head(const HeadArgs& h, cudaStream_t st) {
+  using C = Cfg<N>;
+  using HC = HeadCfg<C1, N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel<C1, N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, HC::SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid((h.c.W + TW - 1) / TW, (h.c.H + C::TH - 1) / C::TH, 1);
+  if (grid.y > 65535) return WCTB_E_UNSUPPORTED;
+  conv_head_kernel<C1, N, EPI><<<grid, 320, HC::SMEM_BYTES, st>>>(h);
+  WCTB_RETURN_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------- fused decoder tail
+//   img = ReLU(conv11( reflect_pad( ReLU(conv12( reflect_pad(x) )) ) ))      x P4 16ch (full res) -> img NCHW 3ch
+// conv12 (16->16) runs on tcgen05 exactly like the generic kernel, but for an intermediate tile that is one pixel
+// larger on every side than the 14x60 final tile; its epilogue keeps the ReLU'd intermediate in shared memory (the
+// pipeline stages are free once the accumulators are complete), patches the halo positions that lie outside the
+// image with the mirrored intermediate values (reflection applies to the INTERMEDIATE, not to conv12's input), and
+// conv11 (16->3, N = 3 is not an MMA shape) is evaluated with FFMA from that tile and written as NCHW.
+// The 16-channel full-resolution conv12 output (64 B/px write + read) never goes to HBM.
+// UPSRC: the input is the half-resolution tensor and nearest-x2 upsampling (model_cd.py:261) is applied while the
+// producer warps fill the operand tile (generic loads), so the upsampled tensor never exists in HBM either.
+struct TailArgs {
+  ConvArgs c;         // conv12: x (P4 16ch; [H/2][W/2] when UPSRC), w packed tf32, bias; y unused; H, W = OUTPUT size
+  const float* w11;   // [tap][16][3] fp32
+  const float* b11;   // [3]
+  float* img;         // [3][H][W]
+};
+constexpr int TAIL_TH = 14, TAIL_TW = 60;
+template <bool UPSRC>
+__global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const TailArgs t) {
+  constexpr int N = 16;
+  using C = Cfg<N>;            // NB = 8 -> 16 intermediate rows x 62 valid intermediate columns
+  constexpr int NSTAGE = 2;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* stages = smem;
+  float4* ibuf = reinterpret_cast<float4*>(smem);                       // [4 chunks][16 rows * 64] -- reuses the stages
+  float4* w11_s = reinterpret_cast<float4*>(smem + NSTAGE * C::STAGE_BYTES);   // [tap][chunk][3] (4 cin each)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * C::STAGE_BYTES + 108 * 16 + 16);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* accum_full = empty + NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  static_assert(4 * 16 * PW * 16 <= NSTAGE * C::STAGE_BYTES, "intermediate tile must fit in the freed stages");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0f = blockIdx.x * TAIL_TW, y0f = blockIdx.y * TAIL_TH;     // final tile origin
+  const int x0 = x0f - 1, y0 = y0f - 1;                                 // intermediate tile origin
+  const int H = t.c.H, W = t.c.W;
+  const long long HW = (long long)H * W;
+  constexpr int nkg = 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, UPSRC ? 129 : 1); mbar_init(empty + s, 1); }
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 108) {                     // epilogue threads stage the conv11 weights
+    const int i = threadIdx.x - 64;
+    const int o = i % 3, c4 = (i / 3) % 4, tap = i / 12;
+    const float* p = t.w11 + ((size_t)tap * 16 + c4 * 4) * 3 + o;
+    w11_s[i] = make_float4(p[0], p[3], p[6], p[9]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- producer: weights always by bulk copy; input rows by bulk copy unless UPSRC
+    if (!UPSRC) {
+      // intermediate tile col j <-> input col gx = x0 - 1 + j (x0 may be -1)
+      const int jlo = max(0, 1 - x0);                                     // first tile col with gx >= 0
+      const int jhi = min(PW, W - x0 + 1);
+      const int ncols = max(jhi - jlo, 0);
+      const uint32_t nrefl_l = (uint32_t)jlo;                             // gx = -1, -2 -> 1, 2
+      const int jr = W - x0 + 1;                                          // tile col of gx == W
+      const uint32_t nrefl_r = (uint32_t)min(max(PW - jr, 0), 2);         // gx = W, W+1 -> W-2, W-3 (only 2 needed)
+      const uint32_t row_bytes = ((uint32_t)ncols + nrefl_l + nrefl_r) * 16u;
+      const uint32_t stage_tx = (uint32_t)C::W_BYTES + 2u * (C::TH + 2) * row_bytes;
+      for (int kg = 0; kg < nkg; ++kg) {
+        const int slot = kg;
+        uint8_t* st = stages + slot * C::STAGE_BYTES;
+        if (lane == 0) {
+          mbar_expect_tx(full + slot, stage_tx);
+          bulk_g2s(smem_u32(st + C::IN_BYTES), t.c.w + (size_t)kg * (C::W_BYTES / 4), C::W_BYTES, full + slot);
+        }
+        __syncwarp();
+        for (int idx = lane; idx < 2 * (C::TH + 2); idx += 32) {
+          const int c = idx / (C::TH + 2), i = idx - c * (C::TH + 2);
+          const int gy = wctb_reflect(y0 - 1 + i, H);
+          const float4* src = t.c.x + (long long)(kg * 2 + c) * HW + (long long)gy * W;
+          const uint32_t dst = smem_u32(st + ((size_t)c * C::P + (size_t)i * PW) * 16);
+          if (ncols > 0) bulk_g2s(dst + jlo * 16, src + (x0 - 1 + jlo), (uint32_t)ncols * 16u, full + slot);
+          for (uint32_t k = 0; k < nrefl_l; ++k) bulk_g2s(dst + k * 16, src + wctb_reflect(x0 - 1 + (int)k, W), 16u, full + slot);
+          for (uint32_t k = 0; k < nrefl_r; ++k) bulk_g2s(dst + (jr + k) * 16, src + wctb_reflect(W + (int)k, W), 16u, full + slot);
+        }
+      }
+    } else if (lane == 0) {
+      for (int kg = 0; kg < nkg; ++kg) {
+        mbar_expect_tx(full + kg, C::W_BYTES);
+        bulk_g2s(smem_u32(stages + kg * C::STAGE_BYTES + C::IN_BYTES), t.c.w + (size_t)kg * (C::W_BYTES / 4), C::W_BYTES, full + kg);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0)
+      mma_issue_loop<N, NSTAGE, C::STAGE_BYTES, C::IN_BYTES, C::P, C::NB>(stages, full, empty, accum_full, tmem_base, nkg);
+    __syncwarp();
+  } else if (warp < 6) {
+    // ---- epilogue: intermediate -> smem, border fix-up, conv11 by FFMA, NCHW store
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;            // 0..127
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    for (int b = 0; b < C::NB; ++b) {
+      const int p = 128 * b + 32 * q + lane;
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N), v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = wctb_relu(v[i] + __ldg(t.c.bias + i));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ibuf[j * (16 * PW) + p] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // reflection of the intermediate at true image borders: rows first, then columns (corners follow)
+    const int rt = (y0 < 0) ? 0 : -1;                         // tile row holding global row -1
+    const int rb = (H - y0 < 16) ? (H - y0) : -1;             // tile row holding global row H
+    for (int i = et; i < 4 * PW; i += 128) {
+      const int c = i & 63, ch = i >> 6;
+      if (rt == 0) ibuf[ch * (16 * PW) + c] = ibuf[ch * (16 * PW) + 2 * PW + c];
+      if (rb >= 2) ibuf[ch * (16 * PW) + rb * PW + c] = ibuf[ch * (16 * PW) + (rb - 2) * PW + c];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int cl = (x0 < 0) ? 0 : -1;
+    const int cr = (W - x0 < PW) ? (W - x0) : -1;
+    if (et < 4 * 16) {
+      const int r = et & 15, ch = et >> 4;
+      if (cl == 0) ibuf[ch * (16 * PW) + r * PW] = ibuf[ch * (16 * PW) + r * PW + 2];
+      if (cr >= 2) ibuf[ch * (16 * PW) + r * PW + cr] = ibuf[ch * (16 * PW) + r * PW + cr - 2];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // conv11: strips of 4 consecutive final pixels per thread (15 strips per row x 14 rows)
+    const float b0 = __ldg(t.b11), b1 = __ldg(t.b11 + 1), b2 = __ldg(t.b11 + 2);
+    for (int sidx = et; sidx < TAIL_TH * (TAIL_TW / 4); sidx += 128) {
+      const int r = sidx / (TAIL_TW / 4), c = (sidx - r * (TAIL_TW / 4)) * 4;
+      float acc[4][3];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) { acc[px][0] = b0; acc[px][1] = b1; acc[px][2] = b2; }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          float4 in[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) in[k] = ibuf[ch * (16 * PW) + (r + dy) * PW + c + k];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float4 w0 = w11_s[((dy * 3 + dx) * 4 + ch) * 3 + 0];
+            const float4 w1 = w11_s[((dy * 3 + dx) * 4 + ch) * 3 + 1];
+            const float4 w2 = w11_s[((dy * 3 + dx) * 4 + ch) * 3 + 2];
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              const float4 v = in[px + dx];
+              acc[px][0] = fmaf(v.x, w0.x, acc[px][0]); acc[px][0] = fmaf(v.y, w0.y, acc[px][0]);
+              acc[px][0] = fmaf(v.z, w0.z, acc[px][0]); acc[px][0] = fmaf(v.w, w0.w, acc[px][0]);
+              acc[px][1] = fmaf(v.x, w1.x, acc[px][1]); acc[px][1] = fmaf(v.y, w1.y, acc[px][1]);
+              acc[px][1] = fmaf(v.z, w1.z, acc[px][1]); acc[px][1] = fmaf(v.w, w1.w, acc[px][1]);
+              acc[px][2] = fmaf(v.x, w2.x, acc[px][2]); acc[px][2] = fmaf(v.y, w2.y, acc[px][2]);
+              acc[px][2] = fmaf(v.z, w2.z, acc[px][2]); acc[px][2] = fmaf(v.w, w2.w, acc[px][2]);
+            }
+          }
+        }
+      }
+      const int gy = y0f + r, gx = x0f + c;
+      if (gy < H) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          float* dst = t.img + (long long)o * HW + (long long)gy * W + gx;
+          if (gx + 3 < W && ((((long long)o * HW + (long long)gy * W + gx) & 3) == 0)) {
+            *reinterpret_cast<float4*>(dst) = make_float4(wctb_relu(acc[0][o]), wctb_relu(acc[1][o]), wctb_relu(acc[2][o]), wctb_relu(acc[3][o]));
+          } else {
+#pragma unroll
+            for (int px = 0; px < 4; ++px) if (gx + px < W) dst[px] = wctb_relu(acc[px][o]);
+          }
+        }
+      }
+    }
+  } else if (UPSRC) {
+    // ---- upsampling producers (128 threads): half-res source -> full-res operand tile
+    const int tp = threadIdx.x - 192;
+    const int Hs = H >> 1, Ws = W >> 1;
+    const long long HWs = (long long)Hs * Ws;
+    for (int kg = 0; kg < nkg; ++kg) {
+      float4* st = reinterpret_cast<float4*>(stages + kg * C::STAGE_BYTES);
+      for (int idx = tp; idx < 2 * (C::TH + 2) * PW; idx += 128) {
+        const int j = idx & 63, i = (idx >> 6) % (C::TH + 2), c = idx / (PW * (C::TH + 2));
+        const int gy = wctb_reflect(y0 - 1 + i, H), gx = wctb_reflect(x0 - 1 + j, W);
+        st[c * C::P + i * PW + j] = __ldg(t.c.x + (long long)(kg * 2 + c) * HWs + (long long)(gy >> 1) * Ws + (gx >> 1));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full + kg)) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <bool UPSRC>
+int launch_tail(const TailArgs& t, cudaStream_t st) {
+  using C = Cfg<16>;
+  constexpr int SMEM = 2 * C::STAGE_BYTES + 108 * 16 + 16 + 256 + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_tail_kernel<UPSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  dim3 grid((t.c.W + TAIL_TW - 1) / TAIL_TW, (t.c.H + TAIL_TH - 1) / TAIL_TH, 1);
+  if (grid.y > 65535) return WCTB_E_UNSUPPORTED;
+  conv_tail_kernel<UPSRC><<<grid, UPSRC ? 320 : 192, SMEM, st>>>(t);
+  WCTB_RETURN_LAUNCH();
 }
 
 // ---------------------------------------------------------------------------------- weight packing
@@ -425,4 +744,32 @@ extern "C" int wctb_selftest_umma(float* out, const float* a, const float* b, in
   }
 #undef WCTB_ST
   WCTB_RETURN_LAUNCH();
+}
+
+extern "C" int wctb_conv_head_supported(int C1, int Cout) { return ((C1 == 16 && Cout == 16) || (C1 == 64 && Cout == 64)) ? 1 : 0; }
+
+extern "C" int wctb_conv_head(const float* x_nchw, const float* w11, const float* b11, const float* w12_packed,
+                              const float* b12, float* y_p4, int H, int W, int C1, int Cout, int epilogue, int round_tf32,
+                              void* stream) {
+  if (!x_nchw || !w11 || !b11 || !w12_packed || !b12 || !y_p4 || H < 2 || W < 2) return WCTB_E_BADARG;
+  if (epilogue != WCTB_EPI_NONE && epilogue != WCTB_EPI_POOL2) return WCTB_E_BADARG;
+  if (!wctb_conv_head_supported(C1, Cout)) return WCTB_E_UNSUPPORTED;
+  if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
+  HeadArgs h{x_nchw, w11, b11, ConvArgs{nullptr, w12_packed, b12, (float4*)y_p4, H, W, C1, Cout, round_tf32}};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C1 == 16) return epilogue == WCTB_EPI_POOL2 ? launch_head<16, 16, WCTB_EPI_POOL2>(h, st) : launch_head<16, 16, WCTB_EPI_NONE>(h, st);
+  return epilogue == WCTB_EPI_POOL2 ? launch_head<64, 64, WCTB_EPI_POOL2>(h, st) : launch_head<64, 64, WCTB_EPI_NONE>(h, st);
+}
+
+extern "C" int wctb_conv_tail_supported(int Cin, int Cmid) { return (Cin == 16 && Cmid == 16) ? 1 : 0; }
+
+extern "C" int wctb_conv_tail(const float* x_p4, const float* w12_packed, const float* b12, const float* w11,
+                              const float* b11, float* y_nchw, int H, int W, int Cin, int Cmid, int upsample_input,
+                              void* stream) {
+  if (!x_p4 || !w12_packed || !b12 || !w11 || !b11 || !y_nchw || H < 2 || W < 2) return WCTB_E_BADARG;
+  if (!wctb_conv_tail_supported(Cin, Cmid)) return WCTB_E_UNSUPPORTED;
+  if (upsample_input && ((H & 1) || (W & 1))) return WCTB_E_BADARG;
+  if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
+  TailArgs t{ConvArgs{(const float4*)x_p4, w12_packed, b12, nullptr, H, W, Cin, Cmid, 0}, w11, b11, y_nchw};
+  return upsample_input ? launch_tail<true>(t, (cudaStream_t)stream) : launch_tail<false>(t, (cudaStream_t)stream);
 }

@@ -63,111 +63,26 @@ extern "C" int wctb_channel_sum(const float* x, int C, int H, int W, int y0, int
 
 // ------------------------------------------------------------------------------------------
 // centred Gram matrix  G += sum_p (x_p - mu)(x_p - mu)^T   in fp64 (DFMA).
-// A CTA owns a GBxGB block (bi <= bj) of G and a slice of the region's pixels; pixels are staged
-// centred, as doubles, in smem [pixel][GB]; 16x16 threads each accumulate a TBxTB sub-block
-// (GB = 16*TB; TB picked from C so small channel counts do not pay for padding).
+// A CTA owns a GBxGB block (bi <= bj) of G and a slice of the region's pixels.  Pixels are staged centred, as
+// doubles, in shared memory [pixel][GB]; SIDE x SIDE threads form a group that accumulates the whole block with a
+// TR x TR register tile each (GB = SIDE*TR); 256/(SIDE*SIDE) groups take interleaved pixels of the stage, so a
+// thread does GP/NG * TR*TR DFMAs between barriers.  Configurations: C=16 -> (TR 2, SIDE 8), C=24 -> (3, 8),
+// C=32 -> (4, 8), C>=64 -> 64x64 blocks (4, 16) over the upper block triangle.
 // Flush with fp64 atomics (order-dependent only at the 1e-16 level).
 // ------------------------------------------------------------------------------------------
-constexpr int GP = 32;   // pixels per smem stage
-template <int TB>
+template <int TR, int SIDE>
 __global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __restrict__ x, int C, int H, int W, int y0,
                                                             int x0, int wreg, long long npix, long long pix_per_cta,
                                                             const double* __restrict__ mean, double* __restrict__ G) {
-  constexpr int GB = 16 * TB;
-  constexpr int NCH4 = GB / 4;            // float4 chunks per channel block
-  __shared__ double sa[GP][GB + 1];
-  __shared__ double sb[GP][GB + 1];
-  const int nb = (C + GB - 1) / GB;
-  int bi = 0, bj = 0;
-  {
-    int t = blockIdx.y;
-    for (bi = 0; bi < nb; ++bi) {
-      int cnt = nb - bi;
-      if (t < cnt) { bj = bi + t; break; }
-      t -= cnt;
-    }
-  }
-  const bool diag = (bi == bj);
-  const long long pbeg = blockIdx.x * pix_per_cta;
-  const long long pend = min(npix, pbeg + pix_per_cta);
-  const int tid = threadIdx.x;
-  const int ti = tid >> 4, tj = tid & 15;
-  double acc[TB][TB];
-#pragma unroll
-  for (int a = 0; a < TB; ++a)
-#pragma unroll
-    for (int b = 0; b < TB; ++b) acc[a][b] = 0.0;
-  const long long HW = (long long)H * W;
-  const int chA = bi * GB, chB = bj * GB;
-
-  for (long long p0 = pbeg; p0 < pend; p0 += GP) {
-    __syncthreads();
-    {
-      const int pp = tid & 31;
-      const long long p = p0 + pp;
-      const bool ok = p < pend;
-      long long off = 0;
-      if (ok) {
-        int r = (int)(p / wreg), c = (int)(p - (long long)r * wreg);
-        off = (long long)(y0 + r) * W + (x0 + c);
-      }
-      for (int ch4 = tid >> 5; ch4 < NCH4; ch4 += 8) {
-        double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        if (ok && chA + ch4 * 4 < C) {
-          float4 v = __ldg(x + (long long)(chA / 4 + ch4) * HW + off);
-          const double* m = mean + chA + ch4 * 4;
-          v0 = (double)v.x - m[0]; v1 = (double)v.y - m[1]; v2 = (double)v.z - m[2]; v3 = (double)v.w - m[3];
-        }
-        sa[pp][ch4 * 4 + 0] = v0; sa[pp][ch4 * 4 + 1] = v1; sa[pp][ch4 * 4 + 2] = v2; sa[pp][ch4 * 4 + 3] = v3;
-        if (!diag) {
-          v0 = v1 = v2 = v3 = 0;
-          if (ok && chB + ch4 * 4 < C) {
-            float4 v = __ldg(x + (long long)(chB / 4 + ch4) * HW + off);
-            const double* m = mean + chB + ch4 * 4;
-            v0 = (double)v.x - m[0]; v1 = (double)v.y - m[1]; v2 = (double)v.z - m[2]; v3 = (double)v.w - m[3];
-          }
-          sb[pp][ch4 * 4 + 0] = v0; sb[pp][ch4 * 4 + 1] = v1; sb[pp][ch4 * 4 + 2] = v2; sb[pp][ch4 * 4 + 3] = v3;
-        }
-      }
-    }
-    __syncthreads();
-    const double(*B)[GB + 1] = diag ? sa : sb;
-#pragma unroll 4
-    for (int pp = 0; pp < GP; ++pp) {
-      double a[TB], b[TB];
-#pragma unroll
-      for (int k = 0; k < TB; ++k) { a[k] = sa[pp][ti * TB + k]; b[k] = B[pp][tj + 16 * k]; }
-#pragma unroll
-      for (int u = 0; u < TB; ++u)
-#pragma unroll
-        for (int v = 0; v < TB; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < TB; ++u)
-#pragma unroll
-    for (int v = 0; v < TB; ++v) {
-      int i = chA + ti * TB + u, j = chB + tj + 16 * v;
-      if (i < C && j < C) {
-        atomicAdd(G + (long long)i * C + j, acc[u][v]);
-        if (!diag) atomicAdd(G + (long long)j * C + i, acc[u][v]);
-      }
-    }
-}
-// Large maps: same tiling, fp32 FFMA partial sums over runs of <= 32 pixels, flushed into fp64 accumulators.
-// Relative error of the Gram ~ 3.5e-7 / sqrt(npix), used only for npix >= 65536.
-// GB = 32 (C <= 32): 4 pixel groups x 64 threads; GB = 64: 1 group x 256 threads; 4x4 register tile per thread,
-// operands read as float4 (two 128-bit shared loads per 16 FMA).
-template <int GB>
-__global__ void __launch_bounds__(256) centered_gram_f32_kernel(const float4* __restrict__ x, int C, int H, int W, int y0,
-                                                                int x0, int wreg, long long npix, long long pix_per_cta,
-                                                                const double* __restrict__ mean, double* __restrict__ G) {
+  constexpr int GB = SIDE * TR;
   constexpr int NCH4 = GB / 4;
-  constexpr int TPG = (GB / 4) * (GB / 4);   // threads per pixel group
-  constexpr int NG = 256 / TPG;              // pixel groups per CTA
-  constexpr int GPX = 32;                    // pixels per smem stage
-  __shared__ __align__(16) float sa[GPX][GB + 4];
-  __shared__ __align__(16) float sb[GPX][GB + 4];
+  constexpr int TPG = SIDE * SIDE;
+  constexpr int NG = 256 / TPG;
+  constexpr int GP = (SIDE == 16) ? 64 : 128;      // pixels per stage
+  constexpr int PITCH = GB + 2;                    // doubles; keeps 16-byte alignment of row starts
+  extern __shared__ __align__(16) double gsm[];
+  double(*sa)[PITCH] = reinterpret_cast<double(*)[PITCH]>(gsm);
+  double(*sb)[PITCH] = reinterpret_cast<double(*)[PITCH]>(gsm + (size_t)GP * PITCH);
   const int nb = (C + GB - 1) / GB;
   int bi = 0, bj = 0;
   {
@@ -183,79 +98,86 @@ __global__ void __launch_bounds__(256) centered_gram_f32_kernel(const float4* __
   const long long pend = min(npix, pbeg + pix_per_cta);
   const int tid = threadIdx.x;
   const int grp = tid / TPG, tl = tid % TPG;
-  const int ti = tl / (GB / 4), tj = tl % (GB / 4);
-  float acc[4][4];
-  double dacc[4][4];
+  const int ti = tl / SIDE, tj = tl % SIDE;
+  double acc[TR][TR];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < TR; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) { acc[u][v] = 0.f; dacc[u][v] = 0.0; }
+    for (int v = 0; v < TR; ++v) acc[u][v] = 0.0;
   const long long HW = (long long)H * W;
   const int chA = bi * GB, chB = bj * GB;
-  int run = 0;
-  for (long long p0 = pbeg; p0 < pend; p0 += GPX) {
+  for (long long p0 = pbeg; p0 < pend; p0 += GP) {
     __syncthreads();
-    {
-      const int pp = tid & 31;
+    for (int e = tid; e < GP * NCH4; e += 256) {
+      const int pp = e % GP, ch4 = e / GP;
       const long long p = p0 + pp;
-      const bool ok = p < pend;
-      long long off = 0;
-      if (ok) {
-        int r = (int)(p / wreg), c = (int)(p - (long long)r * wreg);
-        off = (long long)(y0 + r) * W + (x0 + c);
-      }
-      for (int ch4 = tid >> 5; ch4 < NCH4; ch4 += 8) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && chA + ch4 * 4 < C) {
-          v = __ldg(x + (long long)(chA / 4 + ch4) * HW + off);
+      double va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0};
+      if (p < pend) {
+        const int r = (int)(p / wreg), c = (int)(p - (long long)r * wreg);
+        const long long off = (long long)(y0 + r) * W + (x0 + c);
+        if (chA + ch4 * 4 < C) {
+          const float4 v = __ldg(x + (long long)(chA / 4 + ch4) * HW + off);
           const double* m = mean + chA + ch4 * 4;
-          v.x -= (float)m[0]; v.y -= (float)m[1]; v.z -= (float)m[2]; v.w -= (float)m[3];
+          va[0] = (double)v.x - m[0]; va[1] = (double)v.y - m[1]; va[2] = (double)v.z - m[2]; va[3] = (double)v.w - m[3];
         }
-        *reinterpret_cast<float4*>(&sa[pp][ch4 * 4]) = v;
-        if (!diag) {
-          v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && chB + ch4 * 4 < C) {
-            v = __ldg(x + (long long)(chB / 4 + ch4) * HW + off);
-            const double* m = mean + chB + ch4 * 4;
-            v.x -= (float)m[0]; v.y -= (float)m[1]; v.z -= (float)m[2]; v.w -= (float)m[3];
-          }
-          *reinterpret_cast<float4*>(&sb[pp][ch4 * 4]) = v;
+        if (!diag && chB + ch4 * 4 < C) {
+          const float4 v = __ldg(x + (long long)(chB / 4 + ch4) * HW + off);
+          const double* m = mean + chB + ch4 * 4;
+          vb[0] = (double)v.x - m[0]; vb[1] = (double)v.y - m[1]; vb[2] = (double)v.z - m[2]; vb[3] = (double)v.w - m[3];
         }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sa[pp][ch4 * 4 + k] = va[k];
+      if (!diag) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sb[pp][ch4 * 4 + k] = vb[k];
       }
     }
     __syncthreads();
-    const float(*B)[GB + 4] = diag ? sa : sb;
+    const double(*B)[PITCH] = diag ? sa : sb;
+#pragma unroll 4
+    for (int pp = grp; pp < GP; pp += NG) {
+      double a[TR], b[TR];
 #pragma unroll
-    for (int k = 0; k < GPX / NG; ++k) {
-      const int pp = grp + k * NG;
-      const float4 a4 = *reinterpret_cast<const float4*>(&sa[pp][ti * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&B[pp][tj * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+      for (int k = 0; k < TR; ++k) { a[k] = sa[pp][ti * TR + k]; b[k] = B[pp][tj * TR + k]; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < TR; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
-    }
-    run += GPX / NG;
-    if (run >= 32) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) { dacc[u][v] += (double)acc[u][v]; acc[u][v] = 0.f; }
-      run = 0;
+        for (int v = 0; v < TR; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < TR; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const double val = dacc[u][v] + (double)acc[u][v];
-      int i = chA + ti * 4 + u, j = chB + tj * 4 + v;
+    for (int v = 0; v < TR; ++v) {
+      const int i = chA + ti * TR + u, j = chB + tj * TR + v;
       if (i < C && j < C) {
-        atomicAdd(G + (long long)i * C + j, val);
-        if (!diag) atomicAdd(G + (long long)j * C + i, val);
+        atomicAdd(G + (long long)i * C + j, acc[u][v]);
+        if (!diag) atomicAdd(G + (long long)j * C + i, acc[u][v]);
       }
     }
+}
+
+template <int TR, int SIDE>
+static int launch_gram(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1, const double* mean,
+                       double* gram_out, cudaStream_t st) {
+  constexpr int GB = SIDE * TR;
+  constexpr int GP = (SIDE == 16) ? 64 : 128;
+  const size_t smem = (size_t)2 * GP * (GB + 2) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(centered_gram_kernel<TR, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int nb = (C + GB - 1) / GB, nblk = nb * (nb + 1) / 2;
+  const long long npix = (long long)(y1 - y0) * (x1 - x0);
+  const int target = max(1, (3 * wctb_num_sms()) / nblk);
+  long long per = (npix + target - 1) / target;
+  per = ((per + GP - 1) / GP) * GP;
+  if (per < 4 * GP) per = 4 * GP;
+  dim3 grid((unsigned)((npix + per - 1) / per), nblk);
+  centered_gram_kernel<TR, SIDE><<<grid, 256, smem, st>>>((const float4*)x, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
+  WCTB_RETURN_LAUNCH();
 }
 
 extern "C" int wctb_centered_gram(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1,
@@ -263,39 +185,11 @@ extern "C" int wctb_centered_gram(const float* x, int C, int H, int W, int y0, i
   if (!x || !mean || !gram_out || C <= 0 || (C & 3) || H <= 0 || W <= 0 || y0 < 0 || y1 > H || x0 < 0 || x1 > W ||
       y0 >= y1 || x0 >= x1)
     return WCTB_E_BADARG;
-  {
-    const long long npix_all = (long long)(y1 - y0) * (x1 - x0);
-    if (npix_all >= 65536) {
-      const int GBv = C <= 32 ? 32 : 64;
-      const int nb = (C + GBv - 1) / GBv, nblk = nb * (nb + 1) / 2;
-      int target = max(1, (4 * wctb_num_sms()) / nblk);
-      long long per = (npix_all + target - 1) / target;
-      per = ((per + 31) / 32) * 32;
-      if (per < 1024) per = 1024;
-      dim3 grid((unsigned)((npix_all + per - 1) / per), nblk);
-      cudaStream_t st = (cudaStream_t)stream;
-      if (GBv == 32) centered_gram_f32_kernel<32><<<grid, 256, 0, st>>>((const float4*)x, C, H, W, y0, x0, x1 - x0, npix_all, per, mean, gram_out);
-      else centered_gram_f32_kernel<64><<<grid, 256, 0, st>>>((const float4*)x, C, H, W, y0, x0, x1 - x0, npix_all, per, mean, gram_out);
-      WCTB_RETURN_LAUNCH();
-    }
-  }
-  const int TB = C <= 16 ? 1 : (C <= 32 ? 2 : 4);
-  const int GBv = 16 * TB;
-  int nb = (C + GBv - 1) / GBv;
-  int nblk = nb * (nb + 1) / 2;
-  long long npix = (long long)(y1 - y0) * (x1 - x0);
-  int target = max(1, (4 * wctb_num_sms()) / nblk);
-  long long per = (npix + target - 1) / target;
-  per = ((per + GP - 1) / GP) * GP;
-  if (per < 8 * GP) per = 8 * GP;
-  unsigned gx = (unsigned)((npix + per - 1) / per);
-  dim3 grid(gx, nblk);
   cudaStream_t st = (cudaStream_t)stream;
-  const float4* x4 = (const float4*)x;
-  if (TB == 1) centered_gram_kernel<1><<<grid, 256, 0, st>>>(x4, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
-  else if (TB == 2) centered_gram_kernel<2><<<grid, 256, 0, st>>>(x4, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
-  else centered_gram_kernel<4><<<grid, 256, 0, st>>>(x4, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
-  WCTB_RETURN_LAUNCH();
+  if (C <= 16) return launch_gram<2, 8>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  if (C <= 24) return launch_gram<3, 8>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  if (C <= 32) return launch_gram<4, 8>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  return launch_gram<4, 16>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
 }
 
 // ------------------------------------------------------------------------------------------

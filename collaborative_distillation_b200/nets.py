@@ -18,6 +18,8 @@ import torch.nn as nn
 from . import arch, ops
 from ._lib import WctbError
 
+FUSE_TAIL = True      # [x2 upsample +] conv12 + conv11 of the decoders in one kernel when the TF32 engine is active
+FUSE_HEAD = True      # conv11+conv12(+pool) in one kernel when the TF32 engine is active
 _PRECISION = "tf32"   # "tf32": tcgen05 TF32 tensor-core engine where supported; "fp32": CUDA-core fp32 everywhere
 
 
@@ -130,8 +132,17 @@ class _Encoder(_Net):
         if sh < 2 or sw < 2:
             raise WctbError("input %dx%d too small for stage %d (ReflectionPad2d needs >=2 px at the deepest level)" % (H, W, self.STAGE))
         nxt = lambda i: pk[i + 1]["engine"] == ops.ENGINE_TF32 if i + 1 < n else False
-        y = ops.conv3x3_first(x, pk[0]["w"], pk[0]["b"], self.layers[0]["cout"], nxt(0))
-        for i in range(1, n):
+        L0 = self.layers[0]
+        if (FUSE_HEAD and n >= 2 and pk[1]["engine"] == ops.ENGINE_TF32
+                and ops.conv_head_supported(L0["cout"], self.layers[1]["cout"])):
+            L1 = self.layers[1]
+            y = ops.conv_head(x, pk[0]["w"], pk[0]["b"], pk[1]["w"], pk[1]["b"], L0["cout"], L1["cout"],
+                              ops.EPI_POOL2 if L1["pool_after"] else ops.EPI_NONE, nxt(1))
+            first = 2
+        else:
+            y = ops.conv3x3_first(x, pk[0]["w"], pk[0]["b"], L0["cout"], nxt(0))
+            first = 1
+        for i in range(first, n):
             L = self.layers[i]
             epi = ops.EPI_POOL2 if L["pool_after"] else ops.EPI_NONE
             y = ops.conv3x3_p4(y, pk[i]["w"], pk[i]["b"], L["cout"], epi, nxt(i), pk[i]["engine"])
@@ -156,10 +167,19 @@ class _Decoder(_Net):
         if y.shape[1] < 2 or y.shape[2] < 2:
             raise WctbError("feature map too small for ReflectionPad2d(1)")
         nxt = lambda i: (pk[i + 1]["engine"] == ops.ENGINE_TF32) if i + 1 < n else False
-        for i in range(n - 1):
+        # fused tail: [x2] conv12 + conv11 in one kernel (TF32 engine, 16-channel nets)
+        fuse_tail = FUSE_TAIL and n >= 3 and pk[n - 2]["engine"] == ops.ENGINE_TF32
+        fuse_tail = fuse_tail and ops.conv_tail_supported(self.layers[n - 2]["cin"], self.layers[n - 2]["cout"])
+        last_plain = n - 2 if fuse_tail else n - 1
+        up_in = False
+        for i in range(last_plain):
             L = self.layers[i]
             epi = ops.EPI_UP2 if L["up_after"] else ops.EPI_NONE
+            if fuse_tail and i == n - 3 and L["up_after"]:
+                epi, up_in = ops.EPI_NONE, True          # the tail kernel upsamples while it loads
             y = ops.conv3x3_p4(y, pk[i]["w"], pk[i]["b"], L["cout"], epi, nxt(i), pk[i]["engine"])
+        if fuse_tail:
+            return ops.conv_tail(y, pk[n - 2]["w"], pk[n - 2]["b"], pk[n - 1]["w"], pk[n - 1]["b"], up_in)
         return ops.conv3x3_last(y, pk[n - 1]["w"], pk[n - 1]["b"])
 
     def first_layer_needs_tf32_input(self, precision=None):

@@ -9,7 +9,7 @@ from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, ENGINE_FP32, ENGINE_TF32, check 
 
 _launches = 0  # number of libwctb kernel-launching calls (bench.py reports kernels via its own table)
 KERNELS_PER_CALL = {"nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
-                    "conv_last": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
+                    "conv_last": 1, "conv_head": 1, "conv_tail": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
                     "fold": 2}
 
 
@@ -97,6 +97,38 @@ def conv3x3_p4(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, cout: int, epi
     check(_lib.load().wctb_conv3x3_p4(_need(x), _need(w), _need(b), _need(y), H, W, C4 * 4, cout, epilogue,
                                       int(round_tf32), engine, _stream()), "conv3x3_p4")
     _count("conv_p4")
+    return y
+
+
+def conv_head_supported(c1: int, cout: int) -> bool:
+    return bool(_lib.load().wctb_conv_head_supported(c1, cout))
+
+
+def conv_head(x_nchw, w11, b11, w12_packed, b12, c1: int, cout: int, epilogue: int, round_tf32: bool) -> torch.Tensor:
+    """fused conv11(3->c1)+ReLU+conv12(c1->cout)+ReLU(+pool): image [1,3,H,W] -> P4 [cout/4,Ho,Wo,4]"""
+    if x_nchw.dim() == 4:
+        x_nchw = x_nchw.squeeze(0)
+    _, H, W = x_nchw.shape
+    Ho, Wo = (H // 2, W // 2) if epilogue == EPI_POOL2 else (H, W)
+    y = torch.empty(cout // 4, Ho, Wo, 4, device=x_nchw.device, dtype=torch.float32)
+    check(_lib.load().wctb_conv_head(_need(x_nchw), _need(w11), _need(b11), _need(w12_packed), _need(b12), _need(y), H, W,
+                                     c1, cout, epilogue, int(round_tf32), _stream()), "conv_head")
+    _count("conv_head")
+    return y
+
+
+def conv_tail_supported(cin: int, cmid: int) -> bool:
+    return bool(_lib.load().wctb_conv_tail_supported(cin, cmid))
+
+
+def conv_tail(x_p4, w12_packed, b12, w11, b11, upsample_input: bool) -> torch.Tensor:
+    """fused [nearest x2 +] conv12(16->16)+ReLU+conv11(16->3)+ReLU: P4 [4,h,w,4] -> image [1,3,H,W]"""
+    C4, h, w, _ = x_p4.shape
+    H, W = (2 * h, 2 * w) if upsample_input else (h, w)
+    y = torch.empty(1, 3, H, W, device=x_p4.device, dtype=torch.float32)
+    check(_lib.load().wctb_conv_tail(_need(x_p4), _need(w12_packed), _need(b12), _need(w11), _need(b11), _need(y), H, W,
+                                     C4 * 4, b12.numel(), int(upsample_input), _stream()), "conv_tail")
+    _count("conv_tail")
     return y
 
 

@@ -38,6 +38,8 @@ class WCT(nn.Module):
         self.tau = TAU
         self.dist = None          # set by parallel.StripGroup for multi-GPU runs
         self.fold_into_decoder = False
+        self.overlap_style = True  # single-GPU stylize(): run the (content-independent) style branch on a side stream
+        self._side = None
 
     # ------------------------------------------------------------------ statistics -> (M, b, mean_c)
     def _moments(self, x_p4, region, count, gram_out):
@@ -117,12 +119,63 @@ class WCT(nn.Module):
         del c4
         return dec.forward_p4(cs4)
 
+    # ---- two-stream schedule: the style branch (encoder, statistics, eigensolve of every stage) does not depend on the
+    # content image, so it runs on a side stream and overlaps the content branch -- in particular the single-CTA
+    # eigensolves, which otherwise leave 147 SMs idle.  Results are handed over with CUDA events.
+    def _eig_one(self, x_p4, add_identity=False):
+        C = x_p4.shape[0] * 4
+        n = float(x_p4.shape[1] * x_p4.shape[2])
+        gram = torch.zeros(1, C, C, device=x_p4.device, dtype=torch.float64)
+        mean = self._moments(x_p4, (0, x_p4.shape[1], 0, x_p4.shape[2]), n, gram[0])
+        evals, evecs = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=add_identity)
+        return mean, evals[0], evecs[0]
+
+    @torch.no_grad()
+    def _stylize_two_streams(self, content, style, alpha, num_run, stages):
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        side.wait_stream(main)
+        style_res = {}
+        with torch.cuda.stream(side):
+            for s in stages:
+                s4 = getattr(self, "e%d" % s).forward_p4(style)
+                res = self._eig_one(s4)
+                del s4
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for t in res:
+                    t.record_stream(main)
+                style_res[s] = (res, ev)
+        img = content
+        numpy_variant = bool(getattr(self.args, "numpy", False))
+        for _ in range(num_run):
+            for s in stages:
+                enc, dec = getattr(self, "e%d" % s), getattr(self, "d%d" % s)
+                c4 = enc.forward_p4(img)
+                c_mean, c_e, c_v = self._eig_one(c4, add_identity=numpy_variant)       # util_wct.py:143 (+I on content only)
+                (s_mean, s_e, s_v), ev = style_res[s]
+                main.wait_event(ev)
+                m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
+                if self.fold_into_decoder:
+                    L0 = getattr(dec, dec.layers[0]["name"])
+                    w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
+                    img = dec.forward_p4(c4, first_override=(w, bb))
+                else:
+                    cs4 = ops.wct_apply(c4, m, b, mc, round_tf32=dec.first_layer_needs_tf32_input())
+                    del c4
+                    img = dec.forward_p4(cs4)
+        return img
+
     @torch.no_grad()
     def stylize(self, content, style, alpha=1.0, num_run=1, stages=(5, 4, 3, 2, 1)):
         """content, style: [1,3,H,W] fp32 (CUDA, or CPU -> copied up).  Returns the stylized image on the GPU,
         un-clamped like the reference (WCT.py:120-125)."""
         img = content.to("cuda", torch.float32)
         style = style.to("cuda", torch.float32)
+        if self.dist is None and self.overlap_style:
+            return self._stylize_two_streams(img, style, alpha, num_run, tuple(stages))
         for _ in range(num_run):
             for s in stages:
                 img = self.style_transfer_stage(s, img, style, alpha)

@@ -86,6 +86,26 @@ int wctb_conv3x3_p4(const float* x_p4, const float* w_packed, const float* bias,
                     int H, int W, int Cin, int Cout, int epilogue, int round_tf32, int engine,
                     void* stream);
 
+/* fused encoder head (TF32 engine): conv11 (3 -> C1, FFMA, conv0 folded) + ReLU feeding conv12 (C1 -> Cout, tcgen05)
+ * + ReLU (+pool) in one kernel; the C1-channel full-resolution activation stays in shared memory.
+ * replaces: y = relu(conv11(pad(conv0(y)))); y = relu(conv12(pad(y))); [y = pool(y)]   (model_cd.py:725-728)
+ * w11: [tap][3][C1] fp32, w12_packed: wctb_pack_weights_tf32 layout.  Supported (C1,Cout): (16,16), (64,64). */
+int wctb_conv_head_supported(int C1, int Cout);
+int wctb_conv_head(const float* x_nchw, const float* w11, const float* b11, const float* w12_packed,
+                   const float* b12, float* y_p4, int H, int W, int C1, int Cout, int epilogue,
+                   int round_tf32, void* stream);
+
+/* fused decoder tail (TF32 engine): conv12 (16 -> 16, tcgen05) + ReLU + conv11 (16 -> 3, FFMA) + ReLU in one kernel,
+ * output NCHW [3][H][W]; the 16-channel full-resolution intermediate stays in shared memory.  With
+ * upsample_input != 0, x_p4 is the HALF-resolution tensor [Cin/4][H/2][W/2][4] and nn.UpsamplingNearest2d(2) is applied
+ * while the operand tile is filled, so the upsampled tensor never exists in HBM.
+ * replaces: [y = unpool(y);] y = relu(conv12(pad(y))); y = relu(conv11(pad(y)))      (model_cd.py:291-293)
+ * w12_packed: wctb_pack_weights_tf32 layout; w11: [tap][Cmid][3] fp32.  Supported (Cin,Cmid): (16,16).            */
+int wctb_conv_tail_supported(int Cin, int Cmid);
+int wctb_conv_tail(const float* x_p4, const float* w12_packed, const float* b12, const float* w11,
+                   const float* b11, float* y_nchw, int H, int W, int Cin, int Cmid, int upsample_input,
+                   void* stream);
+
 /* last decoder layer: P4 [Cin/4][H][W][4] -> NCHW [3][H][W], ReLU kept (model_cd.py:293). w: [tap][Cin][3] */
 int wctb_conv3x3_last(const float* x_p4, const float* w, const float* bias, float* y_nchw,
                       int H, int W, int Cin, void* stream);

@@ -97,10 +97,7 @@ def test_moments_match_fp64(C, H, W, region):
     g = ops.centered_gram(p4, mean.to(DEV), region).cpu()
     xc = xr - mean[:, None]
     ref = xc @ xc.t()
-    npix = (y1 - y0) * (x1 - x0)
-    # < 65536 px: fp64 DFMA accumulation.  >= 65536 px: fp32 FFMA runs of 32 px flushed into fp64 (3.5e-7/sqrt(n))
-    tol = 1e-11 if npix < 65536 else 2e-8
-    assert (g - ref).abs().max().item() <= tol * ref.abs().max().item()
+    assert (g - ref).abs().max().item() <= 1e-11 * ref.abs().max().item()      # fp64 DFMA accumulation
     assert (g - g.t()).abs().max().item() <= 1e-13 * ref.abs().max().item()   # fp64 atomics: order-dependent last bits
 
 

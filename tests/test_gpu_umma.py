@@ -88,3 +88,45 @@ def test_pack_weights_tf32_layout():
     p = ops.pack_weights(w.to(DEV), ops.ENGINE_TF32).cpu().view(cin // 8, 9, 2, cout, 4)
     ref = tf32_rna(w).view(cout, cin // 8, 2, 4, 9).permute(1, 4, 2, 0, 3)      # [kg][tap][c][n][e]
     assert torch.equal(p, ref.contiguous())
+
+
+@pytest.mark.parametrize("H,W,c1,n,epi", [(16, 62, 16, 16, 1), (2, 2, 16, 16, 0), (37, 131, 16, 16, 1), (50, 64, 16, 16, 0),
+                                           (33, 63, 64, 64, 1), (18, 125, 64, 64, 0), (161, 200, 16, 16, 1)])
+def test_fused_head_equals_two_layer_path(H, W, c1, n, epi):
+    """conv11(FFMA)+conv12(tcgen05) fused == conv3x3_first -> conv3x3_p4(TF32): same arithmetic, same order."""
+    g = torch.Generator().manual_seed(H + W + c1)
+    x = torch.rand(1, 3, H, W, generator=g).to(DEV)
+    w11 = (torch.randn(c1, 3, 3, 3, generator=g) * 0.3).to(DEV)
+    b11 = (torch.randn(c1, generator=g) * 0.1).to(DEV)
+    w12 = (torch.randn(n, c1, 3, 3, generator=g) * (2.0 / (9 * c1)) ** 0.5).to(DEV)
+    b12 = (torch.randn(n, generator=g) * 0.1).to(DEV)
+    p11 = ops.pack_weights(w11, ops.ENGINE_FP32)
+    p12 = ops.pack_weights(w12, ops.ENGINE_TF32)
+    mid = ops.conv3x3_first(x, p11, b11, c1, True)
+    ref = ops.conv3x3_p4(mid, p12, b12, n, epi, False, ops.ENGINE_TF32)
+    got = ops.conv_head(x, p11, b11, p12, b12, c1, n, epi, False)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("H,W,up", [(14, 60, False), (2, 2, False), (37, 131, False), (16, 64, False), (61, 200, False),
+                                    (28, 120, True), (4, 4, True), (74, 262, True), (150, 64, True)])
+def test_fused_tail_equals_two_layer_path(H, W, up):
+    """[x2] conv12(tcgen05)+conv11(FFMA) fused == conv3x3_p4(TF32) -> conv3x3_last."""
+    g = torch.Generator().manual_seed(H * 7 + W)
+    h, w = (H // 2, W // 2) if up else (H, W)
+    x = tf32_rna(torch.randn(1, 16, h, w, generator=g).relu()).to(DEV)
+    w12 = (torch.randn(16, 16, 3, 3, generator=g) * 0.12).to(DEV)
+    b12 = (torch.randn(16, generator=g) * 0.1).to(DEV)
+    w11 = (torch.randn(3, 16, 3, 3, generator=g) * 0.1).to(DEV)
+    b11 = (torch.randn(3, generator=g) * 0.1 + 0.2).to(DEV)
+    p12 = ops.pack_weights(w12, ops.ENGINE_TF32)
+    p11 = ops.pack_weights(w11, ops.ENGINE_FP32)
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
+    mid = ops.conv3x3_p4(ops.nchw_to_p4(xin), p12, b12, 16, 0, False, ops.ENGINE_TF32)
+    ref = ops.conv3x3_last(mid, p11, b11)
+    got = ops.conv_tail(ops.nchw_to_p4(x), p12, b12, p11, b11, up)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (1, 3, H, W)
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
