@@ -30,6 +30,7 @@ SIGNATURES = {
     "wctb_conv3x3_p4": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "wctb_conv3x3_last": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wctb_conv_head_supported": [_i, _i],
+    "wctb_conv_head_tc": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "wctb_conv_tail_supported": [_i, _i],
     "wctb_conv_tail": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "wctb_conv_head": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

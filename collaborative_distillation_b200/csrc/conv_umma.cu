@@ -420,38 +420,233 @@ int launch_head(const HeadArgs& h, cudaStream_t st) {
   WCTB_RETURN_LAUNCH();
 }
 
+// ---------------------------------------------------------------------------------- fused encoder head, all-tensor-core (16x nets)
+// Same fusion as conv_head_kernel, but conv11 (3 -> 16) also runs on tcgen05:
+//  * the image tile is staged as RGB0 float4 pixels (P4 with C = 4) with pitch 68;
+//  * with LBO = 16 bytes the second K-chunk of an MMA row is simply the NEXT PIXEL, so one K = 8 MMA covers the taps
+//    (dy,dx) and (dy,dx+1): 3x3 taps = 6 MMAs per 128 positions (weights of the padding channel / 4th tap are zero);
+//  * the conv11 accumulators are converted (bias, ReLU, TF32 round) into the two conv12 operand stages in shared
+//    memory, halo positions outside the image are patched with the mirrored values, and conv12 + pool run as in the
+//    generic kernel, re-using the same TMEM columns.
+struct HeadTcArgs {
+  const float* img;    // [3][H][W]
+  const float* w11tc;  // [3 dy][2][2 chunks][16][4] tf32 (conv0 folded)
+  const float* b11;    // [16]
+  ConvArgs c;          // conv12
+};
+constexpr int HT_PI = 68;                 // image tile pitch (pixels)
+constexpr int HT_IMG_ROWS = 21;           // 20 rows + 1 slack row for the tap offsets of garbage positions
+constexpr int HT_NB1 = 10;                // conv11 accumulator blocks: 18 rows * 68 = 1224 positions
+template <int EPI>
+__global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h) {
+  constexpr int N = 16;
+  using C = Cfg<N>;
+  constexpr int IMG_BYTES = HT_IMG_ROWS * HT_PI * 16;      // 22848 (>= pool buffer, which aliases it later)
+  constexpr int W11_BYTES = 6 * 2 * 16 * 16;               // 3072
+  constexpr int TMEM_COLS = 256;
+  static_assert(IMG_BYTES >= C::POOL_BYTES, "pool buffer aliases the image tile");
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* stages = smem;                                   // 2 x (operand tile + conv12 weights)
+  float4* img_s = reinterpret_cast<float4*>(smem + 2 * C::STAGE_BYTES);
+  float* poolbuf = reinterpret_cast<float*>(img_s);
+  uint8_t* w11_s = smem + 2 * C::STAGE_BYTES + IMG_BYTES;
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(w11_s + W11_BYTES);
+  uint64_t* img_ready = wfull + 1;
+  uint64_t* accum1_full = img_ready + 1;
+  uint64_t* op_ready = accum1_full + 1;
+  uint64_t* accum_full = op_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * C::TH;
+  const int H = h.c.H, W = h.c.W;
+  const long long HW = (long long)H * W;
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1); mbar_init(img_ready, 128); mbar_init(accum1_full, 1); mbar_init(op_ready, 128); mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, W11_BYTES + 2 * C::W_BYTES);
+      bulk_g2s(smem_u32(w11_s), h.w11tc, W11_BYTES, wfull);
+      bulk_g2s(smem_u32(stages + C::IN_BYTES), h.c.w, C::W_BYTES, wfull);
+      bulk_g2s(smem_u32(stages + C::STAGE_BYTES + C::IN_BYTES), h.c.w + C::W_BYTES / 4, C::W_BYTES, wfull);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(N);
+      mbar_wait(wfull, 0);
+      mbar_wait(img_ready, 0);
+      tc_fence_after();
+      const uint32_t i_base = smem_u32(img_s), w1_base = smem_u32(w11_s);
+#pragma unroll 1
+      for (int b = 0; b < HT_NB1; ++b) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint64_t ad = umma_desc(i_base + (uint32_t)(128 * b + dy * HT_PI + 2 * hh) * 16u, 16u, 128u);
+            const uint64_t bd = umma_desc(w1_base + (uint32_t)(dy * 2 + hh) * 512u, 256u, 128u);
+            umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, (dy > 0 || hh > 0) ? 1u : 0u);
+          }
+        }
+      }
+      tc_commit(accum1_full);
+      // ---- conv12 from the converted operand stages
+      mbar_wait(op_ready, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int kg = 0; kg < 2; ++kg) {
+        const uint32_t a_base = smem_u32(stages + kg * C::STAGE_BYTES);
+        const uint32_t w_base = a_base + C::IN_BYTES;
+#pragma unroll 1
+        for (int b = 0; b < C::NB; ++b) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint64_t ad = umma_desc(a_base + (uint32_t)(128 * b + dy * PW + dx) * 16u, C::P * 16u, 128u);
+            const uint64_t bd = umma_desc(w_base + (uint32_t)tap * 2u * N * 16u, N * 16u, 128u);
+            umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, (kg > 0 || tap > 0) ? 1u : 0u);
+          }
+        }
+      }
+      tc_commit(accum_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;            // 0..127
+    // ---- P0: RGB0 image tile (reflect-padded by 2; out-of-image conv11 positions are patched later)
+    for (int idx = et; idx < HT_IMG_ROWS * HT_PI; idx += 128) {
+      const int r = idx / HT_PI, qx = idx - r * HT_PI;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < 20) {
+        const int gy = wctb_reflect(y0 - 2 + r, H), gx = wctb_reflect(x0 - 2 + qx, W);
+        const float* p = h.img + (long long)gy * W + gx;
+        v = make_float4(wctb_tf32(__ldg(p)), wctb_tf32(__ldg(p + HW)), wctb_tf32(__ldg(p + 2 * HW)), 0.f);
+      }
+      img_s[idx] = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(img_ready)) : "memory");
+    // ---- E1: conv11 accumulators -> conv12 operand stages (pitch 64)
+    float bb[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bb[i] = __ldg(h.b11 + i);
+    float4* st0 = reinterpret_cast<float4*>(stages);
+    float4* st1 = reinterpret_cast<float4*>(stages + C::STAGE_BYTES);
+    mbar_wait(accum1_full, 0);
+    tc_fence_after();
+    for (int b = 0; b < HT_NB1; ++b) {
+      const int p = 128 * b + 32 * q + lane;
+      const int i = p / HT_PI, j = p - i * HT_PI;
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N), v);
+      if (i < C::TH + 2 && j < PW) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = wctb_tf32(wctb_relu(v[k] + bb[k]));
+        const int d = i * PW + j;
+        st0[d] = make_float4(v[0], v[1], v[2], v[3]);
+        st0[C::P + d] = make_float4(v[4], v[5], v[6], v[7]);
+        st1[d] = make_float4(v[8], v[9], v[10], v[11]);
+        st1[C::P + d] = make_float4(v[12], v[13], v[14], v[15]);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // reflection of the intermediate at true image borders (rows, then columns)
+    const int rt = (y0 == 0) ? 0 : -1;
+    const int rb = (H - y0 + 1 < C::TH + 2) ? (H - y0 + 1) : -1;
+    if (rt == 0 || rb >= 2) {
+      for (int e = et; e < 4 * PW; e += 128) {
+        const int c = e & 63, pl = e >> 6;
+        float4* base = (pl < 2 ? st0 : st1) + (pl & 1) * C::P;
+        if (rt == 0) base[c] = base[2 * PW + c];
+        if (rb >= 2) base[rb * PW + c] = base[(rb - 2) * PW + c];
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int cl = (x0 == 0) ? 0 : -1;
+    const int cr = (W - x0 + 1 < PW) ? (W - x0 + 1) : -1;
+    if ((cl == 0 || cr >= 2) && et < 4 * (C::TH + 2)) {
+      const int r = et % (C::TH + 2), pl = et / (C::TH + 2);
+      float4* base = (pl < 2 ? st0 : st1) + (pl & 1) * C::P;
+      if (cl == 0) base[r * PW] = base[r * PW + 2];
+      if (cr >= 2) base[r * PW + cr] = base[r * PW + cr - 2];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(op_ready)) : "memory");
+    // ---- E2: conv12 epilogue (pool buffer aliases the image tile, which is dead by now)
+    conv_epilogue<N, C::NB, EPI>(h.c, accum_full, tmem_base, poolbuf, warp, lane, x0, y0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int EPI>
+int launch_head_tc(const HeadTcArgs& h, cudaStream_t st) {
+  using C = Cfg<16>;
+  constexpr int SMEM = 2 * C::STAGE_BYTES + HT_IMG_ROWS * HT_PI * 16 + 6 * 2 * 16 * 16 + 256 + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_head_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  dim3 grid((h.c.W + TW - 1) / TW, (h.c.H + C::TH - 1) / C::TH, 1);
+  if (grid.y > 65535) return WCTB_E_UNSUPPORTED;
+  conv_head_tc_kernel<EPI><<<grid, 192, SMEM, st>>>(h);
+  WCTB_RETURN_LAUNCH();
+}
+
 // ---------------------------------------------------------------------------------- fused decoder tail
 //   img = ReLU(conv11( reflect_pad( ReLU(conv12( reflect_pad(x) )) ) ))      x P4 16ch (full res) -> img NCHW 3ch
-// conv12 (16->16) runs on tcgen05 exactly like the generic kernel, but for an intermediate tile that is one pixel
-// larger on every side than the 14x60 final tile; its epilogue keeps the ReLU'd intermediate in shared memory (the
-// pipeline stages are free once the accumulators are complete), patches the halo positions that lie outside the
-// image with the mirrored intermediate values (reflection applies to the INTERMEDIATE, not to conv12's input), and
-// conv11 (16->3, N = 3 is not an MMA shape) is evaluated with FFMA from that tile and written as NCHW.
-// The 16-channel full-resolution conv12 output (64 B/px write + read) never goes to HBM.
-// UPSRC: the input is the half-resolution tensor and nearest-x2 upsampling (model_cd.py:261) is applied while the
+// Both convolutions run on tcgen05.  conv12 (16->16) is computed exactly like the generic kernel, for an
+// intermediate tile one pixel larger on every side than the 14x60 final tile.  Its epilogue keeps the ReLU'd,
+// TF32-rounded intermediate in shared memory, in the same [chunk][row*64+col] float4 layout -- i.e. it is already a
+// valid A operand -- patches the halo positions outside the image with the mirrored intermediate values (reflection
+// applies to the INTERMEDIATE, not to conv12's input), and conv11 (16->3, zero-padded to N = 16) is a second round of
+// MMAs over that tile into a second TMEM range; a final epilogue writes NCHW.  The 16-channel full-resolution
+// conv12 output (64 B/px write + read) never goes to HBM.
+// UPSRC: the input is the half-resolution tensor and nearest-x2 upsampling (model_cd.py:261) is applied while
 // producer warps fill the operand tile (generic loads), so the upsampled tensor never exists in HBM either.
 struct TailArgs {
   ConvArgs c;         // conv12: x (P4 16ch; [H/2][W/2] when UPSRC), w packed tf32, bias; y unused; H, W = OUTPUT size
-  const float* w11;   // [tap][16][3] fp32
+  const float* w11;   // conv11 zero-padded to 16 outputs, packed tf32 like any 16->16 layer
   const float* b11;   // [3]
   float* img;         // [3][H][W]
 };
 constexpr int TAIL_TH = 14, TAIL_TW = 60;
+constexpr int TAIL_IBP = 16 * PW + 8;      // intermediate plane pitch (float4) incl. slack for the tap offsets
 template <bool UPSRC>
 __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const TailArgs t) {
   constexpr int N = 16;
   using C = Cfg<N>;            // NB = 8 -> 16 intermediate rows x 62 valid intermediate columns
   constexpr int NSTAGE = 2;
+  constexpr int NB2 = TAIL_TH * PW / 128;    // 7 accumulator blocks for conv11
+  constexpr int TMEM_COLS = 256;             // [0,128) conv12, [128,240) conv11
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* stages = smem;
-  float4* ibuf = reinterpret_cast<float4*>(smem);                       // [4 chunks][16 rows * 64] -- reuses the stages
-  float4* w11_s = reinterpret_cast<float4*>(smem + NSTAGE * C::STAGE_BYTES);   // [tap][chunk][3] (4 cin each)
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * C::STAGE_BYTES + 108 * 16 + 16);
+  float4* ibuf = reinterpret_cast<float4*>(smem);                       // [4 chunks][TAIL_IBP] -- reuses the stages
+  uint8_t* w11_s = smem + NSTAGE * C::STAGE_BYTES;                      // 2 * W_BYTES: [kg][tap][2][16][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(w11_s + 2 * C::W_BYTES);
   uint64_t* empty = full + NSTAGE;
   uint64_t* accum_full = empty + NSTAGE;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
-  static_assert(4 * 16 * PW * 16 <= NSTAGE * C::STAGE_BYTES, "intermediate tile must fit in the freed stages");
+  uint64_t* w11_full = accum_full + 1;
+  uint64_t* ibuf_ready = w11_full + 1;
+  uint64_t* accum2_full = ibuf_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum2_full + 1);
+  static_assert(4 * TAIL_IBP * 16 <= NSTAGE * C::STAGE_BYTES, "intermediate tile must fit in the freed stages");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0f = blockIdx.x * TAIL_TW, y0f = blockIdx.y * TAIL_TH;     // final tile origin
@@ -463,15 +658,12 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, UPSRC ? 129 : 1); mbar_init(empty + s, 1); }
     mbar_init(accum_full, 1);
+    mbar_init(w11_full, 1);
+    mbar_init(ibuf_ready, 128);
+    mbar_init(accum2_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 108) {                     // epilogue threads stage the conv11 weights
-    const int i = threadIdx.x - 64;
-    const int o = i % 3, c4 = (i / 3) % 4, tap = i / 12;
-    const float* p = t.w11 + ((size_t)tap * 16 + c4 * 4) * 3 + o;
-    w11_s[i] = make_float4(p[0], p[3], p[6], p[9]);
-  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -479,14 +671,18 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
 
   if (warp == 0) {
     // ---- producer: weights always by bulk copy; input rows by bulk copy unless UPSRC
+    if (lane == 0) {
+      mbar_expect_tx(w11_full, 2 * C::W_BYTES);
+      bulk_g2s(smem_u32(w11_s), t.w11, 2 * C::W_BYTES, w11_full);
+    }
     if (!UPSRC) {
       // intermediate tile col j <-> input col gx = x0 - 1 + j (x0 may be -1)
       const int jlo = max(0, 1 - x0);                                     // first tile col with gx >= 0
       const int jhi = min(PW, W - x0 + 1);
       const int ncols = max(jhi - jlo, 0);
-      const uint32_t nrefl_l = (uint32_t)jlo;                             // gx = -1, -2 -> 1, 2
+      const uint32_t nrefl_l = (uint32_t)jlo;                             // gx = -2, -1 -> 2, 1
       const int jr = W - x0 + 1;                                          // tile col of gx == W
-      const uint32_t nrefl_r = (uint32_t)min(max(PW - jr, 0), 2);         // gx = W, W+1 -> W-2, W-3 (only 2 needed)
+      const uint32_t nrefl_r = (uint32_t)min(max(PW - jr, 0), 2);         // gx = W, W+1 -> W-2, W-3
       const uint32_t row_bytes = ((uint32_t)ncols + nrefl_l + nrefl_r) * 16u;
       const uint32_t stage_tx = (uint32_t)C::W_BYTES + 2u * (C::TH + 2) * row_bytes;
       for (int kg = 0; kg < nkg; ++kg) {
@@ -515,11 +711,32 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0)
+    if (lane == 0) {
       mma_issue_loop<N, NSTAGE, C::STAGE_BYTES, C::IN_BYTES, C::P, C::NB>(stages, full, empty, accum_full, tmem_base, nkg);
+      // ---- conv11 over the intermediate tile
+      mbar_wait(w11_full, 0);
+      mbar_wait(ibuf_ready, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(N);
+      const uint32_t a_base = smem_u32(ibuf), w_base = smem_u32(w11_s);
+#pragma unroll 1
+      for (int b = 0; b < NB2; ++b) {
+#pragma unroll 1
+        for (int kg = 0; kg < 2; ++kg) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint64_t ad = umma_desc(a_base + (uint32_t)(2 * kg * TAIL_IBP + 128 * b + dy * PW + dx) * 16u, TAIL_IBP * 16u, 128u);
+            const uint64_t bd = umma_desc(w_base + (uint32_t)((kg * 9 + tap) * 2) * N * 16u, N * 16u, 128u);
+            umma_tf32(tmem_base + 128u + (uint32_t)(b * N), ad, bd, idesc, (kg > 0 || tap > 0) ? 1u : 0u);
+          }
+        }
+      }
+      tc_commit(accum2_full);
+    }
     __syncwarp();
   } else if (warp < 6) {
-    // ---- epilogue: intermediate -> smem, border fix-up, conv11 by FFMA, NCHW store
+    // ---- epilogue 1: intermediate -> smem (TF32), border fix-up;  epilogue 2: conv11 accumulators -> NCHW
     const int q = warp & 3;
     const int et = threadIdx.x - 64;            // 0..127
     mbar_wait(accum_full, 0);
@@ -529,72 +746,47 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N), v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = wctb_relu(v[i] + __ldg(t.c.bias + i));
+      for (int i = 0; i < 16; ++i) v[i] = wctb_tf32(wctb_relu(v[i] + __ldg(t.c.bias + i)));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ibuf[j * (16 * PW) + p] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 4; ++j) ibuf[j * TAIL_IBP + p] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // reflection of the intermediate at true image borders: rows first, then columns (corners follow)
     const int rt = (y0 < 0) ? 0 : -1;                         // tile row holding global row -1
     const int rb = (H - y0 < 16) ? (H - y0) : -1;             // tile row holding global row H
-    for (int i = et; i < 4 * PW; i += 128) {
-      const int c = i & 63, ch = i >> 6;
-      if (rt == 0) ibuf[ch * (16 * PW) + c] = ibuf[ch * (16 * PW) + 2 * PW + c];
-      if (rb >= 2) ibuf[ch * (16 * PW) + rb * PW + c] = ibuf[ch * (16 * PW) + (rb - 2) * PW + c];
+    if (rt == 0 || rb >= 2) {
+      for (int i = et; i < 4 * PW; i += 128) {
+        const int c = i & 63, ch = i >> 6;
+        if (rt == 0) ibuf[ch * TAIL_IBP + c] = ibuf[ch * TAIL_IBP + 2 * PW + c];
+        if (rb >= 2) ibuf[ch * TAIL_IBP + rb * PW + c] = ibuf[ch * TAIL_IBP + (rb - 2) * PW + c];
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int cl = (x0 < 0) ? 0 : -1;
     const int cr = (W - x0 < PW) ? (W - x0) : -1;
-    if (et < 4 * 16) {
+    if ((cl == 0 || cr >= 2) && et < 4 * 16) {
       const int r = et & 15, ch = et >> 4;
-      if (cl == 0) ibuf[ch * (16 * PW) + r * PW] = ibuf[ch * (16 * PW) + r * PW + 2];
-      if (cr >= 2) ibuf[ch * (16 * PW) + r * PW + cr] = ibuf[ch * (16 * PW) + r * PW + cr - 2];
+      if (cl == 0) ibuf[ch * TAIL_IBP + r * PW] = ibuf[ch * TAIL_IBP + r * PW + 2];
+      if (cr >= 2) ibuf[ch * TAIL_IBP + r * PW + cr] = ibuf[ch * TAIL_IBP + r * PW + cr - 2];
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // conv11: strips of 4 consecutive final pixels per thread (15 strips per row x 14 rows)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes -> visible to tcgen05.mma
+    tc_fence_before();
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ibuf_ready)) : "memory");
+    // ---- final epilogue
     const float b0 = __ldg(t.b11), b1 = __ldg(t.b11 + 1), b2 = __ldg(t.b11 + 2);
-    for (int sidx = et; sidx < TAIL_TH * (TAIL_TW / 4); sidx += 128) {
-      const int r = sidx / (TAIL_TW / 4), c = (sidx - r * (TAIL_TW / 4)) * 4;
-      float acc[4][3];
-#pragma unroll
-      for (int px = 0; px < 4; ++px) { acc[px][0] = b0; acc[px][1] = b1; acc[px][2] = b2; }
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          float4 in[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) in[k] = ibuf[ch * (16 * PW) + (r + dy) * PW + c + k];
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const float4 w0 = w11_s[((dy * 3 + dx) * 4 + ch) * 3 + 0];
-            const float4 w1 = w11_s[((dy * 3 + dx) * 4 + ch) * 3 + 1];
-            const float4 w2 = w11_s[((dy * 3 + dx) * 4 + ch) * 3 + 2];
-#pragma unroll
-            for (int px = 0; px < 4; ++px) {
-              const float4 v = in[px + dx];
-              acc[px][0] = fmaf(v.x, w0.x, acc[px][0]); acc[px][0] = fmaf(v.y, w0.y, acc[px][0]);
-              acc[px][0] = fmaf(v.z, w0.z, acc[px][0]); acc[px][0] = fmaf(v.w, w0.w, acc[px][0]);
-              acc[px][1] = fmaf(v.x, w1.x, acc[px][1]); acc[px][1] = fmaf(v.y, w1.y, acc[px][1]);
-              acc[px][1] = fmaf(v.z, w1.z, acc[px][1]); acc[px][1] = fmaf(v.w, w1.w, acc[px][1]);
-              acc[px][2] = fmaf(v.x, w2.x, acc[px][2]); acc[px][2] = fmaf(v.y, w2.y, acc[px][2]);
-              acc[px][2] = fmaf(v.z, w2.z, acc[px][2]); acc[px][2] = fmaf(v.w, w2.w, acc[px][2]);
-            }
-          }
-        }
-      }
+    mbar_wait(accum2_full, 0);
+    tc_fence_after();
+    for (int b = 0; b < NB2; ++b) {
+      const int p = 128 * b + 32 * q + lane;
+      const int r = p >> 6, c = p & 63;
+      float v[4];
+      tmem_ld4(tmem_base + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)(b * N), v);
       const int gy = y0f + r, gx = x0f + c;
-      if (gy < H) {
-#pragma unroll
-        for (int o = 0; o < 3; ++o) {
-          float* dst = t.img + (long long)o * HW + (long long)gy * W + gx;
-          if (gx + 3 < W && ((((long long)o * HW + (long long)gy * W + gx) & 3) == 0)) {
-            *reinterpret_cast<float4*>(dst) = make_float4(wctb_relu(acc[0][o]), wctb_relu(acc[1][o]), wctb_relu(acc[2][o]), wctb_relu(acc[3][o]));
-          } else {
-#pragma unroll
-            for (int px = 0; px < 4; ++px) if (gx + px < W) dst[px] = wctb_relu(acc[px][o]);
-          }
-        }
+      if (c < TAIL_TW && gy < H && gx < W) {
+        const long long o = (long long)gy * W + gx;
+        t.img[o] = wctb_relu(v[0] + b0);
+        t.img[HW + o] = wctb_relu(v[1] + b1);
+        t.img[2 * HW + o] = wctb_relu(v[2] + b2);
       }
     }
   } else if (UPSRC) {
@@ -615,13 +807,13 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 template <bool UPSRC>
 int launch_tail(const TailArgs& t, cudaStream_t st) {
   using C = Cfg<16>;
-  constexpr int SMEM = 2 * C::STAGE_BYTES + 108 * 16 + 16 + 256 + 128;
+  constexpr int SMEM = 2 * C::STAGE_BYTES + 2 * C::W_BYTES + 256 + 128;
   static bool attr_done = false;
   if (!attr_done) {
     WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_tail_kernel<UPSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -772,4 +964,14 @@ extern "C" int wctb_conv_tail(const float* x_p4, const float* w12_packed, const 
   if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
   TailArgs t{ConvArgs{(const float4*)x_p4, w12_packed, b12, nullptr, H, W, Cin, Cmid, 0}, w11, b11, y_nchw};
   return upsample_input ? launch_tail<true>(t, (cudaStream_t)stream) : launch_tail<false>(t, (cudaStream_t)stream);
+}
+
+extern "C" int wctb_conv_head_tc(const float* x_nchw, const float* w11_tc, const float* b11, const float* w12_packed,
+                                 const float* b12, float* y_p4, int H, int W, int epilogue, int round_tf32, void* stream) {
+  if (!x_nchw || !w11_tc || !b11 || !w12_packed || !b12 || !y_p4 || H < 2 || W < 2) return WCTB_E_BADARG;
+  if (epilogue != WCTB_EPI_NONE && epilogue != WCTB_EPI_POOL2) return WCTB_E_BADARG;
+  if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
+  HeadTcArgs h{x_nchw, w11_tc, b11, ConvArgs{nullptr, w12_packed, b12, (float4*)y_p4, H, W, 16, 16, round_tf32}};
+  return epilogue == WCTB_EPI_POOL2 ? launch_head_tc<WCTB_EPI_POOL2>(h, (cudaStream_t)stream)
+                                    : launch_head_tc<WCTB_EPI_NONE>(h, (cudaStream_t)stream);
 }

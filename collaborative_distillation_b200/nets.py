@@ -19,6 +19,7 @@ from . import arch, ops
 from ._lib import WctbError
 
 FUSE_TAIL = True      # [x2 upsample +] conv12 + conv11 of the decoders in one kernel when the TF32 engine is active
+HEAD_TC = True        # 16x nets: conv11 of the fused head on the tensor cores too (else FFMA producers)
 FUSE_HEAD = True      # conv11+conv12(+pool) in one kernel when the TF32 engine is active
 _PRECISION = "tf32"   # "tf32": tcgen05 TF32 tensor-core engine where supported; "fp32": CUDA-core fp32 everywhere
 
@@ -102,13 +103,25 @@ class _Net(nn.Module):
             b = (b.double() + torch.einsum("ojyx,j->o", wd, b0)).float()
             w = torch.einsum("ojyx,ji->oiyx", wd, w0).float()
         engine = ops.ENGINE_FP32 if (first or last) else self._engine(L, precision)
-        return {"w": ops.pack_weights(w.contiguous(), engine), "b": b.contiguous().float(), "engine": engine}
+        out = {"w": ops.pack_weights(w.contiguous(), engine), "b": b.contiguous().float(), "engine": engine}
+        if first and precision == "tf32" and L["cout"] == 16:
+            out["w_tc"] = ops.pack_head_tc_weights(w)       # conv11 on the tensor cores (fused head of the 16x nets)
+        return out
 
     def packed(self, precision=None):
         precision = precision or _PRECISION
         key = self._cache_key(precision)
         if self._pack_cache.get("key") != key:
-            self._pack_cache = {"key": key, "layers": [self._pack_layer(i, precision) for i in range(len(self.layers))]}
+            layers = [self._pack_layer(i, precision) for i in range(len(self.layers))]
+            n = len(layers)
+            if (self.KIND == "dec" and n >= 3 and layers[n - 2]["engine"] == ops.ENGINE_TF32
+                    and ops.conv_tail_supported(self.layers[n - 2]["cin"], self.layers[n - 2]["cout"])):
+                # fused tail runs conv11 on the tensor cores too: zero-pad its 3 output channels to 16, pack as TF32
+                w = getattr(self, self.layers[n - 1]["name"]).weight.detach()
+                wp = torch.zeros(16, w.shape[1], 3, 3, device=w.device, dtype=torch.float32)
+                wp[:3] = w
+                layers[n - 1]["w_tail"] = ops.pack_weights(wp, ops.ENGINE_TF32)
+            self._pack_cache = {"key": key, "layers": layers}
         return self._pack_cache["layers"]
 
     @staticmethod
@@ -136,8 +149,11 @@ class _Encoder(_Net):
         if (FUSE_HEAD and n >= 2 and pk[1]["engine"] == ops.ENGINE_TF32
                 and ops.conv_head_supported(L0["cout"], self.layers[1]["cout"])):
             L1 = self.layers[1]
-            y = ops.conv_head(x, pk[0]["w"], pk[0]["b"], pk[1]["w"], pk[1]["b"], L0["cout"], L1["cout"],
-                              ops.EPI_POOL2 if L1["pool_after"] else ops.EPI_NONE, nxt(1))
+            epi = ops.EPI_POOL2 if L1["pool_after"] else ops.EPI_NONE
+            if HEAD_TC and "w_tc" in pk[0] and L1["cout"] == 16:
+                y = ops.conv_head_tc(x, pk[0]["w_tc"], pk[0]["b"], pk[1]["w"], pk[1]["b"], epi, nxt(1))
+            else:
+                y = ops.conv_head(x, pk[0]["w"], pk[0]["b"], pk[1]["w"], pk[1]["b"], L0["cout"], L1["cout"], epi, nxt(1))
             first = 2
         else:
             y = ops.conv3x3_first(x, pk[0]["w"], pk[0]["b"], L0["cout"], nxt(0))
@@ -168,8 +184,7 @@ class _Decoder(_Net):
             raise WctbError("feature map too small for ReflectionPad2d(1)")
         nxt = lambda i: (pk[i + 1]["engine"] == ops.ENGINE_TF32) if i + 1 < n else False
         # fused tail: [x2] conv12 + conv11 in one kernel (TF32 engine, 16-channel nets)
-        fuse_tail = FUSE_TAIL and n >= 3 and pk[n - 2]["engine"] == ops.ENGINE_TF32
-        fuse_tail = fuse_tail and ops.conv_tail_supported(self.layers[n - 2]["cin"], self.layers[n - 2]["cout"])
+        fuse_tail = FUSE_TAIL and n >= 3 and "w_tail" in pk[n - 1]
         last_plain = n - 2 if fuse_tail else n - 1
         up_in = False
         for i in range(last_plain):
@@ -179,7 +194,7 @@ class _Decoder(_Net):
                 epi, up_in = ops.EPI_NONE, True          # the tail kernel upsamples while it loads
             y = ops.conv3x3_p4(y, pk[i]["w"], pk[i]["b"], L["cout"], epi, nxt(i), pk[i]["engine"])
         if fuse_tail:
-            return ops.conv_tail(y, pk[n - 2]["w"], pk[n - 2]["b"], pk[n - 1]["w"], pk[n - 1]["b"], up_in)
+            return ops.conv_tail(y, pk[n - 2]["w"], pk[n - 2]["b"], pk[n - 1]["w_tail"], pk[n - 1]["b"], up_in)
         return ops.conv3x3_last(y, pk[n - 1]["w"], pk[n - 1]["b"])
 
     def first_layer_needs_tf32_input(self, precision=None):

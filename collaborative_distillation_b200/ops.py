@@ -9,7 +9,7 @@ from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, ENGINE_FP32, ENGINE_TF32, check 
 
 _launches = 0  # number of libwctb kernel-launching calls (bench.py reports kernels via its own table)
 KERNELS_PER_CALL = {"nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
-                    "conv_last": 1, "conv_head": 1, "conv_tail": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
+                    "conv_last": 1, "conv_head": 1, "conv_head_tc": 1, "conv_tail": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
                     "fold": 2}
 
 
@@ -117,17 +117,50 @@ def conv_head(x_nchw, w11, b11, w12_packed, b12, c1: int, cout: int, epilogue: i
     return y
 
 
+def tf32_round(t: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest (ties away) to TF32, for host-side weight preparation"""
+    u = t.contiguous().view(torch.int32)
+    return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_head_tc_weights(w_oihw: torch.Tensor) -> torch.Tensor:
+    """conv11 [16][3][3][3] (conv0 folded) -> [3 dy][2 h][2 c][16 n][4 e] TF32: chunk c of MMA (dy,h) = tap dx = 2h+c"""
+    t = torch.zeros(3, 2, 2, 16, 4, device=w_oihw.device, dtype=torch.float32)
+    for dy in range(3):
+        for hh in range(2):
+            for c in range(2):
+                dx = 2 * hh + c
+                if dx <= 2:
+                    t[dy, hh, c, :, :3] = w_oihw[:, :, dy, dx]
+    return tf32_round(t).contiguous()
+
+
+def conv_head_tc(x_nchw, w11_tc, b11, w12_packed, b12, epilogue: int, round_tf32: bool) -> torch.Tensor:
+    """all-tensor-core fused head of the 16x nets: image [1,3,H,W] -> P4 [4,Ho,Wo,4]"""
+    if x_nchw.dim() == 4:
+        x_nchw = x_nchw.squeeze(0)
+    _, H, W = x_nchw.shape
+    Ho, Wo = (H // 2, W // 2) if epilogue == EPI_POOL2 else (H, W)
+    y = torch.empty(4, Ho, Wo, 4, device=x_nchw.device, dtype=torch.float32)
+    check(_lib.load().wctb_conv_head_tc(_need(x_nchw), _need(w11_tc), _need(b11), _need(w12_packed), _need(b12), _need(y),
+                                        H, W, epilogue, int(round_tf32), _stream()), "conv_head_tc")
+    _count("conv_head_tc")
+    return y
+
+
 def conv_tail_supported(cin: int, cmid: int) -> bool:
     return bool(_lib.load().wctb_conv_tail_supported(cin, cmid))
 
 
 def conv_tail(x_p4, w12_packed, b12, w11, b11, upsample_input: bool) -> torch.Tensor:
-    """fused [nearest x2 +] conv12(16->16)+ReLU+conv11(16->3)+ReLU: P4 [4,h,w,4] -> image [1,3,H,W]"""
+    """fused [nearest x2 +] conv12(16->16)+ReLU+conv11(16->3)+ReLU: P4 [4,h,w,4] -> image [1,3,H,W].
+    w11: conv11 weights zero-padded to 16 outputs and packed for the TF32 engine; b11: [3]."""
     C4, h, w, _ = x_p4.shape
     H, W = (2 * h, 2 * w) if upsample_input else (h, w)
     y = torch.empty(1, 3, H, W, device=x_p4.device, dtype=torch.float32)
     check(_lib.load().wctb_conv_tail(_need(x_p4), _need(w12_packed), _need(b12), _need(w11), _need(b11), _need(y), H, W,
                                      C4 * 4, b12.numel(), int(upsample_input), _stream()), "conv_tail")
+    assert w11.numel() == 9 * 16 * 16
     _count("conv_tail")
     return y
 

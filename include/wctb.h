@@ -95,12 +95,19 @@ int wctb_conv_head(const float* x_nchw, const float* w11, const float* b11, cons
                    const float* b12, float* y_p4, int H, int W, int C1, int Cout, int epilogue,
                    int round_tf32, void* stream);
 
-/* fused decoder tail (TF32 engine): conv12 (16 -> 16, tcgen05) + ReLU + conv11 (16 -> 3, FFMA) + ReLU in one kernel,
+/* all-tensor-core variant of the fused head for the 16x nets (C1 = Cout = 16): conv11 runs on tcgen05 as well.
+ * w11_tc: [3 dy][2][2 chunks][16][4] fp32 rounded to TF32, chunk c of MMA (dy,h) holding tap dx = 2h + c (RGB + a zero
+ * channel; dx = 3 is all zero) -- built by the host from the conv0-folded conv11 weights (see nets.py).            */
+int wctb_conv_head_tc(const float* x_nchw, const float* w11_tc, const float* b11, const float* w12_packed,
+                      const float* b12, float* y_p4, int H, int W, int epilogue, int round_tf32, void* stream);
+
+/* fused decoder tail (TF32 engine): conv12 (16 -> 16) + ReLU + conv11 (16 -> 3) + ReLU in one kernel,
  * output NCHW [3][H][W]; the 16-channel full-resolution intermediate stays in shared memory.  With
  * upsample_input != 0, x_p4 is the HALF-resolution tensor [Cin/4][H/2][W/2][4] and nn.UpsamplingNearest2d(2) is applied
  * while the operand tile is filled, so the upsampled tensor never exists in HBM.
  * replaces: [y = unpool(y);] y = relu(conv12(pad(y))); y = relu(conv11(pad(y)))      (model_cd.py:291-293)
- * w12_packed: wctb_pack_weights_tf32 layout; w11: [tap][Cmid][3] fp32.  Supported (Cin,Cmid): (16,16).            */
+ * Both convs run on tcgen05.  w12_packed: wctb_pack_weights_tf32 layout; w11: conv11 OIHW weights zero-padded to 16 output
+ * channels and packed with wctb_pack_weights_tf32 (Cin = Cmid, Cout = 16); b11: [3].  Supported (Cin,Cmid): (16,16).   */
 int wctb_conv_tail_supported(int Cin, int Cmid);
 int wctb_conv_tail(const float* x_p4, const float* w12_packed, const float* b12, const float* w11,
                    const float* b11, float* y_nchw, int H, int W, int Cin, int Cmid, int upsample_input,
