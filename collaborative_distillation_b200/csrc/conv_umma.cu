@@ -24,6 +24,13 @@
 namespace {
 using namespace wctb_umma;
 
+// optional phase tracing (debug): clock64 stamps of a few CTAs, enabled through wctb_debug_set_trace
+__device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(int slot) {
+  long long* t = g_trace;
+  if (t && blockIdx.y == 10 && blockIdx.x < 8) t[blockIdx.x * 16 + slot] = clock64();
+}
+
 // ---------------------------------------------------------------------------------- geometry
 template <int N> struct Cfg {
   static constexpr int NB = (512 / N) < 8 ? (512 / N) : 8;     // accumulator blocks (128 positions each)
@@ -61,13 +68,15 @@ __device__ __forceinline__ void mma_issue_loop(uint8_t* stages, uint64_t* full, 
     tc_fence_after();
     const uint32_t a_base = smem_u32(stages + slot * STAGE_BYTES);
     const uint32_t w_base = a_base + IN_BYTES;
+    // taps outer, accumulator blocks inner: consecutive MMAs hit DIFFERENT accumulators, so the ~80-cycle
+    // accumulate-dependency latency of tcgen05.mma is hidden (measured: 80 -> ~10 cycles per N=16 MMA)
 #pragma unroll 1
-    for (int b = 0; b < NB; ++b) {
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap - dy * 3;
+      const uint64_t bd = umma_desc(w_base + (uint32_t)tap * 2u * N * 16u, N * 16u, 128u);
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int dy = tap / 3, dx = tap - dy * 3;
+      for (int b = 0; b < NB; ++b) {
         const uint64_t ad = umma_desc(a_base + (uint32_t)(128 * b + dy * PW + dx) * 16u, P * 16u, 128u);
-        const uint64_t bd = umma_desc(w_base + (uint32_t)tap * 2u * N * 16u, N * 16u, 128u);
         umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, (kg > 0 || tap > 0) ? 1u : 0u);
       }
     }
@@ -207,29 +216,33 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const ConvArgs a) {
     const uint32_t row_bytes = (uint32_t)(ncols + (left ? 1 : 0) + (right ? 1 : 0)) * 16u;
     const uint32_t stage_tx = (uint32_t)C::W_BYTES + 2u * (C::TH + 2) * row_bytes;
     const float* wblk = a.w + (size_t)nblk * nkg * (C::W_BYTES / 4);
-    for (int kg = 0; kg < nkg; ++kg) {
-      const int slot = kg % C::NSTAGE;
-      const uint32_t ph = (kg / C::NSTAGE) & 1;
-      mbar_wait(empty + slot, ph ^ 1);
-      uint8_t* st = stages + slot * C::STAGE_BYTES;
-      if (lane == 0) {
+    if (elect_one()) {
+      for (int kg = 0; kg < nkg; ++kg) {
+        const int slot = kg % C::NSTAGE;
+        const uint32_t ph = (kg / C::NSTAGE) & 1;
+        mbar_wait(empty + slot, ph ^ 1);
+        uint8_t* st = stages + slot * C::STAGE_BYTES;
         mbar_expect_tx(full + slot, stage_tx);
         bulk_g2s(smem_u32(st + C::IN_BYTES), wblk + (size_t)kg * (C::W_BYTES / 4), C::W_BYTES, full + slot);
-      }
-      __syncwarp();
-      for (int idx = lane; idx < 2 * (C::TH + 2); idx += 32) {
-        const int c = idx / (C::TH + 2), i = idx - c * (C::TH + 2);
-        const int gy = wctb_reflect(y0 - 1 + i, H);
-        const float4* src = a.x + (long long)(kg * 2 + c) * HW + (long long)gy * W;
-        const uint32_t dst = smem_u32(st + ((size_t)c * C::P + (size_t)i * PW) * 16);
-        bulk_g2s(dst + jlo * 16, src + (x0 - 1 + jlo), (uint32_t)ncols * 16u, full + slot);
-        if (left) bulk_g2s(dst, src + 1, 16u, full + slot);                          // gx = -1 -> 1
-        if (right) bulk_g2s(dst + jr * 16, src + (W - 2), 16u, full + slot);         // gx = W  -> W-2
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const float4* plane = a.x + (long long)(kg * 2 + c) * HW;
+#pragma unroll 1
+          for (int i = 0; i < C::TH + 2; ++i) {
+            const int gy = wctb_reflect(y0 - 1 + i, H);
+            const float4* src = plane + (long long)gy * W;
+            const uint32_t dst = smem_u32(st + ((size_t)c * C::P + (size_t)i * PW) * 16);
+            bulk_g2s(dst + jlo * 16, src + (x0 - 1 + jlo), (uint32_t)ncols * 16u, full + slot);
+            if (left) bulk_g2s(dst, src + 1, 16u, full + slot);                          // gx = -1 -> 1
+            if (right) bulk_g2s(dst + jr * 16, src + (W - 2), 16u, full + slot);         // gx = W  -> W-2
+          }
+        }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0)
+    if (elect_one())
       mma_issue_loop<N, C::NSTAGE, C::STAGE_BYTES, C::IN_BYTES, C::P, C::NB>(stages, full, empty, accum_full, tmem_base, nkg);
     __syncwarp();
   } else {
@@ -326,7 +339,7 @@ __global__ void __launch_bounds__(320, HeadCfg<C1, N>::MIN_CTAS) conv_head_kerne
 
   if (warp == 0) {
     // ---- conv12 weight loader
-    if (lane == 0) {
+    if (elect_one()) {
       for (int kg = 0; kg < nkg; ++kg) {
         const int slot = kg % HC::NSTAGE;
         mbar_wait(empty + slot, ((kg / HC::NSTAGE) & 1) ^ 1);
@@ -337,7 +350,7 @@ __global__ void __launch_bounds__(320, HeadCfg<C1, N>::MIN_CTAS) conv_head_kerne
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0)
+    if (elect_one())
       mma_issue_loop<N, HC::NSTAGE, C::STAGE_BYTES, C::IN_BYTES, C::P, C::NB>(stages, full, empty, accum_full, tmem_base, nkg);
     __syncwarp();
   } else if (warp < 6) {
@@ -462,6 +475,7 @@ __global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * C::TH;
   const int H = h.c.H, W = h.c.W;
   const long long HW = (long long)H * W;
+  if (threadIdx.x == 0) trace(0);
 
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1); mbar_init(img_ready, 128); mbar_init(accum1_full, 1); mbar_init(op_ready, 128); mbar_init(accum_full, 1);
@@ -472,9 +486,10 @@ __global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace(1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(wfull, W11_BYTES + 2 * C::W_BYTES);
       bulk_g2s(smem_u32(w11_s), h.w11tc, W11_BYTES, wfull);
       bulk_g2s(smem_u32(stages + C::IN_BYTES), h.c.w, C::W_BYTES, wfull);
@@ -482,22 +497,20 @@ __global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_tf32(N);
       mbar_wait(wfull, 0);
       mbar_wait(img_ready, 0);
       tc_fence_after();
       const uint32_t i_base = smem_u32(img_s), w1_base = smem_u32(w11_s);
 #pragma unroll 1
-      for (int b = 0; b < HT_NB1; ++b) {
+      for (int t6 = 0; t6 < 6; ++t6) {
+        const int dy = t6 >> 1, hh = t6 & 1;
+        const uint64_t bd = umma_desc(w1_base + (uint32_t)t6 * 512u, 256u, 128u);
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const uint64_t ad = umma_desc(i_base + (uint32_t)(128 * b + dy * HT_PI + 2 * hh) * 16u, 16u, 128u);
-            const uint64_t bd = umma_desc(w1_base + (uint32_t)(dy * 2 + hh) * 512u, 256u, 128u);
-            umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, (dy > 0 || hh > 0) ? 1u : 0u);
-          }
+        for (int b = 0; b < HT_NB1; ++b) {
+          const uint64_t ad = umma_desc(i_base + (uint32_t)(128 * b + dy * HT_PI + 2 * hh) * 16u, 16u, 128u);
+          umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, t6 > 0 ? 1u : 0u);
         }
       }
       tc_commit(accum1_full);
@@ -509,12 +522,12 @@ __global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h
         const uint32_t a_base = smem_u32(stages + kg * C::STAGE_BYTES);
         const uint32_t w_base = a_base + C::IN_BYTES;
 #pragma unroll 1
-        for (int b = 0; b < C::NB; ++b) {
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint64_t bd = umma_desc(w_base + (uint32_t)tap * 2u * N * 16u, N * 16u, 128u);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
+          for (int b = 0; b < C::NB; ++b) {
             const uint64_t ad = umma_desc(a_base + (uint32_t)(128 * b + dy * PW + dx) * 16u, C::P * 16u, 128u);
-            const uint64_t bd = umma_desc(w_base + (uint32_t)tap * 2u * N * 16u, N * 16u, 128u);
             umma_tf32(tmem_base + (uint32_t)(b * N), ad, bd, idesc, (kg > 0 || tap > 0) ? 1u : 0u);
           }
         }
@@ -526,18 +539,29 @@ __global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h
     const int q = warp & 3;
     const int et = threadIdx.x - 64;            // 0..127
     // ---- P0: RGB0 image tile (reflect-padded by 2; out-of-image conv11 positions are patched later)
-    for (int idx = et; idx < HT_IMG_ROWS * HT_PI; idx += 128) {
-      const int r = idx / HT_PI, qx = idx - r * HT_PI;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < 20) {
-        const int gy = wctb_reflect(y0 - 2 + r, H), gx = wctb_reflect(x0 - 2 + qx, W);
-        const float* p = h.img + (long long)gy * W + gx;
-        v = make_float4(wctb_tf32(__ldg(p)), wctb_tf32(__ldg(p + HW)), wctb_tf32(__ldg(p + 2 * HW)), 0.f);
+    {
+      constexpr int NIT = (HT_IMG_ROWS * HT_PI + 127) / 128;      // 12: all loads are issued before the first use
+      float r0[NIT], r1[NIT], r2[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int idx = et + 128 * k;
+        const int r = idx / HT_PI, qx = idx - r * HT_PI;
+        r0[k] = r1[k] = r2[k] = 0.f;
+        if (r < 20) {
+          const int gy = wctb_reflect(y0 - 2 + r, H), gx = wctb_reflect(x0 - 2 + qx, W);
+          const float* p = h.img + (long long)gy * W + gx;
+          r0[k] = __ldg(p); r1[k] = __ldg(p + HW); r2[k] = __ldg(p + 2 * HW);
+        }
       }
-      img_s[idx] = v;
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int idx = et + 128 * k;
+        if (idx < HT_IMG_ROWS * HT_PI) img_s[idx] = make_float4(wctb_tf32(r0[k]), wctb_tf32(r1[k]), wctb_tf32(r2[k]), 0.f);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(img_ready)) : "memory");
+    if (et == 0) trace(2);
     // ---- E1: conv11 accumulators -> conv12 operand stages (pitch 64)
     float bb[16];
 #pragma unroll
@@ -546,6 +570,7 @@ __global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h
     float4* st1 = reinterpret_cast<float4*>(stages + C::STAGE_BYTES);
     mbar_wait(accum1_full, 0);
     tc_fence_after();
+    if (et == 0) trace(3);
     for (int b = 0; b < HT_NB1; ++b) {
       const int p = 128 * b + 32 * q + lane;
       const int i = p / HT_PI, j = p - i * HT_PI;
@@ -585,11 +610,16 @@ __global__ void __launch_bounds__(192, 2) conv_head_tc_kernel(const HeadTcArgs h
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(op_ready)) : "memory");
+    if (et == 0) trace(4);
+    mbar_wait(accum_full, 0);
+    if (et == 0) trace(5);
     // ---- E2: conv12 epilogue (pool buffer aliases the image tile, which is dead by now)
     conv_epilogue<N, C::NB, EPI>(h.c, accum_full, tmem_base, poolbuf, warp, lane, x0, y0, 0);
+    if (et == 0) trace(6);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace(7);
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
@@ -671,7 +701,8 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
 
   if (warp == 0) {
     // ---- producer: weights always by bulk copy; input rows by bulk copy unless UPSRC
-    if (lane == 0) {
+    const bool elected = elect_one();
+    if (elected) {
       mbar_expect_tx(w11_full, 2 * C::W_BYTES);
       bulk_g2s(smem_u32(w11_s), t.w11, 2 * C::W_BYTES, w11_full);
     }
@@ -685,25 +716,27 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
       const uint32_t nrefl_r = (uint32_t)min(max(PW - jr, 0), 2);         // gx = W, W+1 -> W-2, W-3
       const uint32_t row_bytes = ((uint32_t)ncols + nrefl_l + nrefl_r) * 16u;
       const uint32_t stage_tx = (uint32_t)C::W_BYTES + 2u * (C::TH + 2) * row_bytes;
-      for (int kg = 0; kg < nkg; ++kg) {
-        const int slot = kg;
-        uint8_t* st = stages + slot * C::STAGE_BYTES;
-        if (lane == 0) {
-          mbar_expect_tx(full + slot, stage_tx);
-          bulk_g2s(smem_u32(st + C::IN_BYTES), t.c.w + (size_t)kg * (C::W_BYTES / 4), C::W_BYTES, full + slot);
-        }
-        __syncwarp();
-        for (int idx = lane; idx < 2 * (C::TH + 2); idx += 32) {
-          const int c = idx / (C::TH + 2), i = idx - c * (C::TH + 2);
-          const int gy = wctb_reflect(y0 - 1 + i, H);
-          const float4* src = t.c.x + (long long)(kg * 2 + c) * HW + (long long)gy * W;
-          const uint32_t dst = smem_u32(st + ((size_t)c * C::P + (size_t)i * PW) * 16);
-          if (ncols > 0) bulk_g2s(dst + jlo * 16, src + (x0 - 1 + jlo), (uint32_t)ncols * 16u, full + slot);
-          for (uint32_t k = 0; k < nrefl_l; ++k) bulk_g2s(dst + k * 16, src + wctb_reflect(x0 - 1 + (int)k, W), 16u, full + slot);
-          for (uint32_t k = 0; k < nrefl_r; ++k) bulk_g2s(dst + (jr + k) * 16, src + wctb_reflect(W + (int)k, W), 16u, full + slot);
+      if (elected) {
+        for (int kg = 0; kg < nkg; ++kg) {
+          uint8_t* st = stages + kg * C::STAGE_BYTES;
+          mbar_expect_tx(full + kg, stage_tx);
+          bulk_g2s(smem_u32(st + C::IN_BYTES), t.c.w + (size_t)kg * (C::W_BYTES / 4), C::W_BYTES, full + kg);
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const float4* plane = t.c.x + (long long)(kg * 2 + c) * HW;
+#pragma unroll 1
+            for (int i = 0; i < C::TH + 2; ++i) {
+              const int gy = wctb_reflect(y0 - 1 + i, H);
+              const float4* src = plane + (long long)gy * W;
+              const uint32_t dst = smem_u32(st + ((size_t)c * C::P + (size_t)i * PW) * 16);
+              if (ncols > 0) bulk_g2s(dst + jlo * 16, src + (x0 - 1 + jlo), (uint32_t)ncols * 16u, full + kg);
+              for (uint32_t k = 0; k < nrefl_l; ++k) bulk_g2s(dst + k * 16, src + wctb_reflect(x0 - 1 + (int)k, W), 16u, full + kg);
+              for (uint32_t k = 0; k < nrefl_r; ++k) bulk_g2s(dst + (jr + k) * 16, src + wctb_reflect(W + (int)k, W), 16u, full + kg);
+            }
+          }
         }
       }
-    } else if (lane == 0) {
+    } else if (elected) {
       for (int kg = 0; kg < nkg; ++kg) {
         mbar_expect_tx(full + kg, C::W_BYTES);
         bulk_g2s(smem_u32(stages + kg * C::STAGE_BYTES + C::IN_BYTES), t.c.w + (size_t)kg * (C::W_BYTES / 4), C::W_BYTES, full + kg);
@@ -711,7 +744,7 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       mma_issue_loop<N, NSTAGE, C::STAGE_BYTES, C::IN_BYTES, C::P, C::NB>(stages, full, empty, accum_full, tmem_base, nkg);
       // ---- conv11 over the intermediate tile
       mbar_wait(w11_full, 0);
@@ -720,16 +753,14 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
       constexpr uint32_t idesc = umma_idesc_tf32(N);
       const uint32_t a_base = smem_u32(ibuf), w_base = smem_u32(w11_s);
 #pragma unroll 1
-      for (int b = 0; b < NB2; ++b) {
-#pragma unroll 1
-        for (int kg = 0; kg < 2; ++kg) {
+      for (int kt = 0; kt < 18; ++kt) {
+        const int kg = kt / 9, tap = kt - kg * 9;
+        const int dy = tap / 3, dx = tap - dy * 3;
+        const uint64_t bd = umma_desc(w_base + (uint32_t)(kt * 2) * N * 16u, N * 16u, 128u);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint64_t ad = umma_desc(a_base + (uint32_t)(2 * kg * TAIL_IBP + 128 * b + dy * PW + dx) * 16u, TAIL_IBP * 16u, 128u);
-            const uint64_t bd = umma_desc(w_base + (uint32_t)((kg * 9 + tap) * 2) * N * 16u, N * 16u, 128u);
-            umma_tf32(tmem_base + 128u + (uint32_t)(b * N), ad, bd, idesc, (kg > 0 || tap > 0) ? 1u : 0u);
-          }
+        for (int b = 0; b < NB2; ++b) {
+          const uint64_t ad = umma_desc(a_base + (uint32_t)(2 * kg * TAIL_IBP + 128 * b + dy * PW + dx) * 16u, TAIL_IBP * 16u, 128u);
+          umma_tf32(tmem_base + 128u + (uint32_t)(b * N), ad, bd, idesc, kt > 0 ? 1u : 0u);
         }
       }
       tc_commit(accum2_full);
@@ -796,10 +827,21 @@ __global__ void __launch_bounds__(UPSRC ? 320 : 192, 2) conv_tail_kernel(const T
     const long long HWs = (long long)Hs * Ws;
     for (int kg = 0; kg < nkg; ++kg) {
       float4* st = reinterpret_cast<float4*>(stages + kg * C::STAGE_BYTES);
-      for (int idx = tp; idx < 2 * (C::TH + 2) * PW; idx += 128) {
-        const int j = idx & 63, i = (idx >> 6) % (C::TH + 2), c = idx / (PW * (C::TH + 2));
-        const int gy = wctb_reflect(y0 - 1 + i, H), gx = wctb_reflect(x0 - 1 + j, W);
-        st[c * C::P + i * PW + j] = __ldg(t.c.x + (long long)(kg * 2 + c) * HWs + (long long)(gy >> 1) * Ws + (gx >> 1));
+      constexpr int NEL = 2 * (C::TH + 2) * PW;        // 2304 = 18 per thread, in 3 batches of 6 loads in flight
+#pragma unroll 1
+      for (int base = 0; base < NEL; base += 6 * 128) {
+        float4 v[6];
+        int dsto[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int idx = base + tp + 128 * k;
+          const int j = idx & 63, i = (idx >> 6) % (C::TH + 2), c = idx / (PW * (C::TH + 2));
+          const int gy = wctb_reflect(y0 - 1 + i, H), gx = wctb_reflect(x0 - 1 + j, W);
+          dsto[k] = c * C::P + i * PW + j;
+          v[k] = __ldg(t.c.x + (long long)(kg * 2 + c) * HWs + (long long)(gy >> 1) * Ws + (gx >> 1));
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st[dsto[k]] = v[k];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full + kg)) : "memory");
@@ -893,6 +935,53 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(float* __restrict
   if (warp == 0) tmem_dealloc<COLS>(tmem);
 }
 
+// ---------------------------------------------------------------------------------- MMA issue-rate microbenchmark (debug)
+// cycles per tcgen05.mma (M=128, K=8 tf32) for a given N and operand layout: 0 = SWIZZLE_NONE planes (what the conv
+// kernels use), 1 = SWIZZLE_128B rows (128 B per row, K advanced by 32 B inside the row), 2 = SWIZZLE_NONE with
+// LBO = 16 (the tap-pair trick).  Operand contents are irrelevant (uninitialised smem).
+template <int N>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int layout, int nacc, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 1 && elect_one()) {
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + 96 * 1024;
+    constexpr uint32_t idesc = umma_idesc_tf32(N);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < 4; ++k) {
+        uint64_t ad, bd;
+        if (layout == 1) {   // SWIZZLE_128B K-major: SBO = 1024, layout_type = 2
+          ad = (uint64_t)(((a0 + k * 32) >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+          bd = (uint64_t)(((b0 + k * 32) >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        } else if (layout == 2) {
+          ad = umma_desc(a0 + k * 1088, 16u, 128u);
+          bd = umma_desc(b0 + k * 2 * N * 16, N * 16u, 128u);
+        } else {
+          ad = umma_desc(a0 + k * 64 * 16, 18560u, 128u);
+          bd = umma_desc(b0 + k * 2 * N * 16, N * 16u, 128u);
+        }
+#pragma unroll 1
+        for (int b = 0; b < nacc; ++b) umma_tf32(tmem + (uint32_t)(b * N), ad, bd, idesc, 1u);
+      }
+    }
+    tc_commit(&bar);
+    mbar_wait(&bar, 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace
 
 int wctb_conv3x3_p4_tf32_impl(const float* x, const float* w, const float* bias, float* y, int H, int W, int Cin,
@@ -974,4 +1063,19 @@ extern "C" int wctb_conv_head_tc(const float* x_nchw, const float* w11_tc, const
   HeadTcArgs h{x_nchw, w11_tc, b11, ConvArgs{nullptr, w12_packed, b12, (float4*)y_p4, H, W, 16, 16, round_tf32}};
   return epilogue == WCTB_EPI_POOL2 ? launch_head_tc<WCTB_EPI_POOL2>(h, (cudaStream_t)stream)
                                     : launch_head_tc<WCTB_EPI_NONE>(h, (cudaStream_t)stream);
+}
+
+extern "C" int wctb_debug_set_trace(long long* buf) {
+  WCTB_CUDA_TRY(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+  return WCTB_OK;
+}
+
+extern "C" int wctb_debug_mma_rate(long long* out_cycles, int N, int layout, int nacc, int iters, int ctas, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = 200 * 1024;
+#define WCTB_MR(NN) case NN: WCTB_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    mma_rate_kernel<NN><<<ctas, 128, smem, st>>>(out_cycles, layout, nacc, iters); break;
+  switch (N) { WCTB_MR(16) WCTB_MR(32) WCTB_MR(64) WCTB_MR(128) WCTB_MR(256) default: return WCTB_E_UNSUPPORTED; }
+#undef WCTB_MR
+  WCTB_RETURN_LAUNCH();
 }

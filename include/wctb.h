@@ -166,6 +166,12 @@ int wctb_fold_wct_into_conv(const float* w_oihw, const float* bias, const float*
                             const float* mean_c, float* w_out, float* b_out, int Cin, int Cout,
                             void* stream);
 
+/* debug: when buf != NULL a few CTAs of the fused head record clock64() phase stamps into buf[128] (tools/trace_head.py) */
+int wctb_debug_set_trace(long long* buf);
+
+/* debug: cycles for iters*4*nacc tcgen05.mma (M=128,K=8 tf32) per CTA; layout 0 = planes (SWIZZLE_NONE), 1 = SWIZZLE_128B, 2 = LBO 16 */
+int wctb_debug_mma_rate(long long* out_cycles, int N, int layout, int nacc, int iters, int ctas, void* stream);
+
 /* ---- self tests (device-side descriptor / pipeline checks used by tests and smoke) ------- */
 int wctb_selftest_umma(float* out_128xN, const float* a_128xK, const float* b_NxK, int N, int K,
                        void* stream);
