@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, help="cfg2|cfg3|cfg4|weak (default: cfg3 at N=1, weak at N>1)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
-    ap.add_argument("--fold", type=int, default=0, help="fold the WCT matrix into the decoder's first conv")
+    ap.add_argument("--fold", type=int, default=1, help="fold the WCT matrix into the decoder's first conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -33,7 +33,9 @@ __device__ __forceinline__ void trace(int slot) {
 
 // ---------------------------------------------------------------------------------- geometry
 template <int N> struct Cfg {
-  static constexpr int NB = (512 / N) < 8 ? (512 / N) : 8;     // accumulator blocks (128 positions each)
+  // N <= 64: tiles sized so that TWO CTAs fit per SM (<= 256 TMEM columns, <= ~110 KB smem each): the epilogue of one
+  // overlaps the MMAs / loads of the other.  N >= 128 (low-resolution layers): one CTA per SM, 512 columns.
+  static constexpr int NB = N <= 32 ? 8 : (N == 64 ? 4 : (512 / N));   // accumulator blocks (128 positions each)
   static constexpr int TH = 2 * NB;                            // output rows per tile
   static constexpr int P = (TH + 2) * PW + 8;                  // pixel slots per chunk plane (+ slack for tap offsets)
   static constexpr int IN_BYTES = 2 * P * 16;                  // two 4-channel chunks
@@ -42,10 +44,13 @@ template <int N> struct Cfg {
   static constexpr int TMEM_COLS = (NB * N) < 32 ? 32 : (NB * N);
   static constexpr int POOL_BYTES = 2 * 64 * 20 * 4;           // double-buffered row-exchange for the pool epilogue
   static constexpr int AUX_BYTES = 1024;                       // barriers + tmem slot
-  static constexpr int NSTAGE_MAX = (227 * 1024 - POOL_BYTES - AUX_BYTES - 128) / STAGE_BYTES;
+  static constexpr int CTAS_PER_SM = (N <= 64) ? 2 : 1;
+  static constexpr int SMEM_BUDGET = (CTAS_PER_SM == 2 ? 112 : 227) * 1024;
+  static constexpr int NSTAGE_MAX = (SMEM_BUDGET - POOL_BYTES - AUX_BYTES - 128) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_MAX > 4 ? 4 : NSTAGE_MAX;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + POOL_BYTES + AUX_BYTES + 128;
   static_assert(NSTAGE >= 2, "pipeline needs two stages");
+  static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "TMEM budget");
 };
 
 struct ConvArgs {
@@ -176,7 +181,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint64_t* accum
 }
 
 template <int N, int EPI>
-__global__ void __launch_bounds__(192, 1) conv_umma_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(192, Cfg<N>::CTAS_PER_SM) conv_umma_kernel(const ConvArgs a) {
   using C = Cfg<N>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));

@@ -37,7 +37,7 @@ class WCT(nn.Module):
             setattr(self, "d%d" % k, nets.DECODERS[mode][k - 1](getattr(args, "d%d" % k, None)))
         self.tau = TAU
         self.dist = None          # set by parallel.StripGroup for multi-GPU runs
-        self.fold_into_decoder = False
+        self.fold_into_decoder = True   # csF = M(cF - mu) + b folded exactly into the decoder's first conv (no apply pass)
         self.overlap_style = True  # single-GPU stylize(): run the (content-independent) style branch on a side stream
         self._side = None
 
@@ -138,8 +138,10 @@ class WCT(nn.Module):
         side = self._side
         side.wait_stream(main)
         style_res = {}
-        with torch.cuda.stream(side):
-            for s in stages:
+
+        def style_branch(s):
+            # style encoder + statistics + eigensolve of stage s, on the side stream
+            with torch.cuda.stream(side):
                 s4 = getattr(self, "e%d" % s).forward_p4(style)
                 res = self._eig_one(s4)
                 del s4
@@ -148,16 +150,29 @@ class WCT(nn.Module):
                 for t in res:
                     t.record_stream(main)
                 style_res[s] = (res, ev)
+
+        style_branch(stages[0])
         img = content
         numpy_variant = bool(getattr(self.args, "numpy", False))
-        for _ in range(num_run):
-            for s in stages:
+        for run in range(num_run):
+            for i, s in enumerate(stages):
                 enc, dec = getattr(self, "e%d" % s), getattr(self, "d%d" % s)
                 c4 = enc.forward_p4(img)
-                c_mean, c_e, c_v = self._eig_one(c4, add_identity=numpy_variant)       # util_wct.py:143 (+I on content only)
+                C = c4.shape[0] * 4
+                n = float(c4.shape[1] * c4.shape[2])
+                gram = torch.zeros(1, C, C, device=c4.device, dtype=torch.float64)
+                c_mean = self._moments(c4, (0, c4.shape[1], 0, c4.shape[2]), n, gram[0])
+                if run == 0 and i + 1 < len(stages):
+                    # the next stage's style branch is released when this stage's (single-CTA) content eigensolve
+                    # starts, so its convolutions fill the SMs the eigensolve leaves idle
+                    ev_go = torch.cuda.Event()
+                    ev_go.record(main)
+                    side.wait_event(ev_go)
+                    style_branch(stages[i + 1])
+                c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant)   # util_wct.py:143: +I on content only
                 (s_mean, s_e, s_v), ev = style_res[s]
                 main.wait_event(ev)
-                m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
+                m, b, mc = ops.wct_matrix(c_e[0], c_v[0], c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
                 if self.fold_into_decoder:
                     L0 = getattr(dec, dec.layers[0]["name"])
                     w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)

@@ -209,8 +209,9 @@ def test_original_mode_modules_vs_oracle():
 
 # ------------------------------------------------------------------ end to end vs the reference goldens
 @pytest.mark.parametrize("precision,alpha,fold,rms_tol,max_tol", [
-    ("fp32", 1.0, False, 2e-4, 5e-3), ("fp32", 0.6, False, 2e-4, 5e-3), ("fp32", 1.0, True, 2e-4, 5e-3),
-    ("tf32", 1.0, False, 1e-2, 2e-1)])
+    # measured on B200 (final stage): fp32 6.5e-6 / 4.6e-5, fp32+fold 6.8e-6 / 6.3e-5, tf32 5.4e-3 / 3.5e-2
+    ("fp32", 1.0, False, 5e-5, 5e-4), ("fp32", 0.6, False, 5e-5, 5e-4), ("fp32", 1.0, True, 5e-5, 5e-4),
+    ("tf32", 1.0, False, 1e-2, 1e-1), ("tf32", 1.0, True, 1e-2, 1e-1)])
 def test_five_stage_stylize_vs_reference_golden(golden_dir, precision, alpha, fold, rms_tol, max_tol):
     g = np.load(os.path.join(golden_dir, "golden_16x.npz"))
     w = _wct16(precision)
@@ -225,7 +226,22 @@ def test_five_stage_stylize_vs_reference_golden(golden_dir, precision, alpha, fo
         assert tuple(img.shape) == tuple(ref.shape)             # 84x100 -> 80x96: bit-exact shape chain
         d = (img.cpu() - ref)
         rms = d.pow(2).mean().sqrt().item()
+        print("stage %d precision %s fold %s: rms %.3g max %.3g" % (s, precision, fold, rms, d.abs().max().item()))
         # errors compound over the stages (each stage re-encodes the previous output); image range is [0, ~1.4]
         assert rms <= rms_tol, "stage %d rms %g" % (s, rms)
         assert d.abs().max().item() <= max_tol, "stage %d max %g" % (s, d.abs().max().item())
     P.set_precision("tf32")
+
+
+def test_two_stream_stylize_equals_sequential(golden_dir):
+    g = np.load(os.path.join(golden_dir, "golden_16x.npz"))
+    w = _wct16("tf32")
+    P.weights.load_npz_into(w, os.path.join(golden_dir, "weights_16x.npz"))
+    content, style = torch.from_numpy(g["content"]).to(DEV), torch.from_numpy(g["style"]).to(DEV)
+    w.overlap_style = True
+    a = w.stylize(content, style, alpha=0.8, num_run=2)
+    w.overlap_style = False
+    b = w.stylize(content, style, alpha=0.8, num_run=2)
+    torch.cuda.synchronize()
+    assert a.shape == b.shape
+    assert (a - b).abs().max().item() <= 1e-5          # same kernels, same order per stream; fp64 atomics order only
