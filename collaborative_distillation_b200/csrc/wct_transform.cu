@@ -208,7 +208,7 @@ __device__ __forceinline__ void rr_pair(int round, int k, int n, int& p, int& q)
 }
 
 struct JacobiScales { double v[8]; };
-constexpr double JACOBI_TOL = 1e-14;
+constexpr double JACOBI_TOL = 1e-10;   // pair converged when |g_p.g_q| <= tol |g_p||g_q|; error in eigenvalues is 2nd order
 constexpr int JACOBI_MAX_SWEEPS = 40;
 
 // rotate columns gp, gq (length n) cooperatively by LANES lanes (a power of two <= 32) of one warp
@@ -227,10 +227,11 @@ __device__ __forceinline__ int jacobi_rotate(double* gp, double* gq, int n, int 
   }
   // converged pair: orthogonal to working precision, or one column is numerically null
   if (c * c <= JACOBI_TOL * JACOBI_TOL * a * b || a <= floor2 || b <= floor2) return 0;
-  double zeta = (b - a) / (2.0 * c);
-  double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-  double cs = rsqrt(1.0 + t * t);
-  double sn = cs * t;
+  // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b-a)/(2c), written with one sqrt, one division, one rsqrt
+  const double d = b - a, c2 = c + c;
+  const double t = c2 / (d + copysign(sqrt(fma(d, d, c2 * c2)), d));
+  const double cs = rsqrt(fma(t, t, 1.0));
+  const double sn = cs * t;
   for (int i = sub; i < n; i += LANES) {
     double x = gp[i], y = gq[i];
     gp[i] = cs * x - sn * y;
@@ -264,10 +265,11 @@ __device__ __forceinline__ int jacobi_rotate_reg(double* gp, double* gq, int n, 
     c += __shfl_xor_sync(mask, c, o);
   }
   if (c * c <= JACOBI_TOL * JACOBI_TOL * a * b || a <= floor2 || b <= floor2) return 0;
-  double zeta = (b - a) / (2.0 * c);
-  double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-  double cs = rsqrt(1.0 + t * t);
-  double sn = cs * t;
+  // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b-a)/(2c), written with one sqrt, one division, one rsqrt
+  const double d = b - a, c2 = c + c;
+  const double t = c2 / (d + copysign(sqrt(fma(d, d, c2 * c2)), d));
+  const double cs = rsqrt(fma(t, t, 1.0));
+  const double sn = cs * t;
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
     int i = sub + e * LANES;

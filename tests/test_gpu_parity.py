@@ -245,3 +245,26 @@ def test_two_stream_stylize_equals_sequential(golden_dir):
     torch.cuda.synchronize()
     assert a.shape == b.shape
     assert (a - b).abs().max().item() <= 1e-5          # same kernels, same order per stream; fp64 atomics order only
+
+
+def test_original_mode_five_stage_vs_oracle():
+    """--mode original (unpruned VGG-19 widths 64..512): all 5 stages incl. the C=256/512 cooperative Jacobi, the
+    (64,64) fused head and 256/512-channel tcgen05 layers, against the CPU oracle with the same random weights."""
+    ow = O.random_weights("original", seed=5)
+    g = torch.Generator().manual_seed(8)
+    content, style = torch.rand(1, 3, 96, 128, generator=g), torch.rand(1, 3, 80, 96, generator=g)
+    ref = O.stylize(ow, "original", content, style)
+    for precision, rms_tol, max_tol in (("fp32", 2e-4, 5e-3), ("tf32", 2e-2, 3e-1)):
+        P.set_precision(precision)
+        w = P.WCT(SimpleNamespace(mode="original", numpy=False))
+        for s in range(1, 6):
+            getattr(w, "e%d" % s).load_state_dict(ow["e%d" % s])
+            getattr(w, "d%d" % s).load_state_dict(ow["d%d" % s])
+        w = w.to(DEV)
+        out = w.stylize(content.to(DEV), style.to(DEV)).cpu()
+        assert out.shape == ref.shape
+        d = out - ref
+        rms, mx = d.pow(2).mean().sqrt().item(), d.abs().max().item()
+        print("original mode %s: rms %.3g max %.3g (image range [%.2f, %.2f])" % (precision, rms, mx, ref.min(), ref.max()))
+        assert rms <= rms_tol * max(1.0, ref.abs().max().item()) and mx <= max_tol * max(1.0, ref.abs().max().item())
+    P.set_precision("tf32")

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Eigensolver diagnostics on the benchmark workload: live rank, sweeps, time per solve."""
+import os, sys
+from types import SimpleNamespace
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import collaborative_distillation_b200 as P
+from collaborative_distillation_b200 import ops
+P.set_precision("tf32")
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+w = P.WCT(SimpleNamespace(mode="16x", numpy=False))
+P.weights.load_npz_into(w, os.path.join(root, "tests", "golden", "weights_16x.npz"))
+w = w.cuda()
+g = torch.Generator().manual_seed(0)
+x = torch.rand(1, 3, 2160, 3840, generator=g).cuda()
+for s in (5, 4, 3, 2, 1):
+    f = getattr(w, "e%d" % s).forward_p4(x)
+    C = f.shape[0] * 4
+    n = float(f.shape[1] * f.shape[2])
+    gram = torch.zeros(1, C, C, device="cuda", dtype=torch.float64)
+    mean = w._moments(f, (0, f.shape[1], 0, f.shape[2]), n, gram[0])
+    live = int((gram[0].diagonal() > 0).sum())
+    for _ in range(2):
+        ev, evec, sw = ops.eigh_jacobi(gram, [1.0 / (n - 1)], return_sweeps=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.eigh_jacobi(gram, [1.0 / (n - 1)])
+    e1.record(); torch.cuda.synchronize()
+    evs = ev[0].sort(descending=True).values
+    print("stage %d C=%3d live=%3d sweeps=%2d time=%.3f ms  lmax=%.3g  l[live-1]/lmax=%.2e" % (
+        s, C, live, int(sw[0]), e0.elapsed_time(e1) / 5, evs[0].item(), (evs[live - 1] / evs[0]).item()))
