@@ -71,7 +71,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -189,7 +189,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, help="cfg2|cfg3|cfg4|weak (default: cfg3 at N=1, weak at N>1)")
@@ -336,40 +336,70 @@ def main():
 
 
 def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
-    """Wrap ops.conv3x3_p4 with CUDA events for one pass; report the shape class with the largest time share."""
+    """One instrumented pass: CUDA events around every conv launch (generic, fused head, fused tail), grouped by kernel
+    shape class; report the class with the largest time share against the measured peaks."""
     peaks = measured_peaks()
     rec = {}
-    orig = ops.conv3x3_p4
     from collaborative_distillation_b200 import nets
+    originals = {}
 
-    def wrapped(x, w, b, cout, epilogue, round_tf32, engine):
+    def timed_call(key, fn, args, kw, flops_bytes):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        y = orig(x, w, b, cout, epilogue, round_tf32, engine)
+        y = fn(*args, **kw)
         e1.record()
-        C4, H, W, _ = x.shape
-        rec.setdefault((C4 * 4, cout, epilogue, engine), []).append((e0, e1, H, W, y.numel()))
+        fl, by = flops_bytes(y)
+        rec.setdefault(key, []).append((e0, e1, fl, by))
         return y
+
+    def wrap_p4(x, w, b, cout, epilogue, round_tf32, engine):
+        C4, H, W, _ = x.shape
+        cin = C4 * 4
+        key = ("conv_umma" if engine == 1 else "conv_p4_fp32", "%d->%d epi%d" % (cin, cout, epilogue))
+        return timed_call(key, originals["conv3x3_p4"], (x, w, b, cout, epilogue, round_tf32, engine), {},
+                          lambda y: (2.0 * 9 * cin * cout * H * W, 4.0 * (cin * H * W + y.numel())))
+
+    def wrap_head_tc(x, w11, b11, w12, b12, epilogue, round_tf32):
+        H, W = x.shape[-2:]
+        return timed_call(("conv_head_tc", "3->16->16 epi%d" % epilogue), originals["conv_head_tc"],
+                          (x, w11, b11, w12, b12, epilogue, round_tf32), {},
+                          lambda y: (2.0 * H * W * (9 + 9 * 3 * 16 + 9 * 16 * 16), 4.0 * (3 * H * W + y.numel())))
+
+    def wrap_head(x, w11, b11, w12, b12, c1, cout, epilogue, round_tf32):
+        H, W = x.shape[-2:]
+        return timed_call(("conv_head", "3->%d->%d epi%d" % (c1, cout, epilogue)), originals["conv_head"],
+                          (x, w11, b11, w12, b12, c1, cout, epilogue, round_tf32), {},
+                          lambda y: (2.0 * H * W * (9 + 9 * 3 * c1 + 9 * c1 * cout), 4.0 * (3 * H * W + y.numel())))
+
+    def wrap_tail(x, w12, b12, w11, b11, upsample_input):
+        return timed_call(("conv_tail", "16->16->3 up%d" % int(upsample_input)), originals["conv_tail"],
+                          (x, w12, b12, w11, b11, upsample_input), {},
+                          lambda y: (2.0 * y.shape[-2] * y.shape[-1] * 9 * (16 * 16 + 16 * 3), 4.0 * (x.numel() + y.numel())))
+
+    wrappers = {"conv3x3_p4": wrap_p4, "conv_head_tc": wrap_head_tc, "conv_head": wrap_head, "conv_tail": wrap_tail}
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ops.conv3x3_p4 = wrapped
-    nets.ops.conv3x3_p4 = wrapped
+    overlap_prev = getattr(wct, "overlap_style", False)
+    wct.overlap_style = False                       # single stream, so event pairs bracket exactly one kernel each
+    for name, fn in wrappers.items():
+        originals[name] = getattr(ops, name)
+        setattr(ops, name, fn)
     try:
+        step(content_d, style_d)                    # warm the single-stream path (allocator, first-use attributes)
+        rec.clear()
         torch.cuda.synchronize()
         t0.record()
         step(content_d, style_d)
         t1.record()
         torch.cuda.synchronize()
     finally:
-        ops.conv3x3_p4 = orig
-        nets.ops.conv3x3_p4 = orig
+        for name in wrappers:
+            setattr(ops, name, originals[name])
+        wct.overlap_style = overlap_prev
     step_ms = t0.elapsed_time(t1)
     rows = []
-    for (cin, cout, epi, engine), evs in rec.items():
-        ms = sum(a.elapsed_time(b) for a, b, *_ in evs)
-        fl = sum(2.0 * 9 * cin * cout * H * W for _, _, H, W, _ in evs)
-        by = sum(4.0 * (cin * H * W + yn) for _, _, H, W, yn in evs)     # algorithmic: read input once, write output once
-        rows.append({"cin": cin, "cout": cout, "epi": epi, "engine": "tf32" if engine == 1 else "fp32", "launches": len(evs),
-                     "ms": ms, "flops": fl, "bytes": by})
+    for (kern, shape), evs in rec.items():
+        rows.append({"kernel": kern, "shape": shape, "launches": len(evs), "ms": sum(a.elapsed_time(b) for a, b, _, _ in evs),
+                     "flops": sum(e[2] for e in evs), "bytes": sum(e[3] for e in evs)})
     rows.sort(key=lambda r: -r["ms"])
     conv_ms = sum(r["ms"] for r in rows)
     top = rows[0]
@@ -378,7 +408,7 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     ach_tf = top["flops"] / (top["ms"] / 1e3) / 1e12
     ach_gb = top["bytes"] / (top["ms"] / 1e3) / 1e9
     ai = top["flops"] / top["bytes"]
-    peak_tf = tf32_peak if top["engine"] == "tf32" else fp32_peak
+    peak_tf = fp32_peak if top["kernel"] == "conv_p4_fp32" else tf32_peak
     ridge = peak_tf * 1e12 / (peaks["hbm_gbs"] * 1e9)
     if ai < ridge:
         roof = {"bound": "hbm", "achieved": round(ach_gb, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -386,16 +416,20 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     else:
         roof = {"bound": "tensor", "achieved": round(ach_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
                 "frac": round(ach_tf / peak_tf, 4)}
+    # DRAM bytes (read+write) of ONE content-sized launch from `ncu --set full` (profiles/r01_fused_kernels_ncu_full.txt)
+    traffic = {("conv_head_tc", (2160, 3840)): 99572224 + 84228352, ("conv_tail", (2160, 3840)): 132837888 + 64769024}
+    tkey = (top["kernel"], tuple(content_d.shape[-2:]))
     roof.update({
-        "traffic": None, "peaks_source": peaks["source"],
-        "kernel": "conv3x3_p4 %s engine, Cin=%d Cout=%d epi=%d (%d launches/step, %.1f%% of step time)" % (
-            top["engine"], top["cin"], top["cout"], top["epi"], top["launches"], 100 * top["ms"] / step_ms),
+        "traffic": traffic.get(tkey), "traffic_note": "DRAM read+write of one content-image launch of this kernel (ncu --set full); algorithmic bytes of that launch: head 232.2 MB, tail 232.2 MB",
+        "peaks_source": peaks["source"],
+        "kernel": "%s %s (%d launches/step, %.1f%% of the single-stream step)" % (top["kernel"], top["shape"], top["launches"],
+                                                                                  100 * top["ms"] / step_ms),
         "arith_intensity_flop_per_byte": round(ai, 1), "achieved_tflops": round(ach_tf, 2), "achieved_gbs": round(ach_gb, 1),
-        "tensor_peak_note": "TF32 peak taken as bf16_tflops_sustained/2 (%s)" % peaks["source"] if top["engine"] == "tf32" else "fp32 CUDA-core peak 148 SM x 128 FMA x 1.9 GHz",
-        "conv_share_of_step": round(conv_ms / step_ms, 4),
-        "by_shape": [{"k": "%s %d->%d epi%d" % (r["engine"], r["cin"], r["cout"], r["epi"]), "ms": round(r["ms"], 3),
+        "tensor_peak_note": "TF32 peak = bf16_tflops_sustained/2 (%s); fp32 engine: 148 SM x 128 FMA x 1.9 GHz" % peaks["source"],
+        "conv_share_of_step": round(conv_ms / step_ms, 4), "single_stream_step_ms": round(step_ms, 3),
+        "by_shape": [{"k": "%s %s" % (r["kernel"], r["shape"]), "n": r["launches"], "ms": round(r["ms"], 3),
                       "tflops": round(r["flops"] / (r["ms"] / 1e3) / 1e12, 2), "gbs": round(r["bytes"] / (r["ms"] / 1e3) / 1e9, 1)}
-                     for r in rows[:8]],
+                     for r in rows[:10]],
     })
     return roof
 

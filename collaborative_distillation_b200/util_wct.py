@@ -40,6 +40,7 @@ class WCT(nn.Module):
         self.fold_into_decoder = True   # csF = M(cF - mu) + b folded exactly into the decoder's first conv (no apply pass)
         self.overlap_style = True  # single-GPU stylize(): run the (content-independent) style branch on a side stream
         self._side = None
+        self._main = None
 
     # ------------------------------------------------------------------ statistics -> (M, b, mean_c)
     def _moments(self, x_p4, region, count, gram_out):
@@ -130,18 +131,29 @@ class WCT(nn.Module):
         evals, evecs = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=add_identity)
         return mean, evals[0], evecs[0]
 
+    def _mark(self, stage, name):
+        """optional CUDA-event timeline of the critical path (tools/stage_timeline.py sets self.timeline = [])"""
+        tl = getattr(self, "timeline", None)
+        if tl is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            tl.append((stage, name, e))
+
     @torch.no_grad()
     def _stylize_two_streams(self, content, style, alpha, num_run, stages):
-        main = torch.cuda.current_stream()
+        """Content branch on a HIGH-priority stream, the whole (content-independent) style branch -- encoder,
+        statistics and eigensolve of every stage -- on a low-priority stream: style work fills the SMs whenever the
+        critical path leaves them idle (notably during the single-CTA content eigensolves) without delaying it."""
+        cur = torch.cuda.current_stream()
         if self._side is None:
-            self._side = torch.cuda.Stream()
-        side = self._side
-        side.wait_stream(main)
+            self._main = torch.cuda.Stream(priority=-1)
+            self._side = torch.cuda.Stream(priority=0)
+        main, side = self._main, self._side
+        main.wait_stream(cur)
+        side.wait_stream(cur)
         style_res = {}
-
-        def style_branch(s):
-            # style encoder + statistics + eigensolve of stage s, on the side stream
-            with torch.cuda.stream(side):
+        with torch.cuda.stream(side):
+            for s in stages:
                 s4 = getattr(self, "e%d" % s).forward_p4(style)
                 res = self._eig_one(s4)
                 del s4
@@ -150,37 +162,39 @@ class WCT(nn.Module):
                 for t in res:
                     t.record_stream(main)
                 style_res[s] = (res, ev)
-
-        style_branch(stages[0])
-        img = content
         numpy_variant = bool(getattr(self.args, "numpy", False))
-        for run in range(num_run):
-            for i, s in enumerate(stages):
-                enc, dec = getattr(self, "e%d" % s), getattr(self, "d%d" % s)
-                c4 = enc.forward_p4(img)
-                C = c4.shape[0] * 4
-                n = float(c4.shape[1] * c4.shape[2])
-                gram = torch.zeros(1, C, C, device=c4.device, dtype=torch.float64)
-                c_mean = self._moments(c4, (0, c4.shape[1], 0, c4.shape[2]), n, gram[0])
-                if run == 0 and i + 1 < len(stages):
-                    # the next stage's style branch is released when this stage's (single-CTA) content eigensolve
-                    # starts, so its convolutions fill the SMs the eigensolve leaves idle
-                    ev_go = torch.cuda.Event()
-                    ev_go.record(main)
-                    side.wait_event(ev_go)
-                    style_branch(stages[i + 1])
-                c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant)   # util_wct.py:143: +I on content only
-                (s_mean, s_e, s_v), ev = style_res[s]
-                main.wait_event(ev)
-                m, b, mc = ops.wct_matrix(c_e[0], c_v[0], c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
-                if self.fold_into_decoder:
-                    L0 = getattr(dec, dec.layers[0]["name"])
-                    w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
-                    img = dec.forward_p4(c4, first_override=(w, bb))
-                else:
-                    cs4 = ops.wct_apply(c4, m, b, mc, round_tf32=dec.first_layer_needs_tf32_input())
-                    del c4
-                    img = dec.forward_p4(cs4)
+        with torch.cuda.stream(main):
+            img = content
+            for run in range(num_run):
+                for s in stages:
+                    enc, dec = getattr(self, "e%d" % s), getattr(self, "d%d" % s)
+                    mark = self._mark
+                    mark(s, "start")
+                    c4 = enc.forward_p4(img)
+                    mark(s, "enc")
+                    C = c4.shape[0] * 4
+                    n = float(c4.shape[1] * c4.shape[2])
+                    gram = torch.zeros(1, C, C, device=c4.device, dtype=torch.float64)
+                    c_mean = self._moments(c4, (0, c4.shape[1], 0, c4.shape[2]), n, gram[0])
+                    mark(s, "stats")
+                    c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant)   # util_wct.py:143: +I on content only
+                    c_e, c_v = c_e[0], c_v[0]
+                    mark(s, "eig")
+                    (s_mean, s_e, s_v), ev = style_res[s]
+                    main.wait_event(ev)
+                    m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
+                    if self.fold_into_decoder:
+                        L0 = getattr(dec, dec.layers[0]["name"])
+                        w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
+                        img = dec.forward_p4(c4, first_override=(w, bb))
+                    else:
+                        cs4 = ops.wct_apply(c4, m, b, mc, round_tf32=dec.first_layer_needs_tf32_input())
+                        del c4
+                        img = dec.forward_p4(cs4)
+                    mark(s, "dec")
+            img.record_stream(cur)
+        cur.wait_stream(main)
+        cur.wait_stream(side)
         return img
 
     @torch.no_grad()
