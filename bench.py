@@ -286,9 +286,10 @@ def main():
 
     # ---- e2e: pinned host -> device -> stylize -> host, every step
     def e2e_step():
-        c = content_h.to(dev, non_blocking=True)
-        s = style_h.to(dev, non_blocking=True)
-        o = step(c, s)
+        if grp is None:
+            o = step(content_h, style_h)          # public API with pinned HOST tensors: H2D happens inside stylize()
+        else:
+            o = step(content_h.to(dev, non_blocking=True), style_h.to(dev, non_blocking=True))
         out_h[..., :o.shape[-2], :o.shape[-1]].copy_(o, non_blocking=True)
     for _ in range(2):
         e2e_step()

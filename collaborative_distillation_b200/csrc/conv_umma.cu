@@ -90,94 +90,95 @@ __device__ __forceinline__ void mma_issue_loop(uint8_t* stages, uint64_t* full, 
   tc_commit(accum_full);          // accumulators complete
 }
 
-// epilogue for the 4 warps owning the TMEM lane quarters: TMEM -> bias/ReLU/TF32-round -> (pool | up) -> P4 stores
+// epilogue for the 4 warps owning the TMEM lane quarters: TMEM -> bias/ReLU/TF32-round -> (pool | up) -> P4 stores.
+// Channel groups of 16 outer (bias in registers), accumulator blocks inner with the TMEM load of block b+1 in flight
+// while block b is processed.
 template <int N, int NB, int EPI>
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint64_t* accum_full, uint32_t tmem_base, float* poolbuf,
                                               int warp, int lane, int x0, int y0, int nblk) {
   const int H = a.H, W = a.W;
   const long long HW = (long long)H * W;
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    const float* bias = a.bias + nblk * N;
-    const int cplane0 = nblk * (N / 4);
-    if (EPI == WCTB_EPI_POOL2) {
-      const int Ho = H >> 1, Wo = W >> 1;
-      const long long HWo = (long long)Ho * Wo;
-      int it = 0;
-      for (int b = 0; b < NB; ++b) {
-        // block b = tile rows 2b (lanes 0..63) and 2b+1 (lanes 64..127)
+  const int q = warp & 3;           // TMEM lane quarter this warp may access
+  mbar_wait(accum_full, 0);
+  tc_fence_after();
+  const float* bias = a.bias + nblk * N;
+  const int cplane0 = nblk * (N / 4);
+  const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16);
+  const bool rnd = a.round_tf32 != 0;
+  int it = 0;
+#pragma unroll 1
+  for (int g = 0; g < N / 16; ++g) {
+    float bv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bv[i] = __ldg(bias + 16 * g + i);
+    uint32_t buf[2][16];
+    tmem_ld16_issue(tq + (uint32_t)(16 * g), buf[0]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b, ++it) {
+      uint32_t(&cur)[16] = buf[b & 1];
+      tmem_ld16_wait(cur);
+      if (b + 1 < NB) tmem_ld16_issue(tq + (uint32_t)((b + 1) * N + 16 * g), buf[(b + 1) & 1]);
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float t = wctb_relu(__uint_as_float(cur[i]) + bv[i]);
+        v[i] = rnd ? wctb_tf32(t) : t;
+      }
+      if (EPI == WCTB_EPI_POOL2) {
+        // block b = tile rows 2b (lanes 0..63) and 2b+1 (lanes 64..127): row exchange through shared memory
+        const int Ho = H >> 1, Wo = W >> 1;
+        const long long HWo = (long long)Ho * Wo;
         const int cpos = (q & 1) * 32 + lane;                    // column within the 64-pitch row
         const int oy = (y0 >> 1) + b, ox = (x0 + cpos) >> 1;
         const bool ok = (cpos < TW) && oy < Ho && ox < Wo && ((lane & 1) == 0);
-        for (int g = 0; g < N / 16; ++g, ++it) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N + 16 * g), v);
+        float* pb = poolbuf + (it & 1) * (64 * 20);
+        if (q >= 2) {
+          float4* d = reinterpret_cast<float4*>(pb + cpos * 20);
+          d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+          d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q < 2) {
+          const float4* s = reinterpret_cast<const float4*>(pb + cpos * 20);
+          const float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+          const float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float t = wctb_relu(v[i] + __ldg(bias + 16 * g + i));
-            v[i] = a.round_tf32 ? wctb_tf32(t) : t;
+            const float m = fmaxf(v[i], o[i]);
+            v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
           }
-          float* buf = poolbuf + (it & 1) * (64 * 20);
-          if (q >= 2) {
-            float4* d = reinterpret_cast<float4*>(buf + cpos * 20);
-            d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
-            d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (q < 2) {
-            const float4* s = reinterpret_cast<const float4*>(buf + cpos * 20);
-            float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
-            float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+          if (ok) {
+            const long long off = (long long)oy * Wo + ox;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float m = fmaxf(v[i], o[i]);
-              v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            }
-            if (ok) {
-              const long long off = (long long)oy * Wo + ox;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                a.y[(long long)(cplane0 + 4 * g + j) * HWo + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
+            for (int j = 0; j < 4; ++j)
+              a.y[(long long)(cplane0 + 4 * g + j) * HWo + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
-      }
-    } else {
-      for (int b = 0; b < NB; ++b) {
+      } else {
         const int p = 128 * b + 32 * q + lane;
         const int r = p >> 6, c = p & 63;
         const int gy = y0 + r, gx = x0 + c;
-        const bool ok = (c < TW) && gy < H && gx < W;
-        for (int g = 0; g < N / 16; ++g) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * N + 16 * g), v);
+        if ((c < TW) && gy < H && gx < W) {
+          if (EPI == WCTB_EPI_NONE) {
+            const long long off = (long long)gy * W + gx;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = wctb_relu(v[i] + __ldg(bias + 16 * g + i));
-            v[i] = a.round_tf32 ? wctb_tf32(t) : t;
-          }
-          if (ok) {
-            if (EPI == WCTB_EPI_NONE) {
-              const long long off = (long long)gy * W + gx;
+            for (int j = 0; j < 4; ++j)
+              a.y[(long long)(cplane0 + 4 * g + j) * HW + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {  // nearest x2
+            const int Wo = 2 * W;
+            const long long HWo = 4 * HW;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                a.y[(long long)(cplane0 + 4 * g + j) * HW + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {  // nearest x2
-              const int Wo = 2 * W;
-              const long long HWo = 4 * HW;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                float4* pl = a.y + (long long)(cplane0 + 4 * g + j) * HWo;
-                const long long off = (long long)(2 * gy) * Wo + 2 * gx;
-                pl[off] = o; pl[off + 1] = o; pl[off + Wo] = o; pl[off + Wo + 1] = o;
-              }
+            for (int j = 0; j < 4; ++j) {
+              const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              float4* pl = a.y + (long long)(cplane0 + 4 * g + j) * HWo;
+              const long long off = (long long)(2 * gy) * Wo + 2 * gx;
+              pl[off] = o; pl[off + 1] = o; pl[off + Wo] = o; pl[off + Wo + 1] = o;
             }
           }
         }
       }
     }
+  }
 }
 
 template <int N, int EPI>

@@ -133,8 +133,9 @@ class _Net(nn.Module):
 class _Encoder(_Net):
     KIND = "enc"
 
-    def forward_p4(self, x, precision=None):
-        """x [1,3,H,W] (or [3,H,W]) CUDA fp32 -> P4 feature [C/4,h,w,4]"""
+    def forward_p4(self, x, precision=None, round_output=False):
+        """x [1,3,H,W] (or [3,H,W]) CUDA fp32 -> P4 feature [C/4,h,w,4].  round_output: store the feature TF32-rounded
+        (rna) because a tensor-core layer consumes it directly (WCT matrix folded into the decoder's first conv)."""
         self._check_cuda(x)
         precision = precision or _PRECISION
         pk = self.packed(precision)
@@ -144,7 +145,7 @@ class _Encoder(_Net):
         sh, sw = arch.feature_hw(self.STAGE, H, W)
         if sh < 2 or sw < 2:
             raise WctbError("input %dx%d too small for stage %d (ReflectionPad2d needs >=2 px at the deepest level)" % (H, W, self.STAGE))
-        nxt = lambda i: pk[i + 1]["engine"] == ops.ENGINE_TF32 if i + 1 < n else False
+        nxt = lambda i: pk[i + 1]["engine"] == ops.ENGINE_TF32 if i + 1 < n else bool(round_output)
         L0 = self.layers[0]
         if (FUSE_HEAD and n >= 2 and pk[1]["engine"] == ops.ENGINE_TF32
                 and ops.conv_head_supported(L0["cout"], self.layers[1]["cout"])):

@@ -108,7 +108,7 @@ class WCT(nn.Module):
         enc, dec = getattr(self, "e%d" % stage), getattr(self, "d%d" % stage)
         sh = stage - 1
         s4 = enc.forward_p4(style)
-        c4 = enc.forward_p4(content)
+        c4 = enc.forward_p4(content, round_output=self.fold_into_decoder and dec.first_layer_needs_tf32_input())
         reg = lambda r: None if r is None else tuple(v >> sh for v in r)
         m, b, mc = self._wct_params(c4, s4, float(alpha), reg(c_region), reg(s_region), c_count, s_count)
         del s4
@@ -153,6 +153,8 @@ class WCT(nn.Module):
         side.wait_stream(cur)
         style_res = {}
         with torch.cuda.stream(side):
+            if not style.is_cuda:          # host buffer: the H2D copy rides on the style stream (overlaps the content copy)
+                style = style.to("cuda", torch.float32, non_blocking=True)
             for s in stages:
                 s4 = getattr(self, "e%d" % s).forward_p4(style)
                 res = self._eig_one(s4)
@@ -164,13 +166,13 @@ class WCT(nn.Module):
                 style_res[s] = (res, ev)
         numpy_variant = bool(getattr(self.args, "numpy", False))
         with torch.cuda.stream(main):
-            img = content
+            img = content if content.is_cuda else content.to("cuda", torch.float32, non_blocking=True)
             for run in range(num_run):
                 for s in stages:
                     enc, dec = getattr(self, "e%d" % s), getattr(self, "d%d" % s)
                     mark = self._mark
                     mark(s, "start")
-                    c4 = enc.forward_p4(img)
+                    c4 = enc.forward_p4(img, round_output=self.fold_into_decoder and dec.first_layer_needs_tf32_input())
                     mark(s, "enc")
                     C = c4.shape[0] * 4
                     n = float(c4.shape[1] * c4.shape[2])
@@ -201,10 +203,14 @@ class WCT(nn.Module):
     def stylize(self, content, style, alpha=1.0, num_run=1, stages=(5, 4, 3, 2, 1)):
         """content, style: [1,3,H,W] fp32 (CUDA, or CPU -> copied up).  Returns the stylized image on the GPU,
         un-clamped like the reference (WCT.py:120-125)."""
+        if self.dist is None and self.overlap_style:
+            # host (pinned) inputs are copied up on the two branch streams, device inputs are used in place
+            c = content if not content.is_cuda else content.float()
+            st = style if not style.is_cuda else style.float()
+            return self._stylize_two_streams(c.float() if not c.is_cuda else c, st.float() if not st.is_cuda else st,
+                                             alpha, num_run, tuple(stages))
         img = content.to("cuda", torch.float32)
         style = style.to("cuda", torch.float32)
-        if self.dist is None and self.overlap_style:
-            return self._stylize_two_streams(img, style, alpha, num_run, tuple(stages))
         for _ in range(num_run):
             for s in stages:
                 img = self.style_transfer_stage(s, img, style, alpha)
