@@ -70,7 +70,7 @@ extern "C" int wctb_channel_sum(const float* x, int C, int H, int W, int y0, int
 // C=32 -> (4, 8), C>=64 -> 64x64 blocks (4, 16) over the upper block triangle.
 // Flush with fp64 atomics (order-dependent only at the 1e-16 level).
 // ------------------------------------------------------------------------------------------
-template <int TR, int SIDE>
+template <int TR, int SIDE, typename T>
 __global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __restrict__ x, int C, int H, int W, int y0,
                                                             int x0, int wreg, long long npix, long long pix_per_cta,
                                                             const double* __restrict__ mean, double* __restrict__ G) {
@@ -80,9 +80,11 @@ __global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __rest
   constexpr int NG = 256 / TPG;
   constexpr int GP = (SIDE == 16) ? 64 : 128;      // pixels per stage
   constexpr int PITCH = GB + 2;                    // doubles; keeps 16-byte alignment of row starts
-  extern __shared__ __align__(16) double gsm[];
-  double(*sa)[PITCH] = reinterpret_cast<double(*)[PITCH]>(gsm);
-  double(*sb)[PITCH] = reinterpret_cast<double(*)[PITCH]>(gsm + (size_t)GP * PITCH);
+  // T = double: exact-product fp64 accumulation.  T = float (TF32 conv mode only): fp32 FFMA over the <= 32 pixels a
+  // thread sees per stage, flushed into fp64 after every stage (Gram error ~1e-7 relative, far below the TF32 conv noise).
+  extern __shared__ __align__(16) unsigned char gsm_raw[];
+  T(*sa)[PITCH] = reinterpret_cast<T(*)[PITCH]>(gsm_raw);
+  T(*sb)[PITCH] = reinterpret_cast<T(*)[PITCH]>(gsm_raw + (size_t)GP * PITCH * sizeof(T));
   const int nb = (C + GB - 1) / GB;
   int bi = 0, bj = 0;
   {
@@ -99,11 +101,12 @@ __global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __rest
   const int tid = threadIdx.x;
   const int grp = tid / TPG, tl = tid % TPG;
   const int ti = tl / SIDE, tj = tl % SIDE;
-  double acc[TR][TR];
+  T acc[TR][TR];
+  double dacc[TR][TR];
 #pragma unroll
   for (int u = 0; u < TR; ++u)
 #pragma unroll
-    for (int v = 0; v < TR; ++v) acc[u][v] = 0.0;
+    for (int v = 0; v < TR; ++v) { acc[u][v] = T(0); dacc[u][v] = 0.0; }
   const long long HW = (long long)H * W;
   const int chA = bi * GB, chB = bj * GB;
   for (long long p0 = pbeg; p0 < pend; p0 += GP) {
@@ -127,23 +130,29 @@ __global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __rest
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) sa[pp][ch4 * 4 + k] = va[k];
+      for (int k = 0; k < 4; ++k) sa[pp][ch4 * 4 + k] = (T)va[k];
       if (!diag) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sb[pp][ch4 * 4 + k] = vb[k];
+        for (int k = 0; k < 4; ++k) sb[pp][ch4 * 4 + k] = (T)vb[k];
       }
     }
     __syncthreads();
-    const double(*B)[PITCH] = diag ? sa : sb;
+    const T(*B)[PITCH] = diag ? sa : sb;
 #pragma unroll 4
     for (int pp = grp; pp < GP; pp += NG) {
-      double a[TR], b[TR];
+      T a[TR], b[TR];
 #pragma unroll
       for (int k = 0; k < TR; ++k) { a[k] = sa[pp][ti * TR + k]; b[k] = B[pp][tj * TR + k]; }
 #pragma unroll
       for (int u = 0; u < TR; ++u)
 #pragma unroll
         for (int v = 0; v < TR; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    if (sizeof(T) == 4) {
+#pragma unroll
+      for (int u = 0; u < TR; ++u)
+#pragma unroll
+        for (int v = 0; v < TR; ++v) { dacc[u][v] += (double)acc[u][v]; acc[u][v] = T(0); }
     }
   }
 #pragma unroll
@@ -152,21 +161,22 @@ __global__ void __launch_bounds__(256) centered_gram_kernel(const float4* __rest
     for (int v = 0; v < TR; ++v) {
       const int i = chA + ti * TR + u, j = chB + tj * TR + v;
       if (i < C && j < C) {
-        atomicAdd(G + (long long)i * C + j, acc[u][v]);
-        if (!diag) atomicAdd(G + (long long)j * C + i, acc[u][v]);
+        const double val = dacc[u][v] + (double)acc[u][v];
+        atomicAdd(G + (long long)i * C + j, val);
+        if (!diag) atomicAdd(G + (long long)j * C + i, val);
       }
     }
 }
 
-template <int TR, int SIDE>
+template <int TR, int SIDE, typename T>
 static int launch_gram(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1, const double* mean,
                        double* gram_out, cudaStream_t st) {
   constexpr int GB = SIDE * TR;
   constexpr int GP = (SIDE == 16) ? 64 : 128;
-  const size_t smem = (size_t)2 * GP * (GB + 2) * sizeof(double);
+  const size_t smem = (size_t)2 * GP * (GB + 2) * sizeof(T);
   static bool attr_done = false;
   if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(centered_gram_kernel<TR, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(centered_gram_kernel<TR, SIDE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int nb = (C + GB - 1) / GB, nblk = nb * (nb + 1) / 2;
@@ -176,7 +186,7 @@ static int launch_gram(const float* x, int C, int H, int W, int y0, int y1, int 
   per = ((per + GP - 1) / GP) * GP;
   if (per < 4 * GP) per = 4 * GP;
   dim3 grid((unsigned)((npix + per - 1) / per), nblk);
-  centered_gram_kernel<TR, SIDE><<<grid, 256, smem, st>>>((const float4*)x, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
+  centered_gram_kernel<TR, SIDE, T><<<grid, 256, smem, st>>>((const float4*)x, C, H, W, y0, x0, x1 - x0, npix, per, mean, gram_out);
   WCTB_RETURN_LAUNCH();
 }
 
@@ -186,10 +196,23 @@ extern "C" int wctb_centered_gram(const float* x, int C, int H, int W, int y0, i
       y0 >= y1 || x0 >= x1)
     return WCTB_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (C <= 16) return launch_gram<2, 8>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
-  if (C <= 24) return launch_gram<3, 8>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
-  if (C <= 32) return launch_gram<4, 8>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
-  return launch_gram<4, 16>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  if (C <= 16) return launch_gram<2, 8, double>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  if (C <= 24) return launch_gram<3, 8, double>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  if (C <= 32) return launch_gram<4, 8, double>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  return launch_gram<4, 16, double>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+}
+
+// fp32-product variant for the TF32 conv mode (see the kernel comment); same contract as wctb_centered_gram
+extern "C" int wctb_centered_gram_fast(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1,
+                                       const double* mean, double* gram_out, void* stream) {
+  if (!x || !mean || !gram_out || C <= 0 || (C & 3) || H <= 0 || W <= 0 || y0 < 0 || y1 > H || x0 < 0 || x1 > W ||
+      y0 >= y1 || x0 >= x1)
+    return WCTB_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 16) return launch_gram<2, 8, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  if (C <= 24) return launch_gram<3, 8, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  if (C <= 32) return launch_gram<4, 8, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  return launch_gram<4, 16, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -184,15 +184,16 @@ def channel_sum(x: torch.Tensor, region=None) -> torch.Tensor:
     return out
 
 
-def centered_gram(x: torch.Tensor, mean: torch.Tensor, region=None, out: torch.Tensor = None) -> torch.Tensor:
+def centered_gram(x: torch.Tensor, mean: torch.Tensor, region=None, out: torch.Tensor = None, fast: bool = False) -> torch.Tensor:
     """P4 map, fp64 mean [C] -> fp64 [C,C] sum (x-mean)(x-mean)^T over the region (accumulated into `out` if given)"""
     C4, H, W, _ = x.shape
     C = C4 * 4
     y0, y1, x0, x1 = region if region is not None else (0, H, 0, W)
     if out is None:
         out = torch.zeros(C, C, device=x.device, dtype=torch.float64)
-    check(_lib.load().wctb_centered_gram(_need(x), C, H, W, y0, y1, x0, x1, _need(mean, torch.float64),
-                                         _need(out, torch.float64), _stream()), "centered_gram")
+    fn = _lib.load().wctb_centered_gram_fast if fast else _lib.load().wctb_centered_gram
+    check(fn(_need(x), C, H, W, y0, y1, x0, x1, _need(mean, torch.float64), _need(out, torch.float64), _stream()),
+          "centered_gram")
     _count("centered_gram")
     return out
 

@@ -50,7 +50,7 @@ class WCT(nn.Module):
         if self.dist is not None:
             self.dist.allreduce_(s)
         mean = s / count
-        ops.centered_gram(x_p4, mean, region, out=gram_out)
+        ops.centered_gram(x_p4, mean, region, out=gram_out, fast=(nets.get_precision() == "tf32"))
         return mean
 
     def _wct_params(self, c_p4, s_p4, alpha, c_region=None, s_region=None, c_count=None, s_count=None):

@@ -127,6 +127,10 @@ int wctb_channel_sum(const float* x_p4, int C, int H, int W, int y0, int y1, int
                      double* sum_out, void* stream);
 int wctb_centered_gram(const float* x_p4, int C, int H, int W, int y0, int y1, int x0, int x1,
                        const double* mean, double* gram_out, void* stream);
+/* same contract; products and per-stage partial sums in fp32 (flushed to fp64 every 128 pixels): Gram accurate to ~1e-7
+ * relative -- used with the TF32 conv engine, whose feature noise (1e-3) is far larger.                              */
+int wctb_centered_gram_fast(const float* x_p4, int C, int H, int W, int y0, int y1, int x0, int x1,
+                            const double* mean, double* gram_out, void* stream);
 
 /* ---- symmetric eigendecomposition (one-sided Jacobi, fp64) ------------------------------
  * replaces: torch.svd(contentConv, some=False) / torch.svd(styleConv) (util_wct.py:74,100);

@@ -98,6 +98,8 @@ def test_moments_match_fp64(C, H, W, region):
     xc = xr - mean[:, None]
     ref = xc @ xc.t()
     assert (g - ref).abs().max().item() <= 1e-11 * ref.abs().max().item()      # fp64 DFMA accumulation
+    gf = ops.centered_gram(p4, mean.to(DEV), region, fast=True).cpu()
+    assert (gf - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()      # fp32 products / 128-px fp32 partial sums
     assert (g - g.t()).abs().max().item() <= 1e-13 * ref.abs().max().item()   # fp64 atomics: order-dependent last bits
 
 
