@@ -17,6 +17,12 @@ def launches() -> int:
     return _launches
 
 
+def add_launches(n: int):
+    """a replayed CUDA graph re-issues the kernels recorded at capture time"""
+    global _launches
+    _launches += int(n)
+
+
 def _count(kind):
     global _launches
     _launches += KERNELS_PER_CALL[kind]

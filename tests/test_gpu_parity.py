@@ -241,12 +241,21 @@ def test_two_stream_stylize_equals_sequential(golden_dir):
     P.weights.load_npz_into(w, os.path.join(golden_dir, "weights_16x.npz"))
     content, style = torch.from_numpy(g["content"]).to(DEV), torch.from_numpy(g["style"]).to(DEV)
     w.overlap_style = True
-    a = w.stylize(content, style, alpha=0.8, num_run=2)
+    w.use_graph = True
+    a = w.stylize(content, style, alpha=0.8, num_run=2)              # captures a CUDA graph
+    a2 = w.stylize(content * 0.5, style, alpha=0.8, num_run=2)       # replays it on new data
+    a3 = w.stylize(content, style, alpha=0.8, num_run=2)
+    w.use_graph = False
+    e = w.stylize(content, style, alpha=0.8, num_run=2)              # eager two-stream
+    e2 = w.stylize(content * 0.5, style, alpha=0.8, num_run=2)
     w.overlap_style = False
-    b = w.stylize(content, style, alpha=0.8, num_run=2)
+    b = w.stylize(content, style, alpha=0.8, num_run=2)              # sequential single stream
     torch.cuda.synchronize()
     assert a.shape == b.shape
-    assert (a - b).abs().max().item() <= 1e-5          # same kernels, same order per stream; fp64 atomics order only
+    # same kernels, same order per stream; fp64 atomics order only
+    for x, y in ((a, b), (a3, b), (e, b), (a2, e2)):
+        assert (x - y).abs().max().item() <= 1e-5
+    assert (a - a2).abs().max().item() > 1e-3                        # the replay really used the new input
 
 
 def test_original_mode_five_stage_vs_oracle():
