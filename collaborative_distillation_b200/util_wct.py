@@ -133,6 +133,17 @@ class WCT(nn.Module):
         evals, evecs = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=add_identity)
         return mean, evals[0], evecs[0]
 
+    @torch.no_grad()
+    def prepare_style(self, style, stages=(5, 4, 3, 2, 1)):
+        """The content-independent half of the path for one style image: per stage (mean, eigenvalues, eigenvectors) of the
+        style features (util_wct.py:93-100).  Pass the result as `style_cache=` to stylize() to reuse it across content
+        images (WCT.py pairs every content with every style and re-encodes the style each time)."""
+        style = style.to("cuda", torch.float32)
+        out = {}
+        for s in stages:
+            out[s] = self._eig_one(getattr(self, "e%d" % s).forward_p4(style))
+        return out
+
     def _mark(self, stage, name):
         """optional CUDA-event timeline of the critical path (tools/stage_timeline.py sets self.timeline = [])"""
         tl = getattr(self, "timeline", None)
@@ -142,7 +153,7 @@ class WCT(nn.Module):
             tl.append((stage, name, e))
 
     @torch.no_grad()
-    def _stylize_two_streams(self, content, style, alpha, num_run, stages):
+    def _stylize_two_streams(self, content, style, alpha, num_run, stages, style_cache=None):
         """Content branch on a HIGH-priority stream, the whole (content-independent) style branch -- encoder,
         statistics and eigensolve of every stage -- on a low-priority stream: style work fills the SMs whenever the
         critical path leaves them idle (notably during the single-CTA content eigensolves) without delaying it."""
@@ -154,10 +165,14 @@ class WCT(nn.Module):
         main.wait_stream(cur)
         side.wait_stream(cur)
         style_res = {}
+        if style_cache is not None:
+            style_res = {s: (style_cache[s], None) for s in stages}
         with torch.cuda.stream(side):
-            if not style.is_cuda:          # host buffer: the H2D copy rides on the style stream (overlaps the content copy)
+            if style_cache is not None:
+                pass
+            elif not style.is_cuda:        # host buffer: the H2D copy rides on the style stream (overlaps the content copy)
                 style = style.to("cuda", torch.float32, non_blocking=True)
-            for s in stages:
+            for s in (stages if style_cache is None else ()):
                 s4 = getattr(self, "e%d" % s).forward_p4(style)
                 res = self._eig_one(s4)
                 del s4
@@ -186,7 +201,8 @@ class WCT(nn.Module):
                     c_e, c_v = c_e[0], c_v[0]
                     mark(s, "eig")
                     (s_mean, s_e, s_v), ev = style_res[s]
-                    main.wait_event(ev)
+                    if ev is not None:
+                        main.wait_event(ev)
                     m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
                     if self.fold_into_decoder:
                         L0 = getattr(dec, dec.layers[0]["name"])
@@ -204,16 +220,18 @@ class WCT(nn.Module):
         return img
 
     @torch.no_grad()
-    def _stylize_graph(self, content, style, alpha, num_run, stages):
+    def _stylize_graph(self, content, style, alpha, num_run, stages, style_cache=None):
         """Replay (capture on first use) a CUDA graph of the two-stream schedule for this input shape: ~500 kernel launches
         become one graph launch, which removes the CPU launch cost that dominates small / medium images.
         Device inputs are copied into static buffers; PINNED host inputs are captured in place (their H2D copies become
         graph nodes on the two branch streams, so the style branch starts while the content image is still in flight) --
         the graph is then keyed on the host buffer addresses."""
+        if style_cache is not None:
+            style = content[..., :1, :1]       # unused placeholder with a stable shape
         host = (not content.is_cuda) and (not style.is_cuda) and content.is_pinned() and style.is_pinned()
         key = (tuple(content.shape), tuple(style.shape), float(alpha), int(num_run), tuple(stages), nets.get_precision(),
                bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)),
-               (content.data_ptr(), style.data_ptr()) if host else None)
+               (content.data_ptr(), style.data_ptr()) if host else None, id(style_cache) if style_cache is not None else None)
         ent = self._graphs.get(key)
         if ent is None:
             dev = torch.device("cuda", torch.cuda.current_device())
@@ -224,22 +242,22 @@ class WCT(nn.Module):
                 ss = torch.empty(style.shape, dtype=torch.float32, device=dev)
                 sc.copy_(content, non_blocking=True)
                 ss.copy_(style, non_blocking=True)
-            self._stylize_two_streams(sc, ss, alpha, num_run, stages)       # eager warm-up: packs weights, sets attributes
+            self._stylize_two_streams(sc, ss, alpha, num_run, stages, style_cache)   # eager warm-up: packs weights, sets attributes
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             try:
                 n0 = ops.launches()
                 with torch.cuda.graph(graph):
-                    out = self._stylize_two_streams(sc, ss, alpha, num_run, stages)
-                ent = (graph, sc, ss, out, ops.launches() - n0)
+                    out = self._stylize_two_streams(sc, ss, alpha, num_run, stages, style_cache)
+                ent = (graph, sc, ss, out, ops.launches() - n0, style_cache)
             except Exception as e:            # capture not possible on this setup: stay eager for this shape
                 print("wct-b200: CUDA graph capture failed (%s); running eagerly" % (e,))
                 torch.cuda.synchronize()
-                ent = (None, None, None, None, 0)
+                ent = (None, None, None, None, 0, None)
             self._graphs[key] = ent
-        graph, sc, ss, out, nlaunch = ent
+        graph, sc, ss, out, nlaunch, _keepalive = ent
         if graph is None:
-            return self._stylize_two_streams(content, style, alpha, num_run, stages)
+            return self._stylize_two_streams(content, style, alpha, num_run, stages, style_cache)
         if not host:
             sc.copy_(content, non_blocking=True)
             ss.copy_(style, non_blocking=True)
@@ -248,18 +266,16 @@ class WCT(nn.Module):
         return out.clone()
 
     @torch.no_grad()
-    def stylize(self, content, style, alpha=1.0, num_run=1, stages=(5, 4, 3, 2, 1)):
+    def stylize(self, content, style, alpha=1.0, num_run=1, stages=(5, 4, 3, 2, 1), style_cache=None):
         """content, style: [1,3,H,W] fp32 (CUDA, or CPU -> copied up).  Returns the stylized image on the GPU,
         un-clamped like the reference (WCT.py:120-125)."""
         if self.dist is None and self.overlap_style:
             # host (pinned) inputs are copied up on the two branch streams, device inputs are used in place
-            c = content if not content.is_cuda else content.float()
-            st = style if not style.is_cuda else style.float()
-            c = c.float() if not c.is_cuda else c
-            st = st.float() if not st.is_cuda else st
+            c = content.float()
+            st = c[..., :1, :1] if style_cache is not None else style.float()   # with a cache the style image is not needed
             if self.use_graph and getattr(self, "timeline", None) is None:
-                return self._stylize_graph(c, st, alpha, num_run, tuple(stages))
-            return self._stylize_two_streams(c, st, alpha, num_run, tuple(stages))
+                return self._stylize_graph(c, st, alpha, num_run, tuple(stages), style_cache)
+            return self._stylize_two_streams(c, st, alpha, num_run, tuple(stages), style_cache)
         img = content.to("cuda", torch.float32)
         style = style.to("cuda", torch.float32)
         for _ in range(num_run):

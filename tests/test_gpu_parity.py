@@ -279,3 +279,64 @@ def test_original_mode_five_stage_vs_oracle():
         print("original mode %s: rms %.3g max %.3g (image range [%.2f, %.2f])" % (precision, rms, mx, ref.min(), ref.max()))
         assert rms <= rms_tol * max(1.0, ref.abs().max().item()) and mx <= max_tol * max(1.0, ref.abs().max().item())
     P.set_precision("tf32")
+
+
+def test_full_size_properties_cfg3(golden_dir):
+    """BASELINE configs[2] size (3840x2160 content / 2000x2000 style, 16x): size-independent properties of the path.
+    (1) floor-pool shape chain is exact; (2) COLOURING PROPERTY of util_wct.py:117-126: the transformed feature has the
+    style's channel means and (on the directions the content spans) the style's covariance, i.e.
+    cov(csF) = Col Col^T restricted to the live content subspace; for full-rank stages cov(csF) == cov(sF);
+    (3) the decoders end in ReLU: output >= 0 and finite; (4) TF32 and fp32 engines agree on a full-size layer."""
+    w = _wct16("tf32")
+    P.weights.load_npz_into(w, os.path.join(golden_dir, "weights_16x.npz"))
+    g = torch.Generator().manual_seed(0)
+    content = torch.rand(1, 3, 2160, 3840, generator=g).to(DEV)
+    style = torch.rand(1, 3, 2000, 2000, generator=g).to(DEV)
+    for stage in (5, 3, 1):
+        enc = getattr(w, "e%d" % stage)
+        c4, s4 = enc.forward_p4(content), enc.forward_p4(style)
+        assert tuple(c4.shape[1:3]) == (2160 >> (stage - 1), 3840 >> (stage - 1))          # (1)
+        m, b, mc = w._wct_params(c4, s4, 1.0)
+        cs4 = ops.wct_apply(c4, m, b, mc)
+
+        def moments(x4):
+            n = float(x4.shape[1] * x4.shape[2])
+            mean = ops.channel_sum(x4) / n
+            return mean, ops.centered_gram(x4, mean) / (n - 1)
+        mu_cs, cov_cs = moments(cs4)
+        mu_s, cov_s = moments(s4)
+        live = cov_s.diagonal() > 0
+        assert (mu_cs - mu_s).abs().max().item() <= 1e-3 * mu_s.abs().max().item()            # (2) means
+        num = (cov_cs - cov_s)[live][:, live].norm().item()
+        den = cov_s[live][:, live].norm().item()
+        # dead content channels (structural, same for both images) carry nothing; live ones reproduce the style covariance
+        assert num <= 2e-3 * den, "stage %d: ||cov(csF) - cov(sF)|| / ||cov(sF)|| = %g" % (stage, num / den)
+        del c4, s4, cs4
+    out = w.stylize(content, style)
+    assert tuple(out.shape) == (1, 3, 2160, 3840)
+    assert torch.isfinite(out).all() and out.min().item() >= 0.0                                # (3)
+    # (4) one full-resolution layer, both engines, same TF32-representable operands
+    x = ops.nchw_to_p4(torch.rand(16, 2160, 3840, generator=g).to(DEV), round_tf32=True)
+    wt = ops.tf32_round((torch.randn(16, 16, 3, 3, generator=g) * 0.1).to(DEV))
+    bb = (torch.randn(16, generator=g) * 0.1).to(DEV)
+    y_tc = ops.conv3x3_p4(x, ops.pack_weights(wt, ops.ENGINE_TF32), bb, 16, ops.EPI_POOL2, False, ops.ENGINE_TF32)
+    y_32 = ops.conv3x3_p4(x, ops.pack_weights(wt, ops.ENGINE_FP32), bb, 16, ops.EPI_POOL2, False, ops.ENGINE_FP32)
+    assert tuple(y_tc.shape) == (4, 1080, 1920, 4)
+    assert (y_tc - y_32).abs().max().item() <= 2e-5 * max(1.0, y_32.abs().max().item())
+    P.set_precision("tf32")
+
+
+def test_style_cache_equals_full_path(golden_dir):
+    g = np.load(os.path.join(golden_dir, "golden_16x.npz"))
+    w = _wct16("tf32")
+    P.weights.load_npz_into(w, os.path.join(golden_dir, "weights_16x.npz"))
+    content, style = torch.from_numpy(g["content"]).to(DEV), torch.from_numpy(g["style"]).to(DEV)
+    full = w.stylize(content, style, alpha=0.9)
+    cache = w.prepare_style(style)
+    a = w.stylize(content, None, alpha=0.9, style_cache=cache)          # graph path, content-only graph
+    b = w.stylize(content.flip(-1), None, alpha=0.9, style_cache=cache)
+    w.use_graph = False
+    c = w.stylize(content.flip(-1), style, alpha=0.9)
+    torch.cuda.synchronize()
+    assert (a - full).abs().max().item() <= 1e-5
+    assert (b - c).abs().max().item() <= 1e-5
