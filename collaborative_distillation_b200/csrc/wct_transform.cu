@@ -458,13 +458,14 @@ extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double*
   for (int i = 0; i < 8; ++i) scale.v[i] = i < nprob ? scale_host[i] : 1.0;
   if (C <= 128) {
     size_t smem = (size_t)C * (C + 4) * sizeof(double);
-    // lanes per column pair / elements per lane: (8,16) covers k <= 128, (4,16) k <= 64, (4,8) k <= 32
+    // lanes per column pair x elements per lane (LANES*EPL >= C).  Measured on B200 (tools/eig_diag.py): ~512 threads is the
+    // sweet spot -- C=128: <8,16> 1.66 ms vs <16,8> 2.12 ms; C=64: <8,8> 0.57 ms vs <4,16> 0.76 ms.
     if (C > 64) {
       WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_smem_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       jacobi_smem_kernel<8, 16><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
     } else if (C > 32) {
-      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_smem_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      jacobi_smem_kernel<4, 16><<<nprob, 256, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_smem_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jacobi_smem_kernel<8, 8><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
     } else {
       jacobi_smem_kernel<4, 8><<<nprob, 256, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
     }
