@@ -47,7 +47,7 @@ SIGNATURES = {
 }
 
 WCTB_OK = 0
-EPI_NONE, EPI_POOL2, EPI_UP2 = 0, 1, 2
+EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3 = 0, 1, 2, 3
 ENGINE_FP32, ENGINE_TF32 = 0, 1
 
 

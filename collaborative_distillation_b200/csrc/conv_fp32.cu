@@ -315,7 +315,7 @@ extern "C" int wctb_conv3x3_p4(const float* x, const float* w, const float* bias
                                int Cout, int epilogue, int round_tf32, int engine, void* stream) {
   if (!x || !w || !bias || !y || H < 2 || W < 2 || Cin <= 0 || Cout <= 0 || (Cin & 3) || (Cout & 7))
     return WCTB_E_BADARG;
-  if (epilogue < 0 || epilogue > 2) return WCTB_E_BADARG;
+  if (epilogue < 0 || epilogue > 3 || (epilogue == WCTB_EPI_NCHW3 && engine != WCTB_ENGINE_TF32)) return WCTB_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == WCTB_ENGINE_TF32) return wctb_conv3x3_p4_tf32_impl(x, w, bias, y, H, W, Cin, Cout, epilogue, round_tf32, st);
   if (engine != WCTB_ENGINE_FP32) return WCTB_E_BADARG;

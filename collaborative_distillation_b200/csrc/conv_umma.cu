@@ -164,6 +164,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint64_t* accum
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               a.y[(long long)(cplane0 + 4 * g + j) * HW + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else if (EPI == WCTB_EPI_NCHW3) {   // channels 0..2 of the (zero-padded) last layer as NCHW planes
+            if (g == 0 && nblk == 0) {
+              float* img = reinterpret_cast<float*>(a.y);
+              const long long off = (long long)gy * W + gx;
+              img[off] = v[0]; img[HW + off] = v[1]; img[2 * HW + off] = v[2];
+            }
           } else {  // nearest x2
             const int Wo = 2 * W;
             const long long HWo = 4 * HW;
@@ -278,6 +284,7 @@ int launch_conv_epi(const ConvArgs& a, int epi, cudaStream_t st) {
   switch (epi) {
     case WCTB_EPI_NONE: return launch_conv<N, WCTB_EPI_NONE>(a, st);
     case WCTB_EPI_POOL2: return launch_conv<N, WCTB_EPI_POOL2>(a, st);
+    case WCTB_EPI_NCHW3: return N == 16 ? launch_conv<16, WCTB_EPI_NCHW3>(a, st) : WCTB_E_UNSUPPORTED;
     default: return launch_conv<N, WCTB_EPI_UP2>(a, st);
   }
 }

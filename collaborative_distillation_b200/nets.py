@@ -18,6 +18,7 @@ import torch.nn as nn
 from . import arch, ops
 from ._lib import WctbError
 
+LAST_TC = True        # TF32 mode: an unfused last decoder layer (C -> 3) runs on the tensor cores with N padded to 16
 FUSE_TAIL = True      # [x2 upsample +] conv12 + conv11 of the decoders in one kernel when the TF32 engine is active
 HEAD_TC = True        # 16x nets: conv11 of the fused head on the tensor cores too (else FFMA producers)
 FUSE_HEAD = True      # conv11+conv12(+pool) in one kernel when the TF32 engine is active
@@ -104,6 +105,12 @@ class _Net(nn.Module):
             w = torch.einsum("ojyx,ji->oiyx", wd, w0).float()
         engine = ops.ENGINE_FP32 if (first or last) else self._engine(L, precision)
         out = {"w": ops.pack_weights(w.contiguous(), engine), "b": b.contiguous().float(), "engine": engine}
+        if last and precision == "tf32" and LAST_TC and ops.tf32_supported(L["cin"], 16):
+            wp = torch.zeros(16, w.shape[1], 3, 3, device=w.device, dtype=torch.float32)
+            wp[:3] = w
+            bp = torch.zeros(16, device=w.device, dtype=torch.float32)
+            bp[:3] = b.float()
+            out["w_last_tc"], out["b_last_tc"] = ops.pack_weights(wp, ops.ENGINE_TF32), bp
         if first and precision == "tf32" and L["cout"] == 16:
             out["w_tc"] = ops.pack_head_tc_weights(w)       # conv11 on the tensor cores (fused head of the 16x nets)
         return out
@@ -183,7 +190,7 @@ class _Decoder(_Net):
         n = len(self.layers)
         if y.shape[1] < 2 or y.shape[2] < 2:
             raise WctbError("feature map too small for ReflectionPad2d(1)")
-        nxt = lambda i: (pk[i + 1]["engine"] == ops.ENGINE_TF32) if i + 1 < n else False
+        nxt = lambda i: (pk[i + 1]["engine"] == ops.ENGINE_TF32 or "w_last_tc" in pk[i + 1]) if i + 1 < n else False
         # fused tail: [x2] conv12 + conv11 in one kernel (TF32 engine, 16-channel nets)
         fuse_tail = FUSE_TAIL and n >= 3 and "w_tail" in pk[n - 1]
         last_plain = n - 2 if fuse_tail else n - 1
@@ -196,11 +203,15 @@ class _Decoder(_Net):
             y = ops.conv3x3_p4(y, pk[i]["w"], pk[i]["b"], L["cout"], epi, nxt(i), pk[i]["engine"])
         if fuse_tail:
             return ops.conv_tail(y, pk[n - 2]["w"], pk[n - 2]["b"], pk[n - 1]["w_tail"], pk[n - 1]["b"], up_in)
+        if "w_last_tc" in pk[n - 1]:      # TF32 mode: the C -> 3 layer on the tensor cores (3 outputs zero-padded to 16)
+            return ops.conv3x3_p4(y, pk[n - 1]["w_last_tc"], pk[n - 1]["b_last_tc"], 16, ops.EPI_NCHW3, False, ops.ENGINE_TF32)
         return ops.conv3x3_last(y, pk[n - 1]["w"], pk[n - 1]["b"])
 
     def first_layer_needs_tf32_input(self, precision=None):
         pk = self.packed(precision or _PRECISION)
-        return len(pk) > 1 and pk[0]["engine"] == ops.ENGINE_TF32
+        if len(pk) == 1:
+            return "w_last_tc" in pk[0]
+        return pk[0]["engine"] == ops.ENGINE_TF32
 
     def forward(self, y):
         self._check_cuda(y)

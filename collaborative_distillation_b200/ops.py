@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, ENGINE_FP32, ENGINE_TF32, check  # noqa: F401
+from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3, ENGINE_FP32, ENGINE_TF32, check  # noqa: F401
 
 _launches = 0  # number of libwctb kernel-launching calls (bench.py reports kernels via its own table)
 KERNELS_PER_CALL = {"nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
@@ -99,7 +99,10 @@ def conv3x3_p4(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, cout: int, epi
         Ho, Wo = 2 * H, 2 * W
     else:
         Ho, Wo = H, W
-    y = torch.empty(cout // 4, Ho, Wo, 4, device=x.device, dtype=torch.float32)
+    if epilogue == EPI_NCHW3:     # last decoder layer on the tensor cores: cout is the padded 16, output is the NCHW image
+        y = torch.empty(1, 3, H, W, device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty(cout // 4, Ho, Wo, 4, device=x.device, dtype=torch.float32)
     check(_lib.load().wctb_conv3x3_p4(_need(x), _need(w), _need(b), _need(y), H, W, C4 * 4, cout, epilogue,
                                       int(round_tf32), engine, _stream()), "conv3x3_p4")
     _count("conv_p4")

@@ -41,7 +41,9 @@ enum {
 enum {
   WCTB_EPI_NONE = 0,
   WCTB_EPI_POOL2 = 1, /* nn.MaxPool2d(2,2) floor mode fused on the output (model_cd.py:709,727) */
-  WCTB_EPI_UP2 = 2    /* nn.UpsamplingNearest2d(2) fused on the output   (model_cd.py:261,278) */
+  WCTB_EPI_UP2 = 2,   /* nn.UpsamplingNearest2d(2) fused on the output   (model_cd.py:261,278) */
+  WCTB_EPI_NCHW3 = 3  /* TF32 engine only: last decoder layer run with its 3 output channels zero-padded to 16; the
+                         epilogue writes channels 0..2 as NCHW planes [3][H][W] (model_cd.py:84 for stage 1)        */
 };
 
 /* which arithmetic a P4->P4 conv uses */
