@@ -41,6 +41,7 @@ class WCT(nn.Module):
         self.overlap_style = True  # single-GPU stylize(): run the (content-independent) style branch on a side stream
         self._side = None
         self._main = None
+        self.fast_stats = True     # TF32 mode, single GPU: fp32-product Gram (see _moments)
         self.use_graph = True      # single-GPU stylize(): capture the two-stream schedule in a CUDA graph per input shape
         self._graphs = {}
 
@@ -52,7 +53,10 @@ class WCT(nn.Module):
         if self.dist is not None:
             self.dist.allreduce_(s)
         mean = s / count
-        ops.centered_gram(x_p4, mean, region, out=gram_out, fast=(nets.get_precision() == "tf32"))
+        # fp32-product Gram only on a single GPU: its partial sums depend on the pixel partition (1e-7 relative), which the
+        # TF32 pipeline amplifies through the whitening; the sharded path keeps the fp64 Gram so that strips stay
+        # tile-invariant (sharded == single GPU to fp64 summation order).
+        ops.centered_gram(x_p4, mean, region, out=gram_out, fast=(self.fast_stats and nets.get_precision() == "tf32" and self.dist is None))
         return mean
 
     def _wct_params(self, c_p4, s_p4, alpha, c_region=None, s_region=None, c_count=None, s_count=None):

@@ -34,6 +34,7 @@ def main():
         ref = None
         if rank == 0:
             wct.dist = None
+            wct.fast_stats = False             # the sharded path always uses the fp64 Gram (partition independent)
             ref = wct.stylize(content.to(dev), style.to(dev))
         grp = parallel.StripGroup()
         wct.dist = grp
