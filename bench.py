@@ -316,7 +316,7 @@ def main():
             "metric": "megapixels/sec end-to-end WCT stylize (16x VGG, UHD)", "value": round(value, 2), "unit": "MP/s",
             "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 tensor-core convs (fp32 accumulate, fp32 first/last layer), f64 statistics+eigensolve" if args.precision == "tf32" else "f32 convs, f64 statistics+eigensolve",
+            "dtype": "tf32 tensor-core convs (operands rounded to TF32, fp32 accumulate; only the 3->24 first layer of stage 1 is fp32 FFMA), fp32-product/f64-accumulate statistics, f64 eigensolve" if args.precision == "tf32" else "f32 convs, f64 statistics+eigensolve",
             "data": "synthetic torch.rand images (seed 0); shipped 16x weights (tests/golden/weights_16x.npz)",
             "config": {"workload": wl, "mode": "16x", "alpha": 1.0, "stages": 5, "parallelism": "strips%d" % N,
                        "l2": "256 MiB flush between timed iterations", "precision": args.precision, "fold": args.fold,
