@@ -114,3 +114,27 @@ def test_strip_parallel_equals_single_process(tmp_path, world, Wc, Ws, stages):
     # same algorithm per pixel; on CPU oneDNN picks width-dependent conv blockings, so strips differ from the
     # full image by fp32 rounding (amplified by the whitening): observed 5e-5 on a [0,1.4] image.
     assert (got - img).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("stage", [5, 4, 3, 2, 1])
+def test_stage_halo_covers_the_receptive_field(stage):
+    """Impulse test on the CPU oracle: perturbing input column x0 must not change decoder(encoder(.)) outputs farther
+    than stage_halo(stage) columns away -- the guarantee the strip driver relies on when it crops the halo."""
+    weights = O.load_weights_npz(os.path.join(ROOT, "tests", "golden", "weights_16x.npz"))
+    halo = parallel.stage_halo("16x", stage)
+    W = 2 * halo + 64
+    g = torch.Generator().manual_seed(stage)
+    x = torch.rand(1, 3, 32, W, generator=g)
+    x0 = W // 2
+    x2 = x.clone()
+    x2[..., x0] += 0.5
+    torch.set_num_threads(4)
+    with torch.no_grad():
+        f = lambda t: O.decoder_forward(weights["d%d" % stage], "16x", stage, O.encoder_forward(weights["e%d" % stage], "16x", stage, t))
+        a, b = f(x), f(x2)
+    diff = (a - b).abs().amax(dim=(0, 1, 2))           # per output column
+    changed = torch.nonzero(diff > 0).flatten()
+    assert changed.numel() > 0
+    reach = max(x0 - int(changed.min()), int(changed.max()) - x0)
+    assert reach <= halo, "stage %d: influence reaches %d columns, halo is %d" % (stage, reach, halo)
+    assert reach > halo - 32 or stage <= 2, "halo %d is far larger than the measured reach %d" % (halo, reach)
