@@ -99,6 +99,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def peaks_clock_mhz():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p)).get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 1965.0
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -349,22 +357,30 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
         e0.record()
         y = fn(*args, **kw)
         e1.record()
-        fl, by = flops_bytes(y)
-        rec.setdefault(key, []).append((e0, e1, fl, by))
+        fb = flops_bytes(y)
+        rec.setdefault(key, []).append((e0, e1, fb[0], fb[1], fb[2] if len(fb) > 2 else 0.0))
         return y
+
+    # measured tcgen05.mma issue floor (profiles/r01_mma_rate_microbench.txt): cycles per M=128,K=8 MMA vs N
+    CYC = {16: 39.3, 32: 42.0, 64: 48.1, 128: 64.2, 256: 128.4}
+    tiles = lambda H, W, th, tw: ((H + th - 1) // th) * ((W + tw - 1) // tw)
 
     def wrap_p4(x, w, b, cout, epilogue, round_tf32, engine):
         C4, H, W, _ = x.shape
         cin = C4 * 4
         key = ("conv_umma" if engine == 1 else "conv_p4_fp32", "%d->%d epi%d" % (cin, cout, epilogue))
+        n = min(cout, 256)
+        nb = 8 if n <= 32 else (4 if n <= 128 else 2)
+        mma_cyc = tiles(H, W, 2 * nb, 62) * nb * 9 * (cin // 8) * (cout // n) * CYC.get(n, 0.0) if engine == 1 else 0.0
         return timed_call(key, originals["conv3x3_p4"], (x, w, b, cout, epilogue, round_tf32, engine), {},
-                          lambda y: (2.0 * 9 * cin * cout * H * W, 4.0 * (cin * H * W + y.numel())))
+                          lambda y: (2.0 * 9 * cin * cout * H * W, 4.0 * (cin * H * W + y.numel()), mma_cyc))
 
     def wrap_head_tc(x, w11, b11, w12, b12, epilogue, round_tf32):
         H, W = x.shape[-2:]
         return timed_call(("conv_head_tc", "3->16->16 epi%d" % epilogue), originals["conv_head_tc"],
                           (x, w11, b11, w12, b12, epilogue, round_tf32), {},
-                          lambda y: (2.0 * H * W * (9 + 9 * 3 * 16 + 9 * 16 * 16), 4.0 * (3 * H * W + y.numel())))
+                          lambda y: (2.0 * H * W * (9 + 9 * 3 * 16 + 9 * 16 * 16), 4.0 * (3 * H * W + y.numel()),
+                                     tiles(H, W, 16, 62) * (60 + 144) * CYC[16]))
 
     def wrap_head(x, w11, b11, w12, b12, c1, cout, epilogue, round_tf32):
         H, W = x.shape[-2:]
@@ -375,7 +391,8 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     def wrap_tail(x, w12, b12, w11, b11, upsample_input):
         return timed_call(("conv_tail", "16->16->3 up%d" % int(upsample_input)), originals["conv_tail"],
                           (x, w12, b12, w11, b11, upsample_input), {},
-                          lambda y: (2.0 * y.shape[-2] * y.shape[-1] * 9 * (16 * 16 + 16 * 3), 4.0 * (x.numel() + y.numel())))
+                          lambda y: (2.0 * y.shape[-2] * y.shape[-1] * 9 * (16 * 16 + 16 * 3), 4.0 * (x.numel() + y.numel()),
+                                     tiles(y.shape[-2], y.shape[-1], 14, 60) * (144 + 126) * CYC[16]))
 
     wrappers = {"conv3x3_p4": wrap_p4, "conv_head_tc": wrap_head_tc, "conv_head": wrap_head, "conv_tail": wrap_tail}
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -399,8 +416,8 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     step_ms = t0.elapsed_time(t1)
     rows = []
     for (kern, shape), evs in rec.items():
-        rows.append({"kernel": kern, "shape": shape, "launches": len(evs), "ms": sum(a.elapsed_time(b) for a, b, _, _ in evs),
-                     "flops": sum(e[2] for e in evs), "bytes": sum(e[3] for e in evs)})
+        rows.append({"kernel": kern, "shape": shape, "launches": len(evs), "ms": sum(e[0].elapsed_time(e[1]) for e in evs),
+                     "flops": sum(e[2] for e in evs), "bytes": sum(e[3] for e in evs), "mma_cyc": sum(e[4] for e in evs)})
     rows.sort(key=lambda r: -r["ms"])
     conv_ms = sum(r["ms"] for r in rows)
     top = rows[0]
@@ -428,6 +445,11 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
         "arith_intensity_flop_per_byte": round(ai, 1), "achieved_tflops": round(ach_tf, 2), "achieved_gbs": round(ach_gb, 1),
         "tensor_peak_note": "TF32 peak = bf16_tflops_sustained/2 (%s); fp32 engine: 148 SM x 128 FMA x 1.9 GHz" % peaks["source"],
         "conv_share_of_step": round(conv_ms / step_ms, 4), "single_stream_step_ms": round(step_ms, 3),
+        # operand-fetch floor of the top kernel: (#tcgen05.mma it issues) x (measured cycles per MMA for its N) / (148 SMs x
+        # sm clock), as a fraction of its measured time -- the bound that actually applies to the N <= 64 layers
+        "mma_issue_floor": {"floor_ms": round(top["mma_cyc"] / 148.0 / (peaks_clock_mhz() * 1e3), 3), "measured_ms": round(top["ms"], 3),
+                            "frac": round(top["mma_cyc"] / 148.0 / (peaks_clock_mhz() * 1e3) / top["ms"], 4) if top["ms"] > 0 else None,
+                            "sm_mhz_assumed": peaks_clock_mhz()},
         "by_shape": [{"k": "%s %s" % (r["kernel"], r["shape"]), "n": r["launches"], "ms": round(r["ms"], 3),
                       "tflops": round(r["flops"] / (r["ms"] / 1e3) / 1e12, 2), "gbs": round(r["bytes"] / (r["ms"] / 1e3) / 1e9, 1)}
                      for r in rows[:10]],
