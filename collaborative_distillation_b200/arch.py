@@ -47,6 +47,24 @@ def decoder_layers(mode: str, stage: int):
     return out
 
 
+def t7_indices(kind: str, stage: int):
+    """child index (0-based) of every conv inside the Torch7 nn.Sequential of the WCT authors' files, derived from the
+    module order [conv0] (pad conv relu)+ [pool|unpool]; equals the literal tables of model_original.py
+    (e.g. Encoder5 :471-484 conv0:0 conv11:2 ... conv51:42, Decoder5 :561-573 conv51:1 ... conv11:41)."""
+    out = {}
+    if kind == "enc":
+        out["conv0"], idx = 0, 1
+        for L in encoder_layers("original", stage):
+            out[L["name"]] = idx + 1
+            idx += 4 if L["pool_after"] else 3
+    else:
+        idx = 0
+        for L in decoder_layers("original", stage):
+            out[L["name"]] = idx + 1
+            idx += 4 if L["up_after"] else 3
+    return out
+
+
 def feature_channels(mode: str, stage: int) -> int:
     return encoder_layers(mode, stage)[-1]["cout"]
 

@@ -41,9 +41,13 @@ def _load_state(module: nn.Module, model):
     if not model:
         return
     ext = os.path.splitext(model)[1]
-    if ext == ".t7":
-        raise WctbError("Torch7 .t7 weights need torch.utils.serialization.load_lua (removed in torch>=1.0); "
-                        "convert them to a .pth state_dict first (see INTEGRATION.md)")
+    if ext == ".t7":                       # model_original.py:25-29: load_lua + load_param per sequential child
+        from . import t7
+        seq = t7.load_t7(model)
+        for name, idx in arch.t7_indices(module.KIND, module.STAGE).items():
+            t7.load_param_from_t7(seq, idx, getattr(module, name))
+        print("load model '%s' successfully" % model)
+        return
     assert ext == ".pth", "weights must be .pth or .t7 (model_original.py:24)"
     sd = torch.load(model, map_location="cpu")
     if isinstance(sd, dict) and "model" in sd and not torch.is_tensor(sd["model"]):

@@ -120,3 +120,103 @@ def test_reference_import_paths():
         assert importlib.import_module("util_wct").WCT is P.WCT
     finally:
         sys.path.remove(sys_path)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Torch7 weights of --mode original (model_original.py:25-29, utils.py:64-67)
+_T7_TABLE = {  # literal indices of the reference's load_param calls (model_original.py)
+    ("enc", 1): {"conv0": 0, "conv11": 2},
+    ("dec", 1): {"conv11": 1},
+    ("enc", 2): {"conv0": 0, "conv11": 2, "conv12": 5, "conv21": 9},
+    ("dec", 2): {"conv21": 1, "conv12": 5, "conv11": 8},
+    ("enc", 3): {"conv0": 0, "conv11": 2, "conv12": 5, "conv21": 9, "conv22": 12, "conv31": 16},
+    ("dec", 3): {"conv31": 1, "conv22": 5, "conv21": 8, "conv12": 12, "conv11": 15},
+    ("enc", 4): {"conv0": 0, "conv11": 2, "conv12": 5, "conv21": 9, "conv22": 12, "conv31": 16, "conv32": 19, "conv33": 22,
+                 "conv34": 25, "conv41": 29},
+    ("dec", 4): {"conv41": 1, "conv34": 5, "conv33": 8, "conv32": 11, "conv31": 14, "conv22": 18, "conv21": 21, "conv12": 25,
+                 "conv11": 28},
+    ("enc", 5): {"conv0": 0, "conv11": 2, "conv12": 5, "conv21": 9, "conv22": 12, "conv31": 16, "conv32": 19, "conv33": 22,
+                 "conv34": 25, "conv41": 29, "conv42": 32, "conv43": 35, "conv44": 38, "conv51": 42},
+    ("dec", 5): {"conv51": 1, "conv44": 5, "conv43": 8, "conv42": 11, "conv41": 14, "conv34": 18, "conv33": 21, "conv32": 24,
+                 "conv31": 27, "conv22": 31, "conv21": 34, "conv12": 38, "conv11": 41},
+}
+
+
+def test_t7_indices_match_reference_tables():
+    from collaborative_distillation_b200 import arch
+    for (kind, stage), want in _T7_TABLE.items():
+        assert arch.t7_indices(kind, stage) == want, (kind, stage)
+
+
+def _fake_sequential(kind, stage, seed):
+    """an nn.Sequential laid out like the WCT authors' files: [conv0] (pad conv relu)+ [pool|unpool]"""
+    from collaborative_distillation_b200 import arch, t7
+    g = torch.Generator().manual_seed(seed)
+    mods, convs = [], {}
+
+    def conv(name, cin, cout, k):
+        w, b = torch.randn(cout, cin, k, k, generator=g), torch.randn(cout, generator=g)
+        convs[name] = (w, b)
+        return t7.T7Object("nn.SpatialConvolution", {"weight": w, "bias": b, "nInputPlane": cin, "nOutputPlane": cout,
+                                                      "kW": k, "kH": k, "train": False, "gradWeight": None})
+    if kind == "enc":
+        mods.append(conv("conv0", 3, 3, 1))
+        layers = arch.encoder_layers("original", stage)
+    else:
+        layers = arch.decoder_layers("original", stage)
+    for L in layers:
+        mods += [t7.T7Object("nn.SpatialReflectionPadding", {"pad_l": 1, "pad_r": 1, "pad_t": 1, "pad_b": 1}),
+                 conv(L["name"], L["cin"], L["cout"], 3), t7.T7Object("nn.ReLU", {"inplace": True, "threshold": 0})]
+        if L.get("pool_after"):
+            mods.append(t7.T7Object("nn.SpatialMaxPooling", {"kW": 2, "kH": 2, "dW": 2, "dH": 2, "ceil_mode": False}))
+        if L.get("up_after"):
+            mods.append(t7.T7Object("nn.SpatialUpSamplingNearest", {"scale_factor": 2}))
+    return t7.T7Object("nn.Sequential", {"modules": mods, "train": False}), convs
+
+
+@pytest.mark.parametrize("kind,stage", [("enc", 1), ("enc", 3), ("dec", 3), ("dec", 2)])
+def test_t7_weights_load_into_original_modules(tmp_path, kind, stage):
+    from collaborative_distillation_b200 import nets, t7
+    seq, convs = _fake_sequential(kind, stage, seed=stage)
+    path = str(tmp_path / ("%s%d.t7" % (kind, stage)))
+    t7.save_t7(path, seq)
+    back = t7.load_t7(path)
+    assert back.torch_typename == "nn.Sequential" and len(back.modules) == len(seq.modules)
+    assert back.get(0).torch_typename == seq.get(0).torch_typename
+    cls = getattr(nets, ("Encoder%d" if kind == "enc" else "Decoder%d") % stage)
+    m = cls(path)
+    for name, (w, b) in convs.items():
+        assert torch.equal(getattr(m, name).weight.detach(), w), name
+        assert torch.equal(getattr(m, name).bias.detach(), b), name
+
+
+def test_t7_reader_shared_storage_and_views(tmp_path):
+    """tensors that share one storage (weight views) and repeated references resolve through the ref-index memo"""
+    import struct
+    from collaborative_distillation_b200 import t7
+    p = str(tmp_path / "v.t7")
+    base = torch.arange(12, dtype=torch.float32)
+    with open(p, "wb") as f:
+        w = t7._Writer(f)
+        # table {a = tensor[2,3] @offset 1, b = transposed view [3,2] of the SAME storage (by reference), c = a (by reference)}
+        w.w("ii", 3, 1); w.w("i", 3)
+        w.obj("a")
+        w.w("ii", 4, 2); w.string("V 1"); w.string("torch.FloatTensor")
+        w.w("i", 2); w.w("qq", 2, 3); w.w("qq", 3, 1); w.w("q", 1)
+        w.w("ii", 4, 3); w.string("V 1"); w.string("torch.FloatStorage"); w.w("q", 12); f.write(base.numpy().tobytes())
+        w.obj("b")
+        w.w("ii", 4, 4); w.string("V 1"); w.string("torch.FloatTensor")
+        w.w("i", 2); w.w("qq", 3, 2); w.w("qq", 1, 3); w.w("q", 7)
+        w.w("ii", 4, 3)                                                   # storage by reference
+        w.obj("c")
+        w.w("ii", 4, 2)                                                   # tensor by reference
+    out = t7.load_t7(p)
+    assert torch.equal(out["a"], base[:6].view(2, 3))
+    assert torch.equal(out["b"], base[6:12].view(2, 3).t())
+    assert out["c"] is out["a"]
+    with open(p, "rb") as f:
+        blob = f.read()
+    with open(p, "wb") as f:
+        f.write(blob[:-5])
+    with pytest.raises(EOFError):
+        t7.load_t7(p)
