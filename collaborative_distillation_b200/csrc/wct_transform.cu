@@ -384,6 +384,243 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_smem_kernel(const double* _
   if (sweeps_out && threadIdx.x == 0) sweeps_out[prob] = sweep;
 }
 
+// ------------------------------------------------------------------------------------------
+// Variant 1b (C <= 128, the default): Jacobi on the pivoted Cholesky factor.
+//   S = scale*A (+I) compacted to its live block, S = L L^T by an in-place diagonally pivoted Cholesky that stops at
+//   the numerical rank (remaining diagonal <= 1e-14 max diag: the whole remaining Schur complement of a PSD matrix is
+//   then below that level).  Hestenes rotations on the columns of L diagonalise L^T L, which is one Cholesky-LR step
+//   closer to diagonal than S itself, so the sweep count drops from 10-12 (16-22 on synthetic spectra) to 6-9;
+//   lambda_k = ||column k||^2 and the normalised columns are the eigenvectors of S.  Row order is irrelevant to the
+//   column rotations, so the pivoting is virtual (a done-mask), and the L column of pivot p overwrites column p.
+//   Per pair only the cross dot product is computed: the column norms^2 are tracked (a' = a - t c, b' = b + t c) and
+//   recomputed exactly once per sweep; rotations are the scaled ("fast") form  x' = x - tp y, y' = y + tq x  with a
+//   per-column scale s (true column = s * stored), folded back into the columns at the per-sweep refresh.
+//   A sweep whose largest |cos| is below JACOBI_EARLY leaves residual cosines <= ~1e-9 (quadratic convergence) and
+//   ends the iteration without a separate all-check sweep.
+// ------------------------------------------------------------------------------------------
+constexpr double JACOBI_EARLY = 3e-6;
+constexpr double CHOL_RANK_TOL = 1e-14;
+
+__host__ __device__ inline int jacobi_pitch(int k, int lanes) {
+  // column pitch in doubles: == 8 (mod 16) for 8 lanes/pair, == 4 (mod 16) for 4 lanes/pair, so that the columns
+  // touched by one half-warp request fall into disjoint banks
+  return lanes >= 8 ? ((k + 7) / 16) * 16 + 8 : ((k + 11) / 16) * 16 + 4;
+}
+
+template <int LANES, int EPL>
+__global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* __restrict__ A, int C,
+                                                                 const JacobiScales scale, int add_identity,
+                                                                 double* __restrict__ evals, double* __restrict__ evecs,
+                                                                 int* __restrict__ sweeps_out) {
+  extern __shared__ double G[];  // column-major k x k
+  __shared__ double s_d[128];    // Cholesky: running diagonal of the Schur complement; Jacobi: tracked column norms^2
+  __shared__ double s_l[128];    // Cholesky: current L column; Jacobi: column scale s
+  __shared__ double s_si[128];   // Jacobi: 1/s
+  __shared__ int s_live[128];    // compacted index -> original channel
+  __shared__ int s_done[128];
+  __shared__ double s_cv[4];
+  __shared__ int s_ci[4];
+  __shared__ double s_tr[4];
+  __shared__ int s_k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int prob = blockIdx.x;
+  const double sc = scale.v[prob];
+  const double* Ap = A + (long long)prob * C * C;
+  const double idn = add_identity ? 1.0 : 0.0;
+  // ---- live-channel compaction (warp 0, ballot prefix)
+  if (warp == 0) {
+    int base = 0, first_dead = -1;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int i = c0 + lane;
+      const bool in = i < C;
+      const double d = in ? Ap[(long long)i * C + i] * sc + idn : 0.0;
+      const bool live = in && d > 0.0;
+      const unsigned ml = __ballot_sync(0xffffffffu, live), md = __ballot_sync(0xffffffffu, in && !live);
+      if (live) s_live[base + __popc(ml & ((1u << lane) - 1u))] = i;
+      base += __popc(ml);
+      if (first_dead < 0 && md) first_dead = c0 + __ffs(md) - 1;
+    }
+    if (lane == 0) {
+      if ((base & 1) && first_dead >= 0) s_live[base++] = first_dead;   // keep k even for the round-robin pairing
+      s_k = base < 2 ? 0 : base;
+    }
+  }
+  __syncthreads();
+  const int k = s_k;
+  const int pitch = jacobi_pitch(k, LANES);
+  for (int i = tid; i < k * k; i += blockDim.x) {
+    const int r = i / k, c = i - r * k;
+    const int ro = s_live[r], co = s_live[c];
+    double v = Ap[(long long)ro * C + co] * sc;
+    if (ro == co) { v += idn; s_d[r] = v; s_done[r] = 0; }
+    G[c * pitch + r] = v;
+  }
+  // outputs default: eigenvalue 0 / zero vector (dead channels, null space beyond the numerical rank, k == 0)
+  for (int i = tid; i < C; i += blockDim.x) evals[(long long)prob * C + i] = 0.0;
+  for (int i = tid; i < C * C; i += blockDim.x) evecs[(long long)prob * C * C + i] = 0.0;
+  __syncthreads();
+  int sweep = 0;
+  if (k >= 2) {
+    // ---- trace and largest diagonal entry
+    if (warp < 4) {
+      double v = tid < k ? s_d[tid] : 0.0, m = v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      }
+      if (lane == 0) { s_tr[warp] = v; s_cv[warp] = m; }
+    }
+    __syncthreads();
+    const double trace = (s_tr[0] + s_tr[1]) + (s_tr[2] + s_tr[3]);
+    const double thr = CHOL_RANK_TOL * fmax(fmax(s_cv[0], s_cv[1]), fmax(s_cv[2], s_cv[3]));
+    const double floor2 = trace * 1e-15;   // column norm^2 (= eigenvalue) below 1e-15 trace(S): numerically null
+    __syncthreads();
+    // ---- in-place pivoted Cholesky
+    for (int step = 0; step < k; ++step) {
+      if (warp < 4) {
+        double v = (tid < k && !s_done[tid]) ? s_d[tid] : -1.0;
+        int idx = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+          const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+          if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+        }
+        if (lane == 0) { s_cv[warp] = v; s_ci[warp] = idx; }
+      }
+      __syncthreads();
+      double dp = s_cv[0];
+      int p = s_ci[0];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) {
+        const double v2 = s_cv[w];
+        const int i2 = s_ci[w];
+        if (v2 > dp || (v2 == dp && i2 < p)) { dp = v2; p = i2; }
+      }
+      if (!(dp > thr)) break;   // block-uniform: numerical rank reached
+      const double inv = rsqrt(dp);
+      double li = 0.0;
+      if (tid < k) {
+        if (tid == p) { li = dp * inv; s_done[p] = 1; }   // s_done[p] is read by other threads only after the barrier
+        else if (!s_done[tid]) li = G[p * pitch + tid] * inv;
+        G[p * pitch + tid] = li;
+        s_l[tid] = li;
+      }
+      __syncthreads();
+      for (int m = warp; m < k; m += nwarps) {
+        if (s_done[m]) continue;
+        const double lm = s_l[m];
+        double* col = G + m * pitch;
+        for (int i = lane; i < k; i += 32) col[i] = fma(-s_l[i], lm, col[i]);
+      }
+      if (tid < k && !s_done[tid]) s_d[tid] = fma(-li, li, s_d[tid]);
+      __syncthreads();
+    }
+    __syncthreads();
+    for (int m = warp; m < k; m += nwarps) {   // columns never pivoted: beyond the numerical rank
+      if (s_done[m]) continue;
+      for (int i = lane; i < k; i += 32) G[m * pitch + i] = 0.0;
+    }
+    if (tid < k) { s_l[tid] = 1.0; s_si[tid] = 1.0; }
+    __syncthreads();
+    // ---- Hestenes sweeps on the columns of L
+    const int group = tid / LANES, sub = tid % LANES;
+    const int ngroups = blockDim.x / LANES;
+    const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane & ~(LANES - 1)));
+    for (; sweep < JACOBI_MAX_SWEEPS;) {
+      // refresh: fold the scale into the column, exact norm^2
+      for (int j = group; j < k; j += ngroups) {
+        const double sj = s_l[j];
+        double* g = G + j * pitch;
+        double a = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const int i = sub + e * LANES;
+          if (i < k) { const double v = g[i] * sj; g[i] = v; a = fma(v, v, a); }
+        }
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
+        if (sub == 0) { s_d[j] = a; s_l[j] = 1.0; s_si[j] = 1.0; }
+      }
+      __syncthreads();
+      int big = 0;
+      for (int round = 0; round < k - 1; ++round) {
+        for (int pi = group; pi < k / 2; pi += ngroups) {
+          int p, q;
+          rr_pair(round, pi, k, p, q);
+          double* gp = G + p * pitch;
+          double* gq = G + q * pitch;
+          double x[EPL], y[EPL];
+          double c0 = 0, c1 = 0;
+#pragma unroll
+          for (int e = 0; e < EPL; e += 2) {
+            const int i0 = sub + e * LANES, i1 = i0 + LANES;
+            x[e] = i0 < k ? gp[i0] : 0.0;
+            y[e] = i0 < k ? gq[i0] : 0.0;
+            x[e + 1] = i1 < k ? gp[i1] : 0.0;
+            y[e + 1] = i1 < k ? gq[i1] : 0.0;
+            c0 = fma(x[e], y[e], c0);
+            c1 = fma(x[e + 1], y[e + 1], c1);
+          }
+          double c = c0 + c1;
+#pragma unroll
+          for (int o = LANES / 2; o > 0; o >>= 1) c += __shfl_xor_sync(mask, c, o);
+          const double sp = s_l[p], sq = s_l[q];
+          const double a = s_d[p], b = s_d[q];
+          c *= sp * sq;
+          const double cc = c * c, ab = a * b;
+          const bool null = a <= floor2 || b <= floor2;
+          if (!null && cc > JACOBI_EARLY * JACOBI_EARLY * ab) big = 1;
+          if (null || cc <= JACOBI_TOL * JACOBI_TOL * ab) continue;
+          // half-angle form of the inner rotation: cos 2th = |d|/sqrt(h), sin 2th = |2c|/sqrt(h)
+          const double d = b - a, c2 = c + c;
+          const double r = rsqrt(fma(d, d, c2 * c2));
+          const double cs2 = fma(0.5 * fabs(d), r, 0.5);          // cos^2 th in [1/2, 1]
+          const double csi = rsqrt(cs2);                          // 1 / cos th
+          const double cs = cs2 * csi;
+          double t = 0.5 * fabs(c2) * r * (csi * csi);            // tan th
+          if ((d < 0.0) != (c2 < 0.0)) t = -t;
+          const double sip = s_si[p], siq = s_si[q];
+          const double tp = t * sq * sip, tq = t * sp * siq;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const int i = sub + e * LANES;
+            if (i < k) {
+              gp[i] = fma(-tp, y[e], x[e]);
+              gq[i] = fma(tq, x[e], y[e]);
+            }
+          }
+          __syncwarp(mask);   // every lane of the pair has read s_si[p], s_si[q]
+          if (sub == 0) {
+            s_l[p] = sp * cs; s_l[q] = sq * cs;
+            s_si[p] = sip * csi; s_si[q] = siq * csi;
+            s_d[p] = fma(-t, c, a); s_d[q] = fma(t, c, b);
+          }
+        }
+        __syncthreads();
+      }
+      ++sweep;
+      if (!__syncthreads_or(big)) break;
+    }
+    // eigenvalues = true column norms^2, eigenvectors = normalised columns, scattered back to original channel indices
+    for (int j = group; j < k; j += ngroups) {
+      const double* g = G + j * pitch;
+      double a = 0;
+      for (int i = sub; i < k; i += LANES) a = fma(g[i], g[i], a);
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
+      const double sj = s_l[j];
+      const double inv = a > 0 ? rsqrt(a) : 0.0;
+      const int jo = s_live[j];
+      if (sub == 0) evals[(long long)prob * C + jo] = a * sj * sj;
+      for (int i = sub; i < k; i += LANES)
+        evecs[(long long)prob * C * C + (long long)jo * C + s_live[i]] = g[i] * inv;
+    }
+  }
+  if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
+}
+
 __global__ void __launch_bounds__(256) jacobi_global_kernel(const double* __restrict__ A, int nprob, int C,
                                                             const JacobiScales scale, int add_identity,
                                                             double* __restrict__ evals, double* __restrict__ evecs,
@@ -450,13 +687,36 @@ __global__ void __launch_bounds__(256) jacobi_global_kernel(const double* __rest
   if (sweeps_out && gtid < nprob) sweeps_out[gtid] = sweep;
 }
 
+static int g_eigh_variant = 0;   // 0: Cholesky-preconditioned Jacobi (default), 1: legacy Jacobi on S (debug / A-B timing)
+extern "C" int wctb_debug_set_eigh_variant(int v) {
+  if (v < 0 || v > 1) return WCTB_E_BADARG;
+  g_eigh_variant = v;
+  return WCTB_OK;
+}
+
 extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale_host, int add_identity, double* evals,
                                 double* evecs, double* work, int* sweeps_out, void* stream) {
   if (!a || !scale_host || !evals || !evecs || !work || nprob <= 0 || nprob > 8 || C < 2 || (C & 1)) return WCTB_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   JacobiScales scale;
   for (int i = 0; i < 8; ++i) scale.v[i] = i < nprob ? scale_host[i] : 1.0;
-  if (C <= 128) {
+  if (C <= 128 && g_eigh_variant == 0) {
+    // lanes per column pair x elements per lane (LANES*EPL >= C); ~512 threads measured best on B200 (tools/eig_diag.py)
+    if (C > 64) {
+      const size_t smem = (size_t)C * jacobi_pitch(C, 8) * sizeof(double);
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_chol_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jacobi_chol_kernel<8, 16><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    } else if (C > 32) {
+      const size_t smem = (size_t)C * jacobi_pitch(C, 8) * sizeof(double);
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_chol_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jacobi_chol_kernel<8, 8><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    } else {
+      const size_t smem = (size_t)C * jacobi_pitch(C, 4) * sizeof(double);
+      jacobi_chol_kernel<4, 8><<<nprob, 256, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+    }
+    WCTB_RETURN_LAUNCH();
+  }
+  if (C <= 128) {   // legacy variant (wctb_debug_set_eigh_variant(1)): Jacobi on the columns of S itself
     size_t smem = (size_t)C * (C + 4) * sizeof(double);
     // lanes per column pair x elements per lane (LANES*EPL >= C).  Measured on B200 (tools/eig_diag.py): ~512 threads is the
     // sweet spot -- C=128: <8,16> 1.66 ms vs <16,8> 2.12 ms; C=64: <8,8> 0.57 ms vs <4,16> 0.76 ms.

@@ -225,6 +225,11 @@ def eigh_jacobi(a: torch.Tensor, scale, add_identity: bool = False, return_sweep
     return (evals, evecs, sweeps) if return_sweeps else (evals, evecs)
 
 
+def set_eigh_variant(v: int):
+    """debug: 0 = Cholesky-preconditioned Jacobi (default), 1 = legacy Jacobi on the matrix itself (C <= 128 only)"""
+    check(_lib.load().wctb_debug_set_eigh_variant(int(v)), "debug_set_eigh_variant")
+
+
 def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, alpha: float):
     """-> (M fp32 [C,C], b fp32 [C], mean_c fp32 [C])  with csF = M (cF - mean_c) + b"""
     C = c_evals.numel()

@@ -134,13 +134,14 @@ int wctb_centered_gram(const float* x_p4, int C, int H, int W, int y0, int y1, i
 int wctb_centered_gram_fast(const float* x_p4, int C, int H, int W, int y0, int y1, int x0, int x1,
                             const double* mean, double* gram_out, void* stream);
 
-/* ---- symmetric eigendecomposition (one-sided Jacobi, fp64) ------------------------------
+/* ---- symmetric eigendecomposition (one-sided Jacobi on the pivoted Cholesky factor, fp64) ---
  * replaces: torch.svd(contentConv, some=False) / torch.svd(styleConv) (util_wct.py:74,100);
  * only (E, V) are consumed there and the matrices are symmetric PSD.
  * a: nprob (<= 8) matrices [C][C] fp64 (row-major symmetric), each scaled by scale_host[prob] (HOST array) and, if
  * add_identity, + I (the `--numpy` variant, util_wct.py:143) before the solve.
  * Outputs per problem: evals[C] (>= 0, unsorted), evecs[C][C] column k = unit eigenvector k
- * stored as evecs[k*C + i] (zero vector when the eigenvalue is exactly 0).
+ * stored as evecs[k*C + i] (zero vector when the eigenvalue is exactly 0, and -- for C <= 128 -- for the null space
+ * beyond the numerical rank, i.e. eigenvalues below ~1e-14 of the largest diagonal entry, which are reported as 0).
  * work: nprob*C*C + 16 doubles of scratch.  sweeps_out (optional, may be NULL): int[nprob].    */
 int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale_host, int add_identity,
                      double* evals, double* evecs, double* work, int* sweeps_out, void* stream);
@@ -171,6 +172,10 @@ int wctb_wct_apply(const float* x_p4, const float* m, const float* b, const floa
 int wctb_fold_wct_into_conv(const float* w_oihw, const float* bias, const float* m, const float* b,
                             const float* mean_c, float* w_out, float* b_out, int Cin, int Cout,
                             void* stream);
+
+/* debug: 0 (default) = Cholesky-preconditioned Jacobi for C <= 128; 1 = legacy Jacobi on the matrix itself (A/B timing,
+ * tools/eig_diag.py).  Process-wide; not meant to be toggled while work is in flight.                                */
+int wctb_debug_set_eigh_variant(int variant);
 
 /* debug: when buf != NULL a few CTAs of the fused head record clock64() phase stamps into buf[128] (tools/trace_head.py) */
 int wctb_debug_set_trace(long long* buf);

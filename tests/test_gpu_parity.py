@@ -104,8 +104,20 @@ def test_moments_match_fp64(C, H, W, region):
 
 
 # ------------------------------------------------------------------ eigensolver
-@pytest.mark.parametrize("C,rank", [(24, 24), (32, 20), (64, 64), (128, 51), (128, 128), (256, 200), (512, 512)])
-def test_eigh_jacobi_vs_lapack(C, rank):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("C,rank", [(24, 24), (32, 20), (64, 64), (100, 37), (128, 51), (128, 128), (256, 200), (512, 512)])
+def test_eigh_jacobi_vs_lapack(C, rank, variant):
+    """variant 0: Jacobi on the pivoted Cholesky factor (default, C <= 128); 1: legacy Jacobi on the matrix (debug switch)"""
+    if variant == 1 and C > 128:
+        pytest.skip("C > 128 always takes the cooperative-grid kernel")
+    ops.set_eigh_variant(variant)
+    try:
+        _check_eigh(C, rank)
+    finally:
+        ops.set_eigh_variant(0)
+
+
+def _check_eigh(C, rank):
     g = torch.Generator().manual_seed(C + rank)
     B = torch.randn(C, rank, generator=g, dtype=torch.float64) * torch.logspace(0, -2, rank, dtype=torch.float64)
     A = B @ B.t()

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Eigensolver diagnostics on the benchmark workload: live rank, sweeps, time per solve."""
+"""Eigensolver diagnostics on the benchmark workload: live rank, sweeps and time per solve of both solver variants."""
 import os, sys
 from types import SimpleNamespace
 import torch
@@ -20,14 +20,17 @@ for s in (5, 4, 3, 2, 1):
     gram = torch.zeros(1, C, C, device="cuda", dtype=torch.float64)
     mean = w._moments(f, (0, f.shape[1], 0, f.shape[2]), n, gram[0])
     live = int((gram[0].diagonal() > 0).sum())
-    for _ in range(2):
-        ev, evec, sw = ops.eigh_jacobi(gram, [1.0 / (n - 1)], return_sweeps=True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        ops.eigh_jacobi(gram, [1.0 / (n - 1)])
-    e1.record(); torch.cuda.synchronize()
+    line = "stage %d C=%3d live=%3d" % (s, C, live)
+    for variant, name in ((1, "legacy"), (0, "cholesky")):
+        ops.set_eigh_variant(variant)
+        for _ in range(2):
+            ev, evec, sw = ops.eigh_jacobi(gram, [1.0 / (n - 1)], return_sweeps=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.eigh_jacobi(gram, [1.0 / (n - 1)])
+        e1.record(); torch.cuda.synchronize()
+        line += "  | %s sweeps=%2d %.3f ms" % (name, int(sw[0]), e0.elapsed_time(e1) / 5)
     evs = ev[0].sort(descending=True).values
-    print("stage %d C=%3d live=%3d sweeps=%2d time=%.3f ms  lmax=%.3g  l[live-1]/lmax=%.2e" % (
-        s, C, live, int(sw[0]), e0.elapsed_time(e1) / 5, evs[0].item(), (evs[live - 1] / evs[0]).item()))
+    print(line + "  | lmax=%.3g  l[live-1]/lmax=%.2e" % (evs[0].item(), (evs[live - 1] / evs[0]).item()))
