@@ -42,6 +42,8 @@ SIGNATURES = {
     "wctb_wct_apply": [_p, _p, _p, _p, _p, _i, _ll, _i, _p],
     "wctb_fold_wct_into_conv": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "wctb_debug_set_eigh_variant": [_i],
+    "wctb_debug_eigh_profile": [_p],
+    "wctb_debug_dp_rate": [_p, _p],
     "wctb_debug_set_trace": [_p],
     "wctb_debug_mma_rate": [_p, _i, _i, _i, _i, _i, _p],
     "wctb_selftest_umma": [_p, _p, _p, _i, _i, _p],

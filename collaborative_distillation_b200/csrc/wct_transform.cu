@@ -407,11 +407,16 @@ __host__ __device__ inline int jacobi_pitch(int k, int lanes) {
   return lanes >= 8 ? ((k + 7) / 16) * 16 + 8 : ((k + 11) / 16) * 16 + 4;
 }
 
-template <int LANES, int EPL>
+template <int LANES, int EPL, bool PROF>
 __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* __restrict__ A, int C,
                                                                  const JacobiScales scale, int add_identity,
                                                                  double* __restrict__ evals, double* __restrict__ evecs,
-                                                                 int* __restrict__ sweeps_out) {
+                                                                 int* __restrict__ sweeps_out, long long* __restrict__ prof) {
+  // PROF: thread 0 records clock64() phase times into prof[0..3): load+compaction, Cholesky, sweeps (tools/eig_diag.py)
+  long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tk = 0;
+  if (PROF) tk = clock64();
+#define JPROF(slot) do { if (PROF) { const long long now_ = clock64(); pt[slot] += now_ - tk; tk = now_; } } while (0)
   extern __shared__ double G[];  // column-major k x k
   __shared__ double s_d[128];    // Cholesky: running diagonal of the Schur complement; Jacobi: tracked column norms^2
   __shared__ double s_l[128];    // Cholesky: current L column; Jacobi: column scale s
@@ -476,20 +481,21 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* _
     const double thr = CHOL_RANK_TOL * fmax(fmax(s_cv[0], s_cv[1]), fmax(s_cv[2], s_cv[3]));
     const double floor2 = trace * 1e-15;   // column norm^2 (= eigenvalue) below 1e-15 trace(S): numerically null
     __syncthreads();
-    // ---- in-place pivoted Cholesky
-    for (int step = 0; step < k; ++step) {
-      if (warp < 4) {
-        double v = (tid < k && !s_done[tid]) ? s_d[tid] : -1.0;
-        int idx = tid;
+    JPROF(0);   // load + compaction
+    // ---- in-place pivoted Cholesky (two barriers per step: the pivot search of step+1 rides on the update of step)
+    auto pivot_candidates = [&](double v, int idx) {   // warps 0..3: (largest remaining diagonal, smallest index) -> s_cv/s_ci
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
-          const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
-          if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
-        }
-        if (lane == 0) { s_cv[warp] = v; s_ci[warp] = idx; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
       }
-      __syncthreads();
+      if (lane == 0) { s_cv[warp] = v; s_ci[warp] = idx; }
+    };
+    double my_d = tid < k ? s_d[tid] : -1.0;   // running Schur-complement diagonal of row tid (-1: not a candidate)
+    if (warp < 4) pivot_candidates(my_d, tid);
+    __syncthreads();
+    for (int step = 0; step < k; ++step) {
       double dp = s_cv[0];
       int p = s_ci[0];
 #pragma unroll
@@ -502,32 +508,51 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* _
       const double inv = rsqrt(dp);
       double li = 0.0;
       if (tid < k) {
-        if (tid == p) { li = dp * inv; s_done[p] = 1; }   // s_done[p] is read by other threads only after the barrier
-        else if (!s_done[tid]) li = G[p * pitch + tid] * inv;
+        if (tid == p) { li = dp * inv; s_done[p] = 1; my_d = -1.0; }   // s_done[p] is read by others only after the barrier
+        else if (my_d >= 0.0) li = G[p * pitch + tid] * inv;           // my_d < 0 <=> row already pivoted
         G[p * pitch + tid] = li;
         s_l[tid] = li;
       }
       __syncthreads();
-      for (int m = warp; m < k; m += nwarps) {
-        if (s_done[m]) continue;
-        const double lm = s_l[m];
-        double* col = G + m * pitch;
-        for (int i = lane; i < k; i += 32) col[i] = fma(-s_l[i], lm, col[i]);
+      {
+        double lr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lr[e] = lane + 32 * e < k ? s_l[lane + 32 * e] : 0.0;
+        for (int m = warp; m < k; m += nwarps) {
+          if (s_done[m]) continue;
+          const double lm = s_l[m];
+          double* col = G + m * pitch;
+          double v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = lane + 32 * e < k ? col[lane + 32 * e] : 0.0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (lane + 32 * e < k) col[lane + 32 * e] = fma(-lr[e], lm, v[e]);
+        }
       }
-      if (tid < k && !s_done[tid]) s_d[tid] = fma(-li, li, s_d[tid]);
+      if (my_d >= 0.0) my_d = fmax(fma(-li, li, my_d), 0.0);
+      if (warp < 4) pivot_candidates(my_d, tid);
       __syncthreads();
     }
-    __syncthreads();
     for (int m = warp; m < k; m += nwarps) {   // columns never pivoted: beyond the numerical rank
       if (s_done[m]) continue;
       for (int i = lane; i < k; i += 32) G[m * pitch + i] = 0.0;
     }
     if (tid < k) { s_l[tid] = 1.0; s_si[tid] = 1.0; }
     __syncthreads();
-    // ---- Hestenes sweeps on the columns of L
+    JPROF(1);   // Cholesky
+    // ---- Hestenes sweeps on the columns of L.
+    // Round-robin (circle method) over m = k-1 ring positions plus one fixed column.  Pair j of round r is
+    // {(r+j) % m, (r-j) % m}; group 0 pairs the fixed column k-1 with column r % m.  The column at ring position
+    // j in 1..h (h = (k-2)/2) stays in the registers of one group while it walks from position h down to 1 (its "owner");
+    // only the partner (the "visitor", positions -1..-h) goes through shared memory each round, which halves the
+    // shared-memory traffic that bounds this loop.  An owner whose column reaches position 1 stores it (it is group 0's
+    // visitor next round) and picks up the column entering position h, which its previous partner group has just stored.
     const int group = tid / LANES, sub = tid % LANES;
     const int ngroups = blockDim.x / LANES;
     const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane & ~(LANES - 1)));
+    const int m = k - 1, h = (k - 2) / 2;
+    const bool active = group < k / 2;
     for (; sweep < JACOBI_MAX_SWEEPS;) {
       // refresh: fold the scale into the column, exact norm^2
       for (int j = group; j < k; j += ngroups) {
@@ -541,24 +566,31 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* _
         }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
+        __syncwarp(mask);   // every lane of the group has read s_l[j]
         if (sub == 0) { s_d[j] = a; s_l[j] = 1.0; s_si[j] = 1.0; }
       }
       __syncthreads();
       int big = 0;
-      for (int round = 0; round < k - 1; ++round) {
-        for (int pi = group; pi < k / 2; pi += ngroups) {
-          int p, q;
-          rr_pair(round, pi, k, p, q);
-          double* gp = G + p * pitch;
+      int own = group == 0 ? k - 1 : group;   // ring position `group` at round 0
+      double x[EPL];
+      if (active) {
+        const double* g = G + own * pitch;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) x[e] = sub + e * LANES < k ? g[sub + e * LANES] : 0.0;
+      }
+      for (int round = 0; round < m; ++round) {
+        bool handover = false;
+        if (active) {
+          int q = round;                                   // group 0: ring position 0
+          if (group != 0) { q = (2 * round - own) % m; if (q < 0) q += m; }
+          handover = group != 0 && (own - round + m) % m == 1;   // own < m, round < m
           double* gq = G + q * pitch;
-          double x[EPL], y[EPL];
+          double y[EPL];
           double c0 = 0, c1 = 0;
 #pragma unroll
           for (int e = 0; e < EPL; e += 2) {
             const int i0 = sub + e * LANES, i1 = i0 + LANES;
-            x[e] = i0 < k ? gp[i0] : 0.0;
             y[e] = i0 < k ? gq[i0] : 0.0;
-            x[e + 1] = i1 < k ? gp[i1] : 0.0;
             y[e + 1] = i1 < k ? gq[i1] : 0.0;
             c0 = fma(x[e], y[e], c0);
             c1 = fma(x[e + 1], y[e + 1], c1);
@@ -566,43 +598,56 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* _
           double c = c0 + c1;
 #pragma unroll
           for (int o = LANES / 2; o > 0; o >>= 1) c += __shfl_xor_sync(mask, c, o);
-          const double sp = s_l[p], sq = s_l[q];
-          const double a = s_d[p], b = s_d[q];
+          const double sp = s_l[own], sq = s_l[q];
+          const double a = s_d[own], b = s_d[q];
           c *= sp * sq;
           const double cc = c * c, ab = a * b;
           const bool null = a <= floor2 || b <= floor2;
           if (!null && cc > JACOBI_EARLY * JACOBI_EARLY * ab) big = 1;
-          if (null || cc <= JACOBI_TOL * JACOBI_TOL * ab) continue;
-          // half-angle form of the inner rotation: cos 2th = |d|/sqrt(h), sin 2th = |2c|/sqrt(h)
-          const double d = b - a, c2 = c + c;
-          const double r = rsqrt(fma(d, d, c2 * c2));
-          const double cs2 = fma(0.5 * fabs(d), r, 0.5);          // cos^2 th in [1/2, 1]
-          const double csi = rsqrt(cs2);                          // 1 / cos th
-          const double cs = cs2 * csi;
-          double t = 0.5 * fabs(c2) * r * (csi * csi);            // tan th
-          if ((d < 0.0) != (c2 < 0.0)) t = -t;
-          const double sip = s_si[p], siq = s_si[q];
-          const double tp = t * sq * sip, tq = t * sp * siq;
+          if (!(null || cc <= JACOBI_TOL * JACOBI_TOL * ab)) {
+            // half-angle form of the inner rotation: cos 2th = |d|/sqrt(hh), sin 2th = |2c|/sqrt(hh)
+            const double d = b - a, c2 = c + c;
+            const double r = rsqrt(fma(d, d, c2 * c2));
+            const double cs2 = fma(0.5 * fabs(d), r, 0.5);          // cos^2 th in [1/2, 1]
+            const double csi = rsqrt(cs2);                          // 1 / cos th
+            const double cs = cs2 * csi;
+            double t = 0.5 * fabs(c2) * r * (csi * csi);            // tan th
+            if ((d < 0.0) != (c2 < 0.0)) t = -t;
+            const double sip = s_si[own], siq = s_si[q];
+            const double tp = t * sq * sip, tq = t * sp * siq;
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) {
-            const int i = sub + e * LANES;
-            if (i < k) {
-              gp[i] = fma(-tp, y[e], x[e]);
-              gq[i] = fma(tq, x[e], y[e]);
+            for (int e = 0; e < EPL; ++e) {
+              const int i = sub + e * LANES;
+              const double xn = fma(-tp, y[e], x[e]);
+              if (i < k) gq[i] = fma(tq, x[e], y[e]);
+              x[e] = xn;
+            }
+            __syncwarp(mask);   // every lane of the pair has read the scalars of own and q
+            if (sub == 0) {
+              s_l[own] = sp * cs; s_l[q] = sq * cs;
+              s_si[own] = sip * csi; s_si[q] = siq * csi;
+              s_d[own] = fma(-t, c, a); s_d[q] = fma(t, c, b);
             }
           }
-          __syncwarp(mask);   // every lane of the pair has read s_si[p], s_si[q]
-          if (sub == 0) {
-            s_l[p] = sp * cs; s_l[q] = sq * cs;
-            s_si[p] = sip * csi; s_si[q] = siq * csi;
-            s_d[p] = fma(-t, c, a); s_d[q] = fma(t, c, b);
+          if (handover || round == m - 1) {   // the owned column becomes visible again (visitor of group 0 / end of sweep)
+            double* g = G + own * pitch;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e)
+              if (sub + e * LANES < k) g[sub + e * LANES] = x[e];
           }
         }
         __syncthreads();
+        if (handover && round != m - 1) {
+          own = (round + 1 + h) % m;        // the column entering ring position h, stored by its last partner before the barrier
+          const double* g = G + own * pitch;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) x[e] = sub + e * LANES < k ? g[sub + e * LANES] : 0.0;
+        }
       }
       ++sweep;
       if (!__syncthreads_or(big)) break;
     }
+    JPROF(2);   // sweeps
     // eigenvalues = true column norms^2, eigenvectors = normalised columns, scattered back to original channel indices
     for (int j = group; j < k; j += ngroups) {
       const double* g = G + j * pitch;
@@ -619,6 +664,41 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* _
     }
   }
   if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
+  if (PROF && prof && tid == 0 && prob == 0) {
+    for (int i = 0; i < 8; ++i) prof[i] = pt[i];
+    prof[8] = sweep;
+    prof[9] = k;
+  }
+#undef JPROF
+}
+
+// debug: fp64 pipe probe.  out[0] = cycles of a 4096-long dependent DFMA chain (one warp); out[1] = cycles for every warp of
+// a 512-thread CTA to issue 8 independent chains x 512 DFMAs (4096 per thread)
+__global__ void __launch_bounds__(512) dp_rate_kernel(long long* __restrict__ out, double seed) {
+  double a = seed, b = 1.0 + seed * 1e-9;
+  __syncthreads();
+  long long t0 = clock64();
+  if (threadIdx.x < 32) {
+#pragma unroll 16
+    for (int i = 0; i < 4096; ++i) a = fma(a, b, seed);
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  double c[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j] = seed + j;
+  long long t2 = clock64();
+  for (int i = 0; i < 512; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = fma(c[j], b, seed);
+  }
+  __syncthreads();
+  long long t3 = clock64();
+  double sum = a;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum += c[j];
+  if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t3 - t2; }
+  if (sum == 0.123456) out[2] = 1;
 }
 
 __global__ void __launch_bounds__(256) jacobi_global_kernel(const double* __restrict__ A, int nprob, int C,
@@ -694,6 +774,18 @@ extern "C" int wctb_debug_set_eigh_variant(int v) {
   return WCTB_OK;
 }
 
+static long long* g_eigh_prof = nullptr;   // debug: phase profile of the C > 64 shared-memory solve (tools/eig_diag.py)
+extern "C" int wctb_debug_eigh_profile(long long* buf16) {
+  g_eigh_prof = buf16;
+  return WCTB_OK;
+}
+
+extern "C" int wctb_debug_dp_rate(long long* out3, void* stream) {
+  if (!out3) return WCTB_E_BADARG;
+  dp_rate_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(out3, 1e-3);
+  WCTB_RETURN_LAUNCH();
+}
+
 extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale_host, int add_identity, double* evals,
                                 double* evecs, double* work, int* sweeps_out, void* stream) {
   if (!a || !scale_host || !evals || !evecs || !work || nprob <= 0 || nprob > 8 || C < 2 || (C & 1)) return WCTB_E_BADARG;
@@ -704,15 +796,20 @@ extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double*
     // lanes per column pair x elements per lane (LANES*EPL >= C); ~512 threads measured best on B200 (tools/eig_diag.py)
     if (C > 64) {
       const size_t smem = (size_t)C * jacobi_pitch(C, 8) * sizeof(double);
-      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_chol_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      jacobi_chol_kernel<8, 16><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_chol_kernel<8, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (g_eigh_prof) {
+        WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_chol_kernel<8, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jacobi_chol_kernel<8, 16, true><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out, g_eigh_prof);
+        WCTB_RETURN_LAUNCH();
+      }
+      jacobi_chol_kernel<8, 16, false><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out, nullptr);
     } else if (C > 32) {
       const size_t smem = (size_t)C * jacobi_pitch(C, 8) * sizeof(double);
-      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_chol_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      jacobi_chol_kernel<8, 8><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(jacobi_chol_kernel<8, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jacobi_chol_kernel<8, 8, false><<<nprob, 512, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out, nullptr);
     } else {
       const size_t smem = (size_t)C * jacobi_pitch(C, 4) * sizeof(double);
-      jacobi_chol_kernel<4, 8><<<nprob, 256, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out);
+      jacobi_chol_kernel<4, 8, false><<<nprob, 256, smem, st>>>(a, C, scale, add_identity, evals, evecs, sweeps_out, nullptr);
     }
     WCTB_RETURN_LAUNCH();
   }

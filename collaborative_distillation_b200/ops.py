@@ -230,6 +230,31 @@ def set_eigh_variant(v: int):
     check(_lib.load().wctb_debug_set_eigh_variant(int(v)), "debug_set_eigh_variant")
 
 
+def eigh_profile(a: torch.Tensor, scale):
+    """debug: phase profile (clock64 sums of thread 0) of one C in (64,128] solve -> dict"""
+    buf = torch.zeros(16, device=a.device, dtype=torch.int64)
+    check(_lib.load().wctb_debug_eigh_profile(buf.data_ptr()), "debug_eigh_profile")
+    try:
+        eigh_jacobi(a, scale)
+        torch.cuda.synchronize()
+    finally:
+        check(_lib.load().wctb_debug_eigh_profile(None), "debug_eigh_profile")
+    v = buf.tolist()
+    names = ("load", "cholesky", "sweeps_phase")
+    out = dict(zip(names, v[:3]))
+    out["sweeps"], out["k"] = v[8], v[9]
+    return out
+
+
+def dp_rate():
+    """debug: (cycles per dependent DFMA, DFMA per clock per SM with 16 resident warps)"""
+    buf = torch.zeros(4, device="cuda", dtype=torch.int64)
+    check(_lib.load().wctb_debug_dp_rate(buf.data_ptr(), _stream()), "debug_dp_rate")
+    torch.cuda.synchronize()
+    v = buf.tolist()
+    return v[0] / 4096.0, 512 * 4096.0 / v[1]
+
+
 def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, alpha: float):
     """-> (M fp32 [C,C], b fp32 [C], mean_c fp32 [C])  with csF = M (cF - mean_c) + b"""
     C = c_evals.numel()

@@ -177,6 +177,13 @@ int wctb_fold_wct_into_conv(const float* w_oihw, const float* bias, const float*
  * tools/eig_diag.py).  Process-wide; not meant to be toggled while work is in flight.                                */
 int wctb_debug_set_eigh_variant(int variant);
 
+/* debug: when buf16 != NULL the C in (64,128] solve records clock64() phase times of thread 0 into buf16:
+ * [0] load + compaction, [1] Cholesky, [2] Jacobi sweeps, [8] sweep count, [9] live size k.                          */
+int wctb_debug_eigh_profile(long long* buf16);
+/* debug: fp64 pipe probe -- out3[0] = cycles of a 4096-long dependent DFMA chain, out3[1] = cycles for a 512-thread CTA
+ * to issue 4096 DFMAs per thread in 8 independent chains.                                                           */
+int wctb_debug_dp_rate(long long* out3, void* stream);
+
 /* debug: when buf != NULL a few CTAs of the fused head record clock64() phase stamps into buf[128] (tools/trace_head.py) */
 int wctb_debug_set_trace(long long* buf);
 

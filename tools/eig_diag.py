@@ -34,3 +34,12 @@ for s in (5, 4, 3, 2, 1):
         line += "  | %s sweeps=%2d %.3f ms" % (name, int(sw[0]), e0.elapsed_time(e1) / 5)
     evs = ev[0].sort(descending=True).values
     print(line + "  | lmax=%.3g  l[live-1]/lmax=%.2e" % (evs[0].item(), (evs[live - 1] / evs[0]).item()))
+    if 64 < C <= 128:
+        ops.set_eigh_variant(0)
+        pr = ops.eigh_profile(gram, [1.0 / (n - 1)])
+        tot = float(pr["load"] + pr["cholesky"] + pr["sweeps_phase"])
+        print("   profile (clock64 of thread 0, k=%d, %d sweeps): load %.0f, cholesky %.0f, sweeps %.0f cycles (%.1f%% / %.1f%% / %.1f%%)" % (
+            pr["k"], pr["sweeps"], pr["load"], pr["cholesky"], pr["sweeps_phase"], 100 * pr["load"] / tot,
+            100 * pr["cholesky"] / tot, 100 * pr["sweeps_phase"] / tot))
+lat, thr = ops.dp_rate()
+print("fp64 pipe: %.1f cycles per dependent DFMA, %.1f DFMA/clk/SM with 16 warps x 8 independent chains" % (lat, thr))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run the shared-memory eigensolver on a few small problems; meant to be run under
-`compute-sanitizer --tool racecheck --kernel-name regex:jacobi_chol` (shared-memory hazard check)."""
+`compute-sanitizer --tool racecheck --kernel-name kns=jacobi_chol` (shared-memory hazard check)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
