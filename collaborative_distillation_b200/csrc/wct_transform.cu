@@ -407,6 +407,121 @@ __host__ __device__ inline int jacobi_pitch(int k, int lanes) {
   return lanes >= 8 ? ((k + 7) / 16) * 16 + 8 : ((k + 11) / 16) * 16 + 4;
 }
 
+// the sweep loop of jacobi_chol_kernel for columns of at most LANES*EPL rows; returns the number of sweeps.
+// Round-robin (circle method) over m = k-1 ring positions plus one fixed column.  Pair j of round r is
+// {(r+j) % m, (r-j) % m}; group 0 pairs the fixed column k-1 with column r % m.  The column at ring position
+// j in 1..h (h = (k-2)/2) stays in the registers of one group while it walks from position h down to 1 (its "owner");
+// only the partner (the "visitor", positions -1..-h) goes through shared memory each round, which halves the
+// shared-memory traffic that bounds this loop.  An owner whose column reaches position 1 stores it (it is group 0's
+// visitor next round) and picks up the column entering position h, which its previous partner group has just stored.
+template <int LANES, int EPL>
+__device__ __forceinline__ int jacobi_chol_sweeps(double* __restrict__ G, const int k, const int pitch, const double floor2,
+                                                  double* __restrict__ s_d, double* __restrict__ s_l,
+                                                  double* __restrict__ s_si) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int group = tid / LANES, sub = tid % LANES;
+  const int ngroups = blockDim.x / LANES;
+  const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane & ~(LANES - 1)));
+  const int m = k - 1, h = (k - 2) / 2;
+  const bool active = group < k / 2;
+  int sweep = 0;
+  for (; sweep < JACOBI_MAX_SWEEPS;) {
+    // refresh: fold the scale into the column, exact norm^2
+    for (int j = group; j < k; j += ngroups) {
+      const double sj = s_l[j];
+      double* g = G + j * pitch;
+      double a = 0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = sub + e * LANES;
+        if (i < k) { const double v = g[i] * sj; g[i] = v; a = fma(v, v, a); }
+      }
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
+      __syncwarp(mask);   // every lane of the group has read s_l[j]
+      if (sub == 0) { s_d[j] = a; s_l[j] = 1.0; s_si[j] = 1.0; }
+    }
+    __syncthreads();
+    int big = 0;
+    int own = group == 0 ? k - 1 : group;   // ring position `group` at round 0
+    double x[EPL];
+    if (active) {
+      const double* g = G + own * pitch;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) x[e] = sub + e * LANES < k ? g[sub + e * LANES] : 0.0;
+    }
+    for (int round = 0; round < m; ++round) {
+      bool handover = false;
+      if (active) {
+        int q = round;                                   // group 0: ring position 0
+        if (group != 0) { q = 2 * round - own; if (q < 0) q += m; else if (q >= m) q -= m; }   // in (-m, 2m)
+        handover = group != 0 && (own - round == 1 || own - round == 1 - m);   // ring position of own is 1
+        double* gq = G + q * pitch;
+        double y[EPL];
+        double c0 = 0, c1 = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; e += 2) {
+          const int i0 = sub + e * LANES, i1 = i0 + LANES;
+          y[e] = i0 < k ? gq[i0] : 0.0;
+          y[e + 1] = i1 < k ? gq[i1] : 0.0;
+          c0 = fma(x[e], y[e], c0);
+          c1 = fma(x[e + 1], y[e + 1], c1);
+        }
+        double c = c0 + c1;
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) c += __shfl_xor_sync(mask, c, o);
+        const double sp = s_l[own], sq = s_l[q];
+        const double a = s_d[own], b = s_d[q];
+        c *= sp * sq;
+        const double cc = c * c, ab = a * b;
+        const bool null = a <= floor2 || b <= floor2;
+        if (!null && cc > JACOBI_EARLY * JACOBI_EARLY * ab) big = 1;
+        if (!(null || cc <= JACOBI_TOL * JACOBI_TOL * ab)) {
+          // half-angle form of the inner rotation: cos 2th = |d|/sqrt(hh), sin 2th = |2c|/sqrt(hh)
+          const double d = b - a, c2 = c + c;
+          const double r = rsqrt(fma(d, d, c2 * c2));
+          const double cs2 = fma(0.5 * fabs(d), r, 0.5);          // cos^2 th in [1/2, 1]
+          const double csi = rsqrt(cs2);                          // 1 / cos th
+          const double cs = cs2 * csi;
+          double t = 0.5 * fabs(c2) * r * (csi * csi);            // tan th
+          if ((d < 0.0) != (c2 < 0.0)) t = -t;
+          const double sip = s_si[own], siq = s_si[q];
+          const double tp = t * sq * sip, tq = t * sp * siq;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const int i = sub + e * LANES;
+            const double xn = fma(-tp, y[e], x[e]);
+            if (i < k) gq[i] = fma(tq, x[e], y[e]);
+            x[e] = xn;
+          }
+          __syncwarp(mask);   // every lane of the pair has read the scalars of own and q
+          if (sub == 0) {
+            s_l[own] = sp * cs; s_l[q] = sq * cs;
+            s_si[own] = sip * csi; s_si[q] = siq * csi;
+            s_d[own] = fma(-t, c, a); s_d[q] = fma(t, c, b);
+          }
+        }
+        if (handover || round == m - 1) {   // the owned column becomes visible again (visitor of group 0 / end of sweep)
+          double* g = G + own * pitch;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e)
+            if (sub + e * LANES < k) g[sub + e * LANES] = x[e];
+        }
+      }
+      __syncthreads();
+      if (handover && round != m - 1) {
+        own = round + 1 + h; if (own >= m) own -= m;   // the column entering ring position h, stored by its last partner before the barrier
+        const double* g = G + own * pitch;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) x[e] = sub + e * LANES < k ? g[sub + e * LANES] : 0.0;
+      }
+    }
+    ++sweep;
+    if (!__syncthreads_or(big)) break;
+  }
+  return sweep;
+}
+
 template <int LANES, int EPL, bool PROF>
 __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* __restrict__ A, int C,
                                                                  const JacobiScales scale, int add_identity,
@@ -541,112 +656,13 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* _
     if (tid < k) { s_l[tid] = 1.0; s_si[tid] = 1.0; }
     __syncthreads();
     JPROF(1);   // Cholesky
-    // ---- Hestenes sweeps on the columns of L.
-    // Round-robin (circle method) over m = k-1 ring positions plus one fixed column.  Pair j of round r is
-    // {(r+j) % m, (r-j) % m}; group 0 pairs the fixed column k-1 with column r % m.  The column at ring position
-    // j in 1..h (h = (k-2)/2) stays in the registers of one group while it walks from position h down to 1 (its "owner");
-    // only the partner (the "visitor", positions -1..-h) goes through shared memory each round, which halves the
-    // shared-memory traffic that bounds this loop.  An owner whose column reaches position 1 stores it (it is group 0's
-    // visitor next round) and picks up the column entering position h, which its previous partner group has just stored.
+    // ---- Hestenes sweeps on the columns of L (instantiated for the live size: rows beyond LANES*EPL are never touched)
+    if (EPL >= 16 && k <= LANES * (EPL / 4)) sweep = jacobi_chol_sweeps<LANES, (EPL >= 16 ? EPL / 4 : EPL)>(G, k, pitch, floor2, s_d, s_l, s_si);
+    else if (k <= LANES * (EPL / 2)) sweep = jacobi_chol_sweeps<LANES, EPL / 2>(G, k, pitch, floor2, s_d, s_l, s_si);
+    else sweep = jacobi_chol_sweeps<LANES, EPL>(G, k, pitch, floor2, s_d, s_l, s_si);
     const int group = tid / LANES, sub = tid % LANES;
     const int ngroups = blockDim.x / LANES;
     const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane & ~(LANES - 1)));
-    const int m = k - 1, h = (k - 2) / 2;
-    const bool active = group < k / 2;
-    for (; sweep < JACOBI_MAX_SWEEPS;) {
-      // refresh: fold the scale into the column, exact norm^2
-      for (int j = group; j < k; j += ngroups) {
-        const double sj = s_l[j];
-        double* g = G + j * pitch;
-        double a = 0;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          const int i = sub + e * LANES;
-          if (i < k) { const double v = g[i] * sj; g[i] = v; a = fma(v, v, a); }
-        }
-#pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
-        __syncwarp(mask);   // every lane of the group has read s_l[j]
-        if (sub == 0) { s_d[j] = a; s_l[j] = 1.0; s_si[j] = 1.0; }
-      }
-      __syncthreads();
-      int big = 0;
-      int own = group == 0 ? k - 1 : group;   // ring position `group` at round 0
-      double x[EPL];
-      if (active) {
-        const double* g = G + own * pitch;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) x[e] = sub + e * LANES < k ? g[sub + e * LANES] : 0.0;
-      }
-      for (int round = 0; round < m; ++round) {
-        bool handover = false;
-        if (active) {
-          int q = round;                                   // group 0: ring position 0
-          if (group != 0) { q = (2 * round - own) % m; if (q < 0) q += m; }
-          handover = group != 0 && (own - round + m) % m == 1;   // own < m, round < m
-          double* gq = G + q * pitch;
-          double y[EPL];
-          double c0 = 0, c1 = 0;
-#pragma unroll
-          for (int e = 0; e < EPL; e += 2) {
-            const int i0 = sub + e * LANES, i1 = i0 + LANES;
-            y[e] = i0 < k ? gq[i0] : 0.0;
-            y[e + 1] = i1 < k ? gq[i1] : 0.0;
-            c0 = fma(x[e], y[e], c0);
-            c1 = fma(x[e + 1], y[e + 1], c1);
-          }
-          double c = c0 + c1;
-#pragma unroll
-          for (int o = LANES / 2; o > 0; o >>= 1) c += __shfl_xor_sync(mask, c, o);
-          const double sp = s_l[own], sq = s_l[q];
-          const double a = s_d[own], b = s_d[q];
-          c *= sp * sq;
-          const double cc = c * c, ab = a * b;
-          const bool null = a <= floor2 || b <= floor2;
-          if (!null && cc > JACOBI_EARLY * JACOBI_EARLY * ab) big = 1;
-          if (!(null || cc <= JACOBI_TOL * JACOBI_TOL * ab)) {
-            // half-angle form of the inner rotation: cos 2th = |d|/sqrt(hh), sin 2th = |2c|/sqrt(hh)
-            const double d = b - a, c2 = c + c;
-            const double r = rsqrt(fma(d, d, c2 * c2));
-            const double cs2 = fma(0.5 * fabs(d), r, 0.5);          // cos^2 th in [1/2, 1]
-            const double csi = rsqrt(cs2);                          // 1 / cos th
-            const double cs = cs2 * csi;
-            double t = 0.5 * fabs(c2) * r * (csi * csi);            // tan th
-            if ((d < 0.0) != (c2 < 0.0)) t = -t;
-            const double sip = s_si[own], siq = s_si[q];
-            const double tp = t * sq * sip, tq = t * sp * siq;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) {
-              const int i = sub + e * LANES;
-              const double xn = fma(-tp, y[e], x[e]);
-              if (i < k) gq[i] = fma(tq, x[e], y[e]);
-              x[e] = xn;
-            }
-            __syncwarp(mask);   // every lane of the pair has read the scalars of own and q
-            if (sub == 0) {
-              s_l[own] = sp * cs; s_l[q] = sq * cs;
-              s_si[own] = sip * csi; s_si[q] = siq * csi;
-              s_d[own] = fma(-t, c, a); s_d[q] = fma(t, c, b);
-            }
-          }
-          if (handover || round == m - 1) {   // the owned column becomes visible again (visitor of group 0 / end of sweep)
-            double* g = G + own * pitch;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e)
-              if (sub + e * LANES < k) g[sub + e * LANES] = x[e];
-          }
-        }
-        __syncthreads();
-        if (handover && round != m - 1) {
-          own = (round + 1 + h) % m;        // the column entering ring position h, stored by its last partner before the barrier
-          const double* g = G + own * pitch;
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) x[e] = sub + e * LANES < k ? g[sub + e * LANES] : 0.0;
-        }
-      }
-      ++sweep;
-      if (!__syncthreads_or(big)) break;
-    }
     JPROF(2);   // sweeps
     // eigenvalues = true column norms^2, eigenvectors = normalised columns, scattered back to original channel indices
     for (int j = group; j < k; j += ngroups) {
