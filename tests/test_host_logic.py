@@ -220,3 +220,52 @@ def test_t7_reader_shared_storage_and_views(tmp_path):
         f.write(blob[:-5])
     with pytest.raises(EOFError):
         t7.load_t7(p)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the owner/visitor column schedule of the shared-memory eigensolver (csrc/wct_transform.cu: jacobi_chol_sweeps)
+@pytest.mark.parametrize("k", [2, 4, 24, 28, 52, 60, 100, 128])
+def test_jacobi_owner_visitor_schedule(k):
+    """Replays the ring bookkeeping of the kernel on the host: every group keeps one column in registers ('owner'), its
+    partner ('visitor') goes through shared memory.  Checks that every unordered pair meets exactly once per sweep, that no
+    group ever reads a shared-memory copy that is stale (owned by someone's registers), and the hand-over rule."""
+    m, h, ng = k - 1, (k - 2) // 2, k // 2
+    valid = [True] * k                       # shared-memory copy of column c is current
+    own = [k - 1 if g == 0 else g for g in range(ng)]
+    for c in own:
+        assert valid[c]
+        valid[c] = False
+    seen = set()
+    for r in range(m):
+        visitors, handing = [], []
+        for g in range(ng):
+            c = own[g]
+            if g == 0:
+                q = r
+            else:
+                q = 2 * r - c
+                q = q + m if q < 0 else (q - m if q >= m else q)
+            assert q != c and valid[q], (r, g, c, q)
+            pair = (min(c, q), max(c, q))
+            assert pair not in seen
+            seen.add(pair)
+            visitors.append(q)
+            if g != 0 and (c - r == 1 or c - r == 1 - m):
+                handing.append(g)
+        assert len(set(visitors)) == ng and not set(visitors) & set(own)
+        assert len(handing) <= 1
+        for g in handing:                    # stored before the barrier
+            valid[own[g]] = True
+        for g in handing:                    # picked up after the barrier
+            if r != m - 1:
+                cn = r + 1 + h
+                cn = cn - m if cn >= m else cn
+                assert valid[cn], (r, g, cn)
+                valid[cn] = False
+                own[g] = cn
+            else:
+                own[g] = None
+        if r != m - 1:
+            for g in range(1, ng):
+                assert 1 <= (own[g] - (r + 1)) % m <= h
+    assert len(seen) == k * (k - 1) // 2
