@@ -6,6 +6,8 @@ log printer: :78-85; 5-stage loop: :120-125; output naming: :127) running the B2
 
 Everything between image decode and image encode stays on the GPU (`WCT.stylize`); additive flags:
   --precision {tf32,fp32}   conv engine (default tf32 tensor cores)       --weights_root DIR  (default ../trained_models)
+  --gpu_io                  decode (nvJPEG), Resize, ToTensor, save_image quantisation and JPEG encode on the GPU
+                            (collaborative_distillation_b200.image_io; PIL-bit-exact resize / conversions)
 """
 import argparse
 import os
@@ -39,6 +41,7 @@ FLAGS = [  # (name, kwargs) -- same names, types, defaults and help as the refer
     # additive
     ("--precision", dict(type=str, default="tf32", choices=["tf32", "fp32"])),
     ("--weights_root", dict(type=str, default="../trained_models")),
+    ("--gpu_io", dict(action="store_true", help="image decode / resize / encode on the GPU (nvJPEG + libwctb kernels)")),
 ]
 WEIGHT_DIRS = {  # WCT.py:36-70
     "original": ("original_wct_models/vgg_normalised_conv%d_1.t7", "original_wct_models/feature_invertor_conv%d_1.t7"),
@@ -69,6 +72,26 @@ class LogPrinter:
         print(str(sth), file=self.log, flush=True)
 
 
+class _DeviceLoader:
+    """--gpu_io: same (content, style, [name]) items as DataLoader(batch_size=1) over data_loader.Dataset, but decoded,
+    resized and converted on the GPU (data_loader.py:46-76 -> image_io.load_image)."""
+
+    def __init__(self, dataset, image_io):
+        self.ds, self.io = dataset, image_io
+
+    def __len__(self):
+        return len(self.ds)
+
+    def __iter__(self):
+        for i in range(len(self.ds)):
+            c, s, name = self.ds.paths(i)
+            if c is None:      # texture synthesis: noise content of the texture's size (data_loader.py:61-76)
+                style = self.io.load_image(s, self.ds.style_size, longer_side=True)
+                yield torch.rand_like(style), style, [name]
+            else:
+                yield self.io.load_image(c, self.ds.content_size), self.io.load_image(s, self.ds.style_size), [name]
+
+
 def main(argv=None):
     args = parse(argv)
     import torchvision.utils as vutils
@@ -83,7 +106,10 @@ def main(argv=None):
     dataset = Dataset(args.UHD_contentPath if args.UHD else args.contentPath, args.UHD_stylePath if args.UHD else args.stylePath,
                       args.texturePath, args.content_size, args.style_size, args.picked_content_mark, args.picked_style_mark,
                       args.synthesis)
-    loader = torch.utils.data.DataLoader(dataset=dataset, batch_size=1, shuffle=False)
+    if args.gpu_io:
+        loader = _DeviceLoader(dataset, P.image_io)
+    else:
+        loader = torch.utils.data.DataLoader(dataset=dataset, batch_size=1, shuffle=False)
     wct = P.WCT(args).cuda()
     log("Number of content-style pairs: %s" % len(loader))
     total, n = 0.0, 0
@@ -97,7 +123,10 @@ def main(argv=None):
             style_cache[skey] = wct.prepare_style(sImg.cuda())
         out = wct.stylize(cImg.cuda(), None, alpha=args.alpha, num_run=args.num_run, style_cache=style_cache[skey])   # WCT.py:120-125
         out_path = os.path.join(args.outf, "%s_mode=%s_alpha=%s_%s" % (args.log_mark, args.mode, args.alpha, imname))
-        vutils.save_image(out.cpu(), out_path)                                                 # WCT.py:127-128 (timed, like the reference)
+        if args.gpu_io:
+            P.image_io.save_image(out, out_path)               # quantise + JPEG-encode on the device; only the bitstream comes down
+        else:
+            vutils.save_image(out.cpu(), out_path)                                             # WCT.py:127-128 (timed, like the reference)
         dt = time.time() - start
         total, n = total + dt, n + 1
         log("Elapsed time is: %.4f seconds" % dt)

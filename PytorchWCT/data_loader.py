@@ -42,6 +42,14 @@ class Dataset(data.Dataset):
             img = transforms.Resize(size)(img)                     # shorter side -> size (data_loader.py:52-55)
         return self.to_tensor(img)
 
+    def paths(self, index):
+        """(content path or None, style / texture path, output name) of pair `index` -- for the device-side decode
+        (`--gpu_io`, collaborative_distillation_b200.image_io.load_image) that replaces __getitem__'s PIL pipeline."""
+        c, s = self.items[index]
+        if self.synthesis:
+            return None, os.path.join(self.texturePath, s), s.split(".")[0] + ".jpg"
+        return os.path.join(self.contentPath, c), os.path.join(self.stylePath, s), c.split(".")[0] + "+" + s.split(".")[0] + ".jpg"
+
     def __getitem__(self, index):
         c, s = self.items[index]
         if not self.synthesis:

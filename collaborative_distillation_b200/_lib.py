@@ -41,6 +41,11 @@ SIGNATURES = {
     "wctb_wct_matrix": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p],
     "wctb_wct_apply": [_p, _p, _p, _p, _p, _i, _ll, _i, _p],
     "wctb_fold_wct_into_conv": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "wctb_u8hwc_to_nchw": [_p, _p, _i, _i, _p],
+    "wctb_nchw_to_u8hwc": [_p, _p, _i, _i, _p],
+    "wctb_resize_ksize": [_i, _i],
+    "wctb_resize_coeffs_host": [_i, _i, _p, _p],
+    "wctb_resize_u8_pass": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p],
     "wctb_debug_set_eigh_variant": [_i],
     "wctb_debug_eigh_profile": [_p],
     "wctb_debug_dp_rate": [_p, _p],
@@ -83,6 +88,60 @@ def load():
         raise WctbError("libwctb ABI version mismatch")
     _lib = lib
     return lib
+
+
+# ---- libwctb_io.so: nvJPEG behind include/wctb_io.h (stateful codec; separate library) ----------------------
+IO_LIB_PATH = os.path.join(_HERE, "csrc", "libwctb_io.so")
+_sz = ctypes.c_size_t
+_psz = ctypes.POINTER(ctypes.c_size_t)
+_pi = ctypes.POINTER(ctypes.c_int)
+IO_SIGNATURES = {
+    "wctb_io_abi_version": [],
+    "wctb_io_last_status": [],
+    "wctb_io_create": [ctypes.POINTER(_p)],
+    "wctb_io_jpeg_info": [_p, _p, _sz, _pi, _pi, _pi, _pi],
+    "wctb_io_jpeg_decode": [_p, _p, _sz, _p, _i, _i, _p],
+    "wctb_io_jpeg_encode": [_p, _p, _i, _i, _i, _i, _p, _psz],
+    "wctb_io_jpeg_retrieve": [_p, _p, _sz, _psz, _p],
+}
+_io_lib = None
+
+
+def load_io():
+    """Load libwctb_io.so (once).  Raises WctbError if it is missing or nvJPEG cannot be resolved."""
+    global _io_lib
+    if _io_lib is not None:
+        return _io_lib
+    if not os.path.exists(IO_LIB_PATH):
+        raise WctbError("libwctb_io.so not found at %s -- run the build (csrc/build.py)" % IO_LIB_PATH)
+    try:
+        lib = ctypes.CDLL(IO_LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise WctbError("failed to load %s: %s" % (IO_LIB_PATH, e))
+    for name, args in IO_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _i
+    lib.wctb_io_destroy.argtypes = [_p]
+    lib.wctb_io_destroy.restype = None
+    lib.wctb_io_error_string.argtypes = [_i]
+    lib.wctb_io_error_string.restype = ctypes.c_char_p
+    if lib.wctb_io_abi_version() != 1:
+        raise WctbError("libwctb_io ABI version mismatch")
+    _io_lib = lib
+    return lib
+
+
+def check_io(code: int, what: str):
+    if code != 0:
+        lib = load_io()
+        raise WctbIoError(code, "%s failed: %s (status %d)" % (what, lib.wctb_io_error_string(code).decode(), lib.wctb_io_last_status()))
+
+
+class WctbIoError(WctbError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
 
 
 def check(code: int, what: str):

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["conv_fp32.cu", "conv_umma.cu", "wct_transform.cu"]
+SOURCES = ["conv_fp32.cu", "conv_umma.cu", "wct_transform.cu", "image_io.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
@@ -33,6 +33,18 @@ def build(verbose=False, force=False):
         objs.append(o)
     if force or _stale(out, objs):
         subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-lcudart"])
+    build_io(force=force)
+    return out
+
+
+def build_io(force=False):
+    """libwctb_io.so: the nvJPEG binding of include/wctb_io.h (host C++ only; separate so that libwctb.so stays
+    free of library dependencies beyond cudart)."""
+    out = os.path.join(HERE, "libwctb_io.so")
+    src = os.path.join(HERE, "jpeg_io.cpp")
+    if force or _stale(out, [src, os.path.join(ROOT, "include", "wctb_io.h")]):
+        subprocess.check_call([NVCC, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                               "-o", out, src, "-lnvjpeg", "-lcudart"])
     return out
 
 

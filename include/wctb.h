@@ -173,6 +173,29 @@ int wctb_fold_wct_into_conv(const float* w_oihw, const float* bias, const float*
                             const float* mean_c, float* w_out, float* b_out, int Cin, int Cout,
                             void* stream);
 
+/* ---- image I/O around the path: byte / integer kernels, bit-exact --------------------
+ * Images here are interleaved 8-bit RGB, [H][W][3] (what PIL / nvJPEG produce and consume).
+ *
+ * u8hwc_to_nchw  replaces transforms.ToTensor() (reference data_loader.py:56-57): fp32 [3][H][W] = u8 / 255
+ *                (correctly rounded fp32 division, as torch's `.to(float32).div(255)`).
+ * nchw_to_u8hwc  replaces the quantisation inside vutils.save_image() (reference WCT.py:128):
+ *                u8 = trunc(clamp(x*255 + 0.5, 0, 255)) with the two fp32 roundings of `mul(255).add_(0.5)`.        */
+int wctb_u8hwc_to_nchw(const uint8_t* src_hwc, float* dst_nchw, int H, int W, void* stream);
+int wctb_nchw_to_u8hwc(const float* src_nchw, uint8_t* dst_hwc, int H, int W, void* stream);
+
+/* 8-bit antialiased bilinear resize = transforms.Resize(size) on a PIL image (reference data_loader.py:52-55), i.e.
+ * Pillow's ImagingResample for 8-bit pixels: per output pixel a normalised triangle filter of support
+ * max(in/out, 1), coefficients in 22-bit fixed point, horizontal pass then vertical pass through an 8-bit intermediate.
+ *   wctb_resize_ksize        HOST: taps per output pixel for in_size -> out_size (>= 3), or WCTB_E_BADARG
+ *   wctb_resize_coeffs_host  HOST (needs no GPU): bounds_host[2*out] = (first tap, tap count),
+ *                            coeffs_host[out*ksize] = fixed-point weights; the caller copies both to the device
+ *   wctb_resize_u8_pass      DEVICE: resample axis 1 (width: dst is [H][out][3]) or axis 0 (height: dst is [out][W][3])
+ * A full resize is: pass(axis=1) if the width changes, then pass(axis=0) if the height changes (PIL's order).       */
+int wctb_resize_ksize(int in_size, int out_size);
+int wctb_resize_coeffs_host(int in_size, int out_size, int* bounds_host, int* coeffs_host);
+int wctb_resize_u8_pass(const uint8_t* src_hwc, uint8_t* dst_hwc, int H, int W, int out_size, int axis,
+                        const int* bounds, const int* coeffs, int ksize, void* stream);
+
 /* debug: 0 (default) = Cholesky-preconditioned Jacobi for C <= 128; 1 = legacy Jacobi on the matrix itself (A/B timing,
  * tools/eig_diag.py).  Process-wide; not meant to be toggled while work is in flight.                                */
 int wctb_debug_set_eigh_variant(int variant);
