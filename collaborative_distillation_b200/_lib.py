@@ -39,6 +39,7 @@ SIGNATURES = {
     "wctb_centered_gram_fast": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "wctb_eigh_jacobi": [_p, _i, _i, ctypes.POINTER(ctypes.c_double), _i, _p, _p, _p, _p, _p],
     "wctb_wct_matrix": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p],
+    "wctb_wct_matrix_topk": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _i, _i, _p, _p, _p, _p, _p],
     "wctb_wct_apply": [_p, _p, _p, _p, _p, _i, _ll, _i, _p],
     "wctb_fold_wct_into_conv": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "wctb_u8hwc_to_nchw": [_p, _p, _i, _i, _p],

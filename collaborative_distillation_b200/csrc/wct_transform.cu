@@ -875,12 +875,15 @@ __global__ void eig_max_kernel(const double* __restrict__ e, int C, double* __re
   }
 }
 // out[i][j] = sum_k f(e_k) v_k[i] v_k[j]   (power = -0.5 or +0.5, thresholded at tau*emax)
+// thr_abs (optional): absolute threshold written by eig_topk_threshold_kernel; a direction is then kept iff e >= *thr_abs.
 __global__ void spectral_fn_kernel(const double* __restrict__ e, const double* __restrict__ v, int C, double tau,
-                                   const double* __restrict__ emax, double power, double* __restrict__ out) {
+                                   const double* __restrict__ emax, double power, double* __restrict__ out,
+                                   const double* __restrict__ thr_abs = nullptr) {
   int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
   __shared__ double vi[16][17], vj[16][17], f[16];
   double acc = 0;
-  const double thr = tau * (*emax);
+  // default: keep e > tau*emax.  With thr_abs: keep e >= *thr_abs, written as e > (largest double below *thr_abs).
+  const double thr = thr_abs ? nextafter(*thr_abs, -1.0) : tau * (*emax);
   for (int k0 = 0; k0 < C; k0 += 16) {
     int k = k0 + threadIdx.y;
     vi[threadIdx.y][threadIdx.x] = (k < C && blockIdx.y * 16 + threadIdx.x < C) ? v[(long long)k * C + blockIdx.y * 16 + threadIdx.x] : 0.0;
@@ -923,6 +926,64 @@ __global__ void wct_matrix_kernel(const double* __restrict__ col, const double* 
     mc_out[i] = (float)c_mean[i];
   }
 }
+// Eigenvalue truncation knobs of the reference (util_wct.py:26-27 NumEigenValue / RatEigenValue, commented uses at :87-88,
+// :113-114): keep only the `keep` largest directions (and, as always, only those above tau*emax).
+// thr_out = max(keep-th largest eigenvalue, smallest eigenvalue above tau*emax); +inf when nothing qualifies.  C <= 1024.
+__global__ void eig_topk_threshold_kernel(const double* __restrict__ e, int C, int keep, double tau, double* __restrict__ thr_out) {
+  __shared__ double se[1024];
+  __shared__ double red[32];
+  __shared__ double s_kth;
+  const int tid = threadIdx.x, nw = blockDim.x >> 5;
+  for (int i = tid; i < C; i += blockDim.x) se[i] = e[i];
+  if (tid == 0) s_kth = 0.0;
+  __syncthreads();
+  double m = 0;
+  for (int i = tid; i < C; i += blockDim.x) m = fmax(m, se[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  double emax = red[0];
+  for (int i = 1; i < nw; ++i) emax = fmax(emax, red[i]);
+  __syncthreads();
+  const double thr_rel = tau * emax;
+  const int want = (keep <= 0 || keep > C ? C : keep) - 1;     // rank (0 = largest) of the last kept eigenvalue
+  double mn = INFINITY;
+  for (int i = tid; i < C; i += blockDim.x) {
+    const double ei = se[i];
+    int rank = 0;
+    for (int j = 0; j < C; ++j) rank += (se[j] > ei) || (se[j] == ei && j < i);
+    if (rank == want) s_kth = ei;                              // ranks are unique: exactly one writer
+    if (ei > thr_rel) mn = fmin(mn, ei);
+  }
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mn;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < nw; ++i) mn = fmin(mn, red[i]);
+    *thr_out = fmax(s_kth, mn);
+  }
+}
+extern "C" int wctb_wct_matrix_topk(const double* c_evals, const double* c_evecs, const double* c_mean, const double* s_evals,
+                                    const double* s_evecs, const double* s_mean, int C, double tau, double alpha, int keep_c,
+                                    int keep_s, float* m_out, float* b_out, float* mean_c_out, double* work, void* stream) {
+  if (!c_evals || !c_evecs || !c_mean || !s_evals || !s_evecs || !s_mean || !m_out || !b_out || !mean_c_out || !work ||
+      C <= 0 || C > 1024)
+    return WCTB_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long CC = (long long)C * C;
+  double* wh = work;
+  double* col = work + CC;
+  double* m64 = work + 2 * CC;
+  double* thr = work + 3 * CC;  // [2] absolute thresholds (content, style)
+  eig_topk_threshold_kernel<<<1, 256, 0, st>>>(c_evals, C, keep_c, tau, thr);
+  eig_topk_threshold_kernel<<<1, 256, 0, st>>>(s_evals, C, keep_s, tau, thr + 1);
+  dim3 blk(16, 16), grd((C + 15) / 16, (C + 15) / 16);
+  spectral_fn_kernel<<<grd, blk, 0, st>>>(c_evals, c_evecs, C, tau, thr, -0.5, wh, thr);
+  spectral_fn_kernel<<<grd, blk, 0, st>>>(s_evals, s_evecs, C, tau, thr + 1, 0.5, col, thr + 1);
+  wct_matrix_kernel<<<grd, blk, 0, st>>>(col, wh, C, alpha, c_mean, s_mean, m_out, b_out, mean_c_out, m64);
+  WCTB_RETURN_LAUNCH();
+}
+
 extern "C" int wctb_wct_matrix(const double* c_evals, const double* c_evecs, const double* c_mean, const double* s_evals,
                                const double* s_evecs, const double* s_mean, int C, double tau, double alpha,
                                float* m_out, float* b_out, float* mean_c_out, double* work, void* stream) {

@@ -177,7 +177,7 @@ class JpegCodec:
         m = ctypes.c_size_t()
         check_io(self._lib.wctb_io_jpeg_retrieve(self._h, out, n.value, ctypes.byref(m), st), "jpeg_retrieve")
         _counts["jpeg_encode"] += 1
-        return bytes(out[:m.value])
+        return ctypes.string_at(out, m.value)
 
 
 _default_codec = None

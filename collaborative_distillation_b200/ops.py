@@ -255,8 +255,9 @@ def dp_rate():
     return v[0] / 4096.0, 512 * 4096.0 / v[1]
 
 
-def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, alpha: float):
-    """-> (M fp32 [C,C], b fp32 [C], mean_c fp32 [C])  with csF = M (cF - mean_c) + b"""
+def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, alpha: float, keep_c: int = 0, keep_s: int = 0):
+    """-> (M fp32 [C,C], b fp32 [C], mean_c fp32 [C])  with csF = M (cF - mean_c) + b.
+    keep_c / keep_s > 0: use only that many of the largest content / style eigen-directions (util_wct.py:26-27,87-88)."""
     C = c_evals.numel()
     dev = c_evals.device
     m = torch.empty(C, C, device=dev, dtype=torch.float32)
@@ -264,6 +265,13 @@ def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, a
     mc = torch.empty(C, device=dev, dtype=torch.float32)
     work = torch.empty(3 * C * C + 8, device=dev, dtype=torch.float64)
     f64 = torch.float64
+    if keep_c > 0 or keep_s > 0:
+        check(_lib.load().wctb_wct_matrix_topk(_need(c_evals, f64), _need(c_evecs, f64), _need(c_mean, f64), _need(s_evals, f64),
+                                               _need(s_evecs, f64), _need(s_mean, f64), C, float(tau), float(alpha), int(keep_c),
+                                               int(keep_s), _need(m), _need(b), _need(mc), _need(work, f64), _stream()),
+              "wct_matrix_topk")
+        _count("wct_matrix")
+        return m, b, mc
     check(_lib.load().wctb_wct_matrix(_need(c_evals, f64), _need(c_evecs, f64), _need(c_mean, f64), _need(s_evals, f64),
                                       _need(s_evecs, f64), _need(s_mean, f64), C, float(tau), float(alpha), _need(m),
                                       _need(b), _need(mc), _need(work, f64), _stream()), "wct_matrix")

@@ -13,6 +13,8 @@ Differences from the reference, all stated in DESIGN.md:
 """
 from __future__ import annotations
 
+import collections
+
 import torch
 import torch.nn as nn
 
@@ -21,6 +23,8 @@ from ._lib import WctbError
 
 EigenValueThre = 1e-100   # kept for reference-compat; see TAU
 TAU = 1e-7                # relative eigenvalue threshold used by the GPU path
+NumEigenValue = None      # util_wct.py:26 (30 there; its use at :87,:113 is commented out): keep only this many directions
+RatEigenValue = None      # util_wct.py:27 (0.25 there; use at :88,:114 commented out): keep int(C * ratio) directions
 
 
 class WCT(nn.Module):
@@ -36,6 +40,8 @@ class WCT(nn.Module):
             setattr(self, "e%d" % k, nets.ENCODERS[mode][k - 1](getattr(args, "e%d" % k, None)))
             setattr(self, "d%d" % k, nets.DECODERS[mode][k - 1](getattr(args, "d%d" % k, None)))
         self.tau = TAU
+        self.num_eig = NumEigenValue   # per-instance knobs; None = keep all directions (the reference's active behaviour)
+        self.rat_eig = RatEigenValue
         self.dist = None          # set by parallel.StripGroup for multi-GPU runs
         self.fold_into_decoder = True   # csF = M(cF - mu) + b folded exactly into the decoder's first conv (no apply pass)
         self.overlap_style = True  # single-GPU stylize(): run the (content-independent) style branch on a side stream
@@ -43,7 +49,16 @@ class WCT(nn.Module):
         self._main = None
         self.fast_stats = True     # TF32 mode, single GPU: fp32-product Gram (see _moments)
         self.use_graph = True      # single-GPU stylize(): capture the two-stream schedule in a CUDA graph per input shape
-        self._graphs = {}
+        self.max_graphs = 4        # captured graphs kept (LRU): each one pins the activations of its input shape in HBM
+        self._graphs = collections.OrderedDict()
+
+    def _keep(self, C):
+        """number of eigen-directions kept for content and style (0 = all): k = NumEigenValue, or int(C * RatEigenValue)"""
+        if self.num_eig is not None:
+            return int(self.num_eig)
+        if self.rat_eig is not None:
+            return int(C * self.rat_eig)
+        return 0
 
     # ------------------------------------------------------------------ statistics -> (M, b, mean_c)
     def _moments(self, x_p4, region, count, gram_out):
@@ -78,7 +93,8 @@ class WCT(nn.Module):
             evals, evecs = torch.cat([ce, se]), torch.cat([cv, sv])
         else:
             evals, evecs = ops.eigh_jacobi(grams, scale)
-        return ops.wct_matrix(evals[0], evecs[0], c_mean, evals[1], evecs[1], s_mean, self.tau, alpha)
+        k = self._keep(C)
+        return ops.wct_matrix(evals[0], evecs[0], c_mean, evals[1], evecs[1], s_mean, self.tau, alpha, k, k)
 
     # ------------------------------------------------------------------ reference API
     def whiten_and_color(self, cF, sF):
@@ -216,7 +232,7 @@ class WCT(nn.Module):
                     (s_mean, s_e, s_v), ev = style_res[s]
                     if ev is not None:
                         main.wait_event(ev)
-                    m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
+                    m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha), self._keep(C), self._keep(C))
                     if self.fold_into_decoder:
                         L0 = getattr(dec, dec.layers[0]["name"])
                         w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
@@ -243,7 +259,7 @@ class WCT(nn.Module):
             style = content[..., :1, :1]       # unused placeholder with a stable shape
         host = (not content.is_cuda) and (not style.is_cuda) and content.is_pinned() and style.is_pinned()
         key = (tuple(content.shape), tuple(style.shape), float(alpha), int(num_run), tuple(stages), nets.get_precision(),
-               bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)),
+               bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)), self.num_eig, self.rat_eig, float(self.tau),
                (content.data_ptr(), style.data_ptr()) if host else None, id(style_cache) if style_cache is not None else None)
         ent = self._graphs.get(key)
         if ent is None:
@@ -268,6 +284,10 @@ class WCT(nn.Module):
                 torch.cuda.synchronize()
                 ent = (None, None, None, None, 0, None)
             self._graphs[key] = ent
+            while len(self._graphs) > max(1, int(self.max_graphs)):     # a folder of differently sized images must not
+                self._graphs.popitem(last=False)                        # accumulate one private memory pool per shape
+        else:
+            self._graphs.move_to_end(key)
         graph, sc, ss, out, nlaunch, _keepalive = ent
         if graph is None:
             return self._stylize_two_streams(content, style, alpha, num_run, stages, style_cache)

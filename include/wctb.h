@@ -159,6 +159,14 @@ int wctb_wct_matrix(const double* c_evals, const double* c_evecs, const double* 
                     int C, double tau, double alpha, float* m_out, float* b_out,
                     float* mean_c_out, double* work, void* stream);
 
+/* same, with the reference's eigenvalue-truncation knobs (util_wct.py:26-27 NumEigenValue / RatEigenValue; their uses at
+ * :87-88 and :113-114 are commented out in the reference): only the keep_c (content) / keep_s (style) LARGEST directions
+ * are used, and of those only the ones above tau*max as before; keep <= 0 or >= C keeps all (== wctb_wct_matrix).      */
+int wctb_wct_matrix_topk(const double* c_evals, const double* c_evecs, const double* c_mean,
+                         const double* s_evals, const double* s_evecs, const double* s_mean,
+                         int C, double tau, double alpha, int keep_c, int keep_s, float* m_out, float* b_out,
+                         float* mean_c_out, double* work, void* stream);
+
 /* csF = M (cF - mean_c) + b on a P4 map of npix pixels (whole extended strip).
  * replaces: torch.mm(step2, cF), torch.mm(..., whiten_cF), + s_mean (util_wct.py:120,125,126). */
 int wctb_wct_apply(const float* x_p4, const float* m, const float* b, const float* mean_c,

@@ -135,7 +135,7 @@ def _rank(e):
     return k
 
 
-def whiten_and_color(cF: torch.Tensor, sF: torch.Tensor, numpy_variant: bool = False) -> torch.Tensor:
+def whiten_and_color(cF: torch.Tensor, sF: torch.Tensor, numpy_variant: bool = False, keep: int | None = None) -> torch.Tensor:
     """cF [C,HWc], sF [C,HWs] (any float dtype; computed in fp64) -> [C,HWc] fp64.
 
     numpy_variant=True reproduces whiten_and_color_np's `+ eye(C)` on the content
@@ -160,6 +160,8 @@ def whiten_and_color(cF: torch.Tensor, sF: torch.Tensor, numpy_variant: bool = F
     _, s_e, s_vh = torch.linalg.svd(s_cov)                 # :100
     s_v = s_vh.t()
     k_s = _rank(s_e)
+    if keep is not None:                                   # :87-88, :113-114 (commented out in the reference):
+        k_c, k_s = min(k_c, int(keep)), min(k_s, int(keep))   # k = NumEigenValue or int(C * RatEigenValue)
 
     c_d = c_e[:k_c].pow(-0.5)                              # :117
     whiten = (c_v[:, :k_c] * c_d) @ c_v[:, :k_c].t() @ cFc  # :118-120

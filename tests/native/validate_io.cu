@@ -199,6 +199,54 @@ static int check_jpeg(int H, int W) {
   return fail;
 }
 
+// wctb_wct_matrix_topk with identity eigenvectors: M must be diagonal with alpha*sqrt(es_i)/sqrt(ec_i) on the directions
+// kept on BOTH sides (+ (1-alpha)), which checks the rank / threshold logic on unsorted spectra with zeros.
+static int check_topk(int C, int keep_c, int keep_s) {
+  std::vector<double> ec(C), es(C), V((size_t)C * C, 0.0), mean(C, 0.0);
+  for (int i = 0; i < C; ++i) {
+    ec[i] = (i % 5 == 3) ? 0.0 : 0.01 + (double)((i * 7919) % 101);   // unsorted, distinct, a few exact zeros
+    es[i] = (i % 7 == 2) ? 0.0 : 0.5 + (double)((i * 104729) % 89);
+    V[(size_t)i * C + i] = 1.0;
+  }
+  const double tau = 1e-7, alpha = 0.75;
+  double *d_ec, *d_es, *d_V, *d_mean, *d_work;
+  float *d_m, *d_b, *d_mc;
+  CK(cudaMalloc(&d_ec, C * 8)); CK(cudaMalloc(&d_es, C * 8)); CK(cudaMalloc(&d_V, (size_t)C * C * 8)); CK(cudaMalloc(&d_mean, C * 8));
+  CK(cudaMalloc(&d_work, ((size_t)3 * C * C + 8) * 8)); CK(cudaMalloc(&d_m, (size_t)C * C * 4)); CK(cudaMalloc(&d_b, C * 4)); CK(cudaMalloc(&d_mc, C * 4));
+  CK(cudaMemcpy(d_ec, ec.data(), C * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_es, es.data(), C * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_V, V.data(), (size_t)C * C * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_mean, mean.data(), C * 8, cudaMemcpyHostToDevice));
+  int rc = wctb_wct_matrix_topk(d_ec, d_V, d_mean, d_es, d_V, d_mean, C, tau, alpha, keep_c, keep_s, d_m, d_b, d_mc, d_work, nullptr);
+  if (rc != 0) { LOG("wct_matrix_topk rc=%d  FAIL\n", rc); return 1; }
+  std::vector<float> m((size_t)C * C);
+  CK(cudaMemcpy(m.data(), d_m, m.size() * 4, cudaMemcpyDeviceToHost));
+  auto kept = [&](const std::vector<double>& e, int keep, int i) {
+    double mx = 0;
+    for (double v : e) mx = v > mx ? v : mx;
+    if (!(e[i] > tau * mx)) return false;
+    if (keep <= 0 || keep >= C) return true;
+    int rank = 0;
+    for (int j = 0; j < C; ++j) rank += e[j] > e[i];
+    return rank < keep;
+  };
+  double worst = 0;
+  int nk = 0;
+  for (int i = 0; i < C; ++i)
+    for (int j = 0; j < C; ++j) {
+      double want = 0;
+      if (i == j) {
+        bool k = kept(ec, keep_c, i) && kept(es, keep_s, i);
+        nk += k;
+        want = (k ? alpha * sqrt(es[i]) / sqrt(ec[i]) : 0.0) + (1.0 - alpha);
+      }
+      double d = fabs((double)m[(size_t)i * C + j] - want) / (1.0 + fabs(want));
+      worst = d > worst ? d : worst;
+    }
+  bool ok = worst < 1e-6;
+  LOG("wct_matrix_topk C=%d keep=(%d,%d): %d directions kept on both sides, worst rel err %.2e  %s\n", C, keep_c, keep_s, nk, worst, ok ? "ok" : "FAIL");
+  CK(cudaFree(d_ec)); CK(cudaFree(d_es)); CK(cudaFree(d_V)); CK(cudaFree(d_mean)); CK(cudaFree(d_work)); CK(cudaFree(d_m)); CK(cudaFree(d_b)); CK(cudaFree(d_mc));
+  return !ok;
+}
+
 int main(int argc, char** argv) {
   if (argc > 1) g_out = fopen(argv[1], "w");
   cudaDeviceProp prop;
@@ -212,6 +260,10 @@ int main(int argc, char** argv) {
   g_fail |= check_resize(101, 67, 49, 67);
   g_fail |= check_resize(720, 1280, 288, 512);
   g_fail |= check_resize(2160, 3840, 1080, 1920);
+  g_fail |= check_topk(24, 10, 10);
+  g_fail |= check_topk(64, 30, 0);
+  g_fail |= check_topk(128, 0, 0);
+  g_fail |= check_topk(512, 128, 100);
   g_fail |= check_jpeg(360, 500);
   g_fail |= check_jpeg(1080, 1920);
   LOG("RESULT: %s\n", g_fail ? "FAIL" : "ALL OK");

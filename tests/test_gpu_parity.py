@@ -166,6 +166,25 @@ def test_whiten_and_color_vs_reference_golden(golden_dir, case):
         assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
 
 
+@pytest.mark.pending_hw
+@pytest.mark.parametrize("case,tag,num,rat", [("full_rank", "num10", 10, None), ("wide", "num30", 30, None),
+                                              ("dead_channels", "num12", 12, None), ("wide", "rat025", None, 0.25),
+                                              ("dead_channels", "rat025", None, 0.25)])
+def test_eigenvalue_truncation_vs_reference_golden(golden_dir, case, tag, num, rat):
+    """NumEigenValue / RatEigenValue knobs (util_wct.py:26-27,87-88,113-114) through wctb_wct_matrix_topk."""
+    g = np.load(os.path.join(golden_dir, "golden_wct.npz"))
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, "golden_wct_topk.npz"))["%s.%s" % (case, tag)])
+    cF, sF = torch.from_numpy(g[case + ".cF"]), torch.from_numpy(g[case + ".sF"])
+    w = _wct16()
+    w.num_eig, w.rat_eig = num, rat
+    got = w.whiten_and_color(cF, sF).cpu()
+    assert relerr(got, ref) <= 2e-6
+    assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    w.num_eig, w.rat_eig = 10 ** 6, None              # keep >= C is the untruncated transform
+    full = torch.from_numpy(g[case + ".out_torch"])
+    assert relerr(w.whiten_and_color(cF, sF).cpu(), full) <= 2e-6
+
+
 def test_transform_api_fills_callers_buffer(golden_dir):
     g = np.load(os.path.join(golden_dir, "golden_16x.npz"))
     w = _wct16()

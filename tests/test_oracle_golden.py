@@ -100,3 +100,22 @@ def test_original_mode_matches_reference(golden_dir):
     img = O.stylize(w, "original", c256, s256, stages=(1,), taps=taps)
     np.testing.assert_allclose(img[:, :, 100:132, 60:92].numpy(), g["cfg1.img1.crop"], rtol=0, atol=2e-5)
     assert abs(img.double().abs().sum().item() - g["cfg1.img1.sum"][1]) <= 1e-6 * g["cfg1.img1.sum"][1]
+
+
+TOPK_CASES = [("full_rank", "num10", 10), ("wide", "num30", 30), ("dead_channels", "num12", 12),
+              ("full_rank", "rat025", int(24 * 0.25)), ("wide", "rat025", int(64 * 0.25)), ("dead_channels", "rat025", int(32 * 0.25))]
+
+
+@pytest.mark.parametrize("case,tag,keep", TOPK_CASES)
+def test_eigenvalue_truncation_matches_reference(golden_dir, case, tag, keep):
+    """util_wct.py:26-27,87-88,113-114 (NumEigenValue / RatEigenValue): fixtures from the reference with its own
+    commented-out lines enabled in memory (tests/golden/make_golden_topk.py)."""
+    g = np.load(os.path.join(golden_dir, "golden_wct.npz"))
+    ref = np.load(os.path.join(golden_dir, "golden_wct_topk.npz"))["%s.%s" % (case, tag)]
+    cF, sF = torch.from_numpy(g[case + ".cF"]), torch.from_numpy(g[case + ".sF"])
+    got = O.whiten_and_color(cF, sF, keep=keep).numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-7 * np.abs(ref).max())
+    # and the knob really truncates: the coloured, centred output has rank <= keep
+    centred = got - got.mean(1, keepdims=True)
+    sv = np.linalg.svd(centred, compute_uv=False)
+    assert (sv > 1e-8 * sv[0]).sum() <= keep
