@@ -48,6 +48,7 @@ SIGNATURES = {
     "wctb_resize_coeffs_host": [_i, _i, _p, _p],
     "wctb_resize_u8_pass": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p],
     "wctb_debug_set_eigh_variant": [_i],
+    "wctb_debug_set_gram_variant": [_i],
     "wctb_debug_eigh_profile": [_p],
     "wctb_debug_dp_rate": [_p, _p],
     "wctb_debug_set_trace": [_p],
@@ -87,6 +88,8 @@ def load():
     lib.wctb_error_string.restype = ctypes.c_char_p
     if lib.wctb_abi_version() != 1:
         raise WctbError("libwctb ABI version mismatch")
+    if os.environ.get("WCTB_GRAM_VARIANT"):          # A/B switch for tools / bench runs (see wctb.h, debug section)
+        lib.wctb_debug_set_gram_variant(int(os.environ["WCTB_GRAM_VARIANT"]))
     _lib = lib
     return lib
 

@@ -202,6 +202,202 @@ extern "C" int wctb_centered_gram(const float* x, int C, int H, int W, int y0, i
   return launch_gram<4, 16, double>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-resident fp32 Gram for the small-channel, many-pixel stages (C = 24: stage 1, C = 32: stage 2).
+// The staged kernel above is shared-memory bound there (6 LDS.32 per 9 FFMA: CUDA events put it at ~5x its FFMA and
+// HBM floors).  Here a thread owns whole PIXELS: it loads the chunks (float4 = 4 channels) of its pixel straight from
+// global memory (a warp reads 512 contiguous bytes per chunk plane), centres them with a split (hi, lo) fp32 mean and
+// accumulates 4x4 outer-product blocks of the upper block triangle in registers.  The NCH(NCH+1)/2 blocks are dealt in
+// contiguous runs to SPLIT warp groups ("parts") of the CTA; a part only loads the chunks its blocks touch, all parts
+// walk the same pixels (re-reads hit L1; a barrier every 4th iteration keeps the parts inside the L1 window), and each
+// part prefetches its lines two iterations ahead.  No shared-memory traffic in the loop.  Register budget: 12 warps/SM
+// (3 per scheduler) -> <= 168 registers: <= 96 accumulators + <= 32 operands.
+// Flush: warp-shuffle reduction in fp64, then fp64 atomics (same accumulate-into-G contract as the staged kernel).
+// Accuracy: per-thread fp32 sums over npix/(gridDim*PIX) pixels (hundreds..2e3) -> ~1e-6 each, averaging over the
+// >= 1e4 threads to ~1e-8 relative in G; the contract of the fast variant is 1e-6 (tests/test_gpu_parity.py).
+// ------------------------------------------------------------------------------------------
+template <int NCH, int SPLIT>
+struct GramDeal {
+  static constexpr int NPAIR = NCH * (NCH + 1) / 2;
+  static constexpr int BASE = NPAIR / SPLIT, REM = NPAIR % SPLIT;
+  __host__ __device__ static constexpr int begin(int part) { return part * BASE + (part < REM ? part : REM); }
+  __host__ __device__ static constexpr int count(int part) { return BASE + (part < REM ? 1 : 0); }
+  static constexpr int MAXCOUNT = BASE + (REM ? 1 : 0);
+  __host__ __device__ static constexpr bool owns(int part, int q) { return q >= begin(part) && q < begin(part) + count(part); }
+  __host__ __device__ static constexpr bool uses_chunk(int part, int c) {
+    int q = 0;
+    for (int i = 0; i < NCH; ++i)
+      for (int j = i; j < NCH; ++j, ++q)
+        if (owns(part, q) && (i == c || j == c)) return true;
+    return false;
+  }
+};
+
+// one pixel per thread: load the chunks this part touches, centre, accumulate its blocks.  CHECK = last iteration (slots
+// beyond npix contribute zero); FULLROW = the region spans whole rows, so pixel p of the region is pixel y0*W + p of the plane.
+template <int NCH, int SPLIT, int PART, bool FULLROW, bool CHECK>
+__device__ __forceinline__ void gram_regs_step(float (&acc)[GramDeal<NCH, SPLIT>::MAXCOUNT][16], const float4* __restrict__ x,
+                                               long long HW, int W, int y0, int x0, unsigned wreg, unsigned npix, unsigned p,
+                                               const float4* __restrict__ s_mh) {
+  using D = GramDeal<NCH, SPLIT>;
+  float4 cur[NCH];
+  const bool have = !CHECK || p < npix;
+  long long off;
+  if (FULLROW) {
+    off = (long long)y0 * W + p;
+  } else {
+    const unsigned pp = have ? p : 0u;
+    const unsigned r = pp / wreg, cc = pp - r * wreg;
+    off = (long long)(y0 + r) * W + (x0 + cc);
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    cur[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (D::uses_chunk(PART, c) && have) {
+      const float4 v = __ldg(x + (long long)c * HW + off);
+      const float4 mh = s_mh[c];
+      // fp32 mean: its rounding error d (<= 2^-24 |mean|) only adds N d_i d_j to G, ~1e-14 relative
+      cur[c] = make_float4(v.x - mh.x, v.y - mh.y, v.z - mh.z, v.w - mh.w);
+    }
+  }
+  int q = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+#pragma unroll
+    for (int j = i; j < NCH; ++j) {
+      if (D::owns(PART, q)) {
+        const int slot = q - D::begin(PART);
+        const float a[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+        const float b[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[slot][u * 4 + v] = fmaf(a[u], b[v], acc[slot][u * 4 + v]);
+      }
+      ++q;
+    }
+  }
+}
+
+template <int NCH, int SPLIT, int PART, int PIX, bool FULLROW>
+__device__ __forceinline__ void gram_regs_body(const float4* __restrict__ x, long long HW, int W, int y0, int x0, unsigned wreg,
+                                               unsigned npix, unsigned iters, const float4* __restrict__ s_mh,
+                                               double* __restrict__ G) {
+  using D = GramDeal<NCH, SPLIT>;
+  constexpr int C = NCH * 4;
+  constexpr int NP = D::MAXCOUNT;
+  float acc[NP][16];
+#pragma unroll
+  for (int s = 0; s < NP; ++s)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[s][e] = 0.f;
+  const unsigned stride = gridDim.x * PIX;
+  const unsigned pbase = blockIdx.x * PIX + (threadIdx.x % PIX);
+  // iterations 0 .. iters-2 are in range for every thread (see launch_gram_regs); only the last one needs the range check.
+  // Uniform trip count: the barrier is reached by every thread of the CTA.
+  for (unsigned it = 0; it + 1 < iters; ++it) {
+    const unsigned p = pbase + it * stride;          // no 32-bit overflow: the host checks npix < 2^31 - 2^24
+    {   // prefetch two iterations ahead
+      const unsigned pf = p + 2 * stride;
+      if (pf < npix) {
+        long long off;
+        if (FULLROW) {
+          off = (long long)y0 * W + pf;
+        } else {
+          const unsigned r = pf / wreg, cc = pf - r * wreg;
+          off = (long long)(y0 + r) * W + (x0 + cc);
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          if (D::uses_chunk(PART, c)) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + (long long)c * HW + off));
+      }
+    }
+    gram_regs_step<NCH, SPLIT, PART, FULLROW, false>(acc, x, HW, W, y0, x0, wreg, npix, p, s_mh);
+    // named barrier over the whole CTA: the parts sit in different branches of the dispatch (warp-uniform), so this is
+    // written as bar.sync <id>, <count> rather than __syncthreads()
+    if ((it & 3) == 3) asm volatile("bar.sync 1, %0;" ::"r"(PIX * SPLIT) : "memory");
+  }
+  gram_regs_step<NCH, SPLIT, PART, FULLROW, true>(acc, x, HW, W, y0, x0, wreg, npix, pbase + (iters - 1) * stride, s_mh);
+  // flush
+  const int lane = threadIdx.x & 31;
+  {
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+#pragma unroll
+      for (int j = i; j < NCH; ++j) {
+        if (D::owns(PART, q)) {
+          const int slot = q - D::begin(PART);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              double sum = (double)acc[slot][u * 4 + v];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+              if (lane == 0) {
+                atomicAdd(G + (long long)(i * 4 + u) * C + (j * 4 + v), sum);
+                if (i != j) atomicAdd(G + (long long)(j * 4 + v) * C + (i * 4 + u), sum);
+              }
+            }
+        }
+        ++q;
+      }
+    }
+  }
+}
+
+template <int NCH, int SPLIT, int PART, int PIX, bool FULLROW>
+__device__ __forceinline__ void gram_regs_dispatch(int part, const float4* __restrict__ x, long long HW, int W, int y0, int x0,
+                                                   unsigned wreg, unsigned npix, unsigned iters, const float4* s_mh,
+                                                   double* __restrict__ G) {
+  if (part == PART) {
+    gram_regs_body<NCH, SPLIT, PART, PIX, FULLROW>(x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
+  } else if constexpr (PART + 1 < SPLIT) {
+    gram_regs_dispatch<NCH, SPLIT, PART + 1, PIX, FULLROW>(part, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
+  }
+}
+
+template <int NCH, int SPLIT, int PIX, bool FULLROW>
+__global__ void __launch_bounds__(PIX* SPLIT, 1) gram_regs_kernel(const float4* __restrict__ x, int H, int W, int y0, int x0,
+                                                                   unsigned wreg, unsigned npix, unsigned iters,
+                                                                   const double* __restrict__ mean, double* __restrict__ G) {
+  static_assert(PIX % 32 == 0, "a warp must not straddle two parts");
+  __shared__ float4 s_mh[NCH];
+  if (threadIdx.x < NCH * 4) reinterpret_cast<float*>(s_mh)[threadIdx.x] = (float)mean[threadIdx.x];
+  __syncthreads();
+  // every part runs the same number of barriers (iters is uniform), so the divergent dispatch is barrier-safe
+  gram_regs_dispatch<NCH, SPLIT, 0, PIX, FULLROW>(threadIdx.x / PIX, x, (long long)H * W, W, y0, x0, wreg, npix, iters, s_mh, G);
+}
+
+template <int NCH, int SPLIT, int PIX>
+static int launch_gram_regs(const float* x, int H, int W, int y0, int y1, int x0, int x1, const double* mean, double* gram_out,
+                            cudaStream_t st) {
+  const long long npix = (long long)(y1 - y0) * (x1 - x0);
+  long long ctas = (npix + PIX - 1) / PIX;
+  const long long cap = wctb_num_sms();          // one CTA per SM (register-limited), persistent over its pixels
+  if (ctas > cap) ctas = cap;
+  // iters = ceil(npix / stride), stride = ctas*PIX  =>  (iters-1)*stride < npix, so slot pbase + it*stride (pbase < stride)
+  // is in range for every thread while it <= iters-2; only the last iteration is range-checked in the kernel.
+  const long long stride = ctas * PIX;
+  const unsigned iters = (unsigned)((npix + stride - 1) / stride);
+  const unsigned wreg = (unsigned)(x1 - x0);
+  if (x0 == 0 && x1 == W)
+    gram_regs_kernel<NCH, SPLIT, PIX, true><<<(unsigned)ctas, PIX * SPLIT, 0, st>>>((const float4*)x, H, W, y0, x0, wreg,
+                                                                                    (unsigned)npix, iters, mean, gram_out);
+  else
+    gram_regs_kernel<NCH, SPLIT, PIX, false><<<(unsigned)ctas, PIX * SPLIT, 0, st>>>((const float4*)x, H, W, y0, x0, wreg,
+                                                                                     (unsigned)npix, iters, mean, gram_out);
+  WCTB_RETURN_LAUNCH();
+}
+
+static int g_gram_variant = 0;   // 0: register-resident kernel for C = 24 / 32 (default), 1: staged kernel everywhere (A/B)
+extern "C" int wctb_debug_set_gram_variant(int v) {
+  if (v < 0 || v > 1) return WCTB_E_BADARG;
+  g_gram_variant = v;
+  return WCTB_OK;
+}
+
 // fp32-product variant for the TF32 conv mode (see the kernel comment); same contract as wctb_centered_gram
 extern "C" int wctb_centered_gram_fast(const float* x, int C, int H, int W, int y0, int y1, int x0, int x1,
                                        const double* mean, double* gram_out, void* stream) {
@@ -209,6 +405,10 @@ extern "C" int wctb_centered_gram_fast(const float* x, int C, int H, int W, int 
       y0 >= y1 || x0 >= x1)
     return WCTB_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_gram_variant == 0 && (long long)(y1 - y0) * (x1 - x0) < (1LL << 31) - (1LL << 24)) {
+    if (C == 24) return launch_gram_regs<6, 4, 96>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+    if (C == 32) return launch_gram_regs<8, 6, 64>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+  }
   if (C <= 16) return launch_gram<2, 8, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
   if (C <= 24) return launch_gram<3, 8, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
   if (C <= 32) return launch_gram<4, 8, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);

@@ -230,6 +230,11 @@ def set_eigh_variant(v: int):
     check(_lib.load().wctb_debug_set_eigh_variant(int(v)), "debug_set_eigh_variant")
 
 
+def set_gram_variant(v: int):
+    """debug: 0 = register-resident fast Gram for C = 24 / 32 (default), 1 = staged shared-memory kernel everywhere"""
+    check(_lib.load().wctb_debug_set_gram_variant(int(v)), "debug_set_gram_variant")
+
+
 def eigh_profile(a: torch.Tensor, scale):
     """debug: phase profile (clock64 sums of thread 0) of one C in (64,128] solve -> dict"""
     buf = torch.zeros(16, device=a.device, dtype=torch.int64)

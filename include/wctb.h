@@ -208,6 +208,10 @@ int wctb_resize_u8_pass(const uint8_t* src_hwc, uint8_t* dst_hwc, int H, int W, 
  * tools/eig_diag.py).  Process-wide; not meant to be toggled while work is in flight.                                */
 int wctb_debug_set_eigh_variant(int variant);
 
+/* debug: 0 (default) = wctb_centered_gram_fast uses the register-resident kernel for C = 24 / 32 (a thread owns whole
+ * pixels; no shared-memory traffic in the loop); 1 = the staged shared-memory kernel everywhere (A/B timing).          */
+int wctb_debug_set_gram_variant(int variant);
+
 /* debug: when buf16 != NULL the C in (64,128] solve records clock64() phase times of thread 0 into buf16:
  * [0] load + compaction, [1] Cholesky, [2] Jacobi sweeps, [8] sweep count, [9] live size k.                          */
 int wctb_debug_eigh_profile(long long* buf16);

@@ -84,7 +84,9 @@ def test_conv_last_fp32(H, W, cin):
 # ------------------------------------------------------------------ statistics
 @pytest.mark.parametrize("C,H,W,region", [(24, 31, 47, None), (128, 9, 11, None), (64, 40, 50, (3, 37, 8, 50)),
                                           (256, 6, 7, None), (16, 5, 300, (0, 5, 16, 272)),
-                                          (24, 300, 310, None), (128, 260, 270, (4, 260, 0, 264)), (32, 257, 300, None)])
+                                          (24, 300, 310, None), (128, 260, 270, (4, 260, 0, 264)), (32, 257, 300, None),
+                                          (24, 40, 50, (3, 37, 8, 50)), (32, 33, 70, (0, 33, 5, 64)), (24, 3, 5, None),
+                                          (32, 700, 900, (10, 690, 0, 900))])
 def test_moments_match_fp64(C, H, W, region):
     x = (torch.randn(C, H, W, generator=torch.Generator().manual_seed(4)) * 3 + 1.5).relu()
     p4 = ops.nchw_to_p4(x.to(DEV))
@@ -101,6 +103,14 @@ def test_moments_match_fp64(C, H, W, region):
     gf = ops.centered_gram(p4, mean.to(DEV), region, fast=True).cpu()
     assert (gf - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()      # fp32 products / 128-px fp32 partial sums
     assert (g - g.t()).abs().max().item() <= 1e-13 * ref.abs().max().item()   # fp64 atomics: order-dependent last bits
+    # the two fast kernels (register-resident for C = 24 / 32, staged shared-memory) meet the same contract
+    ops.set_gram_variant(1)
+    try:
+        gl = ops.centered_gram(p4, mean.to(DEV), region, fast=True).cpu()
+    finally:
+        ops.set_gram_variant(0)
+    assert (gl - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    assert (gf - gf.t()).abs().max().item() <= 1e-13 * ref.abs().max().item()
 
 
 # ------------------------------------------------------------------ eigensolver
