@@ -38,6 +38,7 @@ SIGNATURES = {
     "wctb_centered_gram": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "wctb_centered_gram_fast": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "wctb_eigh_jacobi": [_p, _i, _i, ctypes.POINTER(ctypes.c_double), _i, _p, _p, _p, _p, _p],
+    "wctb_eigh_jacobi_tol": [_p, _i, _i, ctypes.POINTER(ctypes.c_double), _i, _d, _p, _p, _p, _p, _p],
     "wctb_wct_matrix": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p],
     "wctb_wct_matrix_topk": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _i, _i, _p, _p, _p, _p, _p],
     "wctb_wct_apply": [_p, _p, _p, _p, _p, _i, _ll, _i, _p],
@@ -49,6 +50,7 @@ SIGNATURES = {
     "wctb_resize_u8_pass": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p],
     "wctb_debug_set_eigh_variant": [_i],
     "wctb_debug_set_gram_variant": [_i],
+    "wctb_debug_set_first_variant": [_i],
     "wctb_debug_eigh_profile": [_p],
     "wctb_debug_dp_rate": [_p, _p],
     "wctb_debug_set_trace": [_p],
@@ -90,6 +92,8 @@ def load():
         raise WctbError("libwctb ABI version mismatch")
     if os.environ.get("WCTB_GRAM_VARIANT"):          # A/B switch for tools / bench runs (see wctb.h, debug section)
         lib.wctb_debug_set_gram_variant(int(os.environ["WCTB_GRAM_VARIANT"]))
+    if os.environ.get("WCTB_FIRST_VARIANT"):
+        lib.wctb_debug_set_first_variant(int(os.environ["WCTB_FIRST_VARIANT"]))
     _lib = lib
     return lib
 

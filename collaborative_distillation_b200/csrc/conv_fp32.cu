@@ -121,15 +121,87 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
     y[(long long)c4 * HW + (long long)yy * W + xx] = acc;
   }
 }
+// Two pixels per thread (columns xx and xx + 32 of a 64 x 8 tile): every broadcast LDS.128 of a weight quad feeds 8 FFMA
+// instead of 4, which is what bounded the one-pixel kernel (27 LDS.128 per 108 FFMA); both stores stay 512-byte coalesced.
+// Same arithmetic order per output as conv_first_kernel (bias, then taps 0..26), so results are bit-identical.
+__global__ void __launch_bounds__(256) conv_first2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float4* __restrict__ y,
+                                                          int H, int W, int Cout, int round_tf32) {
+  extern __shared__ float4 smem4[];
+  float* ws = reinterpret_cast<float*>(smem4);  // [27][Cout]
+  float* bs = ws + 27 * Cout;
+  for (int i = threadIdx.x + threadIdx.y * 32; i < 27 * Cout; i += 256) ws[i] = w[i];
+  for (int i = threadIdx.x + threadIdx.y * 32; i < Cout; i += 256) bs[i] = bias[i];
+  __syncthreads();
+  const int xa = blockIdx.x * 64 + threadIdx.x, xb = xa + 32;
+  const int yy = blockIdx.y * 8 + threadIdx.y;
+  if (xa >= W || yy >= H) return;
+  const bool hasb = xb < W;
+  float ina[27], inb[27];
+  const long long HW = (long long)H * W;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int gy = wctb_reflect(yy + dy - 1, H);
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int gxa = wctb_reflect(xa + dx - 1, W);
+      const int gxb = wctb_reflect(xb + dx - 1, W);   // clamped into range when xb >= W (result unused)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ina[(dy * 3 + dx) * 3 + c] = __ldg(x + c * HW + (long long)gy * W + gxa);
+        inb[(dy * 3 + dx) * 3 + c] = __ldg(x + c * HW + (long long)gy * W + gxb);
+      }
+    }
+  }
+  const float4* w4 = reinterpret_cast<const float4*>(ws);
+  const int C4 = Cout >> 2;
+  for (int c4 = 0; c4 < C4; ++c4) {
+    float4 a = reinterpret_cast<const float4*>(bs)[c4];
+    float4 b = a;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4 wv = w4[k * C4 + c4];
+      a.x = fmaf(ina[k], wv.x, a.x); b.x = fmaf(inb[k], wv.x, b.x);
+      a.y = fmaf(ina[k], wv.y, a.y); b.y = fmaf(inb[k], wv.y, b.y);
+      a.z = fmaf(ina[k], wv.z, a.z); b.z = fmaf(inb[k], wv.z, b.z);
+      a.w = fmaf(ina[k], wv.w, a.w); b.w = fmaf(inb[k], wv.w, b.w);
+    }
+    a.x = wctb_relu(a.x); a.y = wctb_relu(a.y); a.z = wctb_relu(a.z); a.w = wctb_relu(a.w);
+    b.x = wctb_relu(b.x); b.y = wctb_relu(b.y); b.z = wctb_relu(b.z); b.w = wctb_relu(b.w);
+    if (round_tf32) {
+      a.x = wctb_tf32(a.x); a.y = wctb_tf32(a.y); a.z = wctb_tf32(a.z); a.w = wctb_tf32(a.w);
+      b.x = wctb_tf32(b.x); b.y = wctb_tf32(b.y); b.z = wctb_tf32(b.z); b.w = wctb_tf32(b.w);
+    }
+    float4* row = y + (long long)c4 * HW + (long long)yy * W;
+    row[xa] = a;
+    if (hasb) row[xb] = b;
+  }
+}
+
+static int g_first_variant = 0;   // 0: two pixels per thread when W >= 64 (default), 1: one pixel per thread (A/B)
+extern "C" int wctb_debug_set_first_variant(int v) {
+  if (v < 0 || v > 1) return WCTB_E_BADARG;
+  g_first_variant = v;
+  return WCTB_OK;
+}
+
 extern "C" int wctb_conv3x3_first(const float* x, const float* w, const float* bias, float* y, int H, int W,
                                   int Cout, int round_tf32, void* stream) {
   if (!x || !w || !bias || !y || H < 2 || W < 2 || Cout <= 0 || (Cout & 3) || Cout > 512) return WCTB_E_BADARG;
-  dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
   size_t smem = (size_t)(27 * Cout + Cout) * sizeof(float);
+  const bool two = g_first_variant == 0 && W >= 64;
   if (smem > 48 * 1024) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (two) WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_first2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  conv_first_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(x, w, bias, (float4*)y, H, W, Cout, round_tf32);
+  dim3 block(32, 8);
+  if (two) {
+    dim3 grid((W + 63) / 64, (H + 7) / 8);
+    conv_first2_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(x, w, bias, (float4*)y, H, W, Cout, round_tf32);
+  } else {
+    dim3 grid((W + 31) / 32, (H + 7) / 8);
+    conv_first_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(x, w, bias, (float4*)y, H, W, Cout, round_tf32);
+  }
   WCTB_RETURN_LAUNCH();
 }
 

@@ -430,7 +430,7 @@ __device__ __forceinline__ void rr_pair(int round, int k, int n, int& p, int& q)
   if (p > q) { int t = p; p = q; q = t; }
 }
 
-struct JacobiScales { double v[8]; };
+struct JacobiScales { double v[8]; double early2; };   // per-problem scale; (early-stop |cos| threshold)^2 of the Cholesky-Jacobi sweeps
 constexpr double JACOBI_TOL = 1e-10;   // pair converged when |g_p.g_q| <= tol |g_p||g_q|; error in eigenvalues is 2nd order
 constexpr int JACOBI_MAX_SWEEPS = 40;
 
@@ -616,7 +616,7 @@ __host__ __device__ inline int jacobi_pitch(int k, int lanes) {
 // visitor next round) and picks up the column entering position h, which its previous partner group has just stored.
 template <int LANES, int EPL>
 __device__ __forceinline__ int jacobi_chol_sweeps(double* __restrict__ G, const int k, const int pitch, const double floor2,
-                                                  double* __restrict__ s_d, double* __restrict__ s_l,
+                                                  const double early2, double* __restrict__ s_d, double* __restrict__ s_l,
                                                   double* __restrict__ s_si) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int group = tid / LANES, sub = tid % LANES;
@@ -675,7 +675,7 @@ __device__ __forceinline__ int jacobi_chol_sweeps(double* __restrict__ G, const 
         c *= sp * sq;
         const double cc = c * c, ab = a * b;
         const bool null = a <= floor2 || b <= floor2;
-        if (!null && cc > JACOBI_EARLY * JACOBI_EARLY * ab) big = 1;
+        if (!null && cc > early2 * ab) big = 1;
         if (!(null || cc <= JACOBI_TOL * JACOBI_TOL * ab)) {
           // half-angle form of the inner rotation: cos 2th = |d|/sqrt(hh), sin 2th = |2c|/sqrt(hh)
           const double d = b - a, c2 = c + c;
@@ -857,9 +857,9 @@ __global__ void __launch_bounds__(64 * LANES) jacobi_chol_kernel(const double* _
     __syncthreads();
     JPROF(1);   // Cholesky
     // ---- Hestenes sweeps on the columns of L (instantiated for the live size: rows beyond LANES*EPL are never touched)
-    if (EPL >= 16 && k <= LANES * (EPL / 4)) sweep = jacobi_chol_sweeps<LANES, (EPL >= 16 ? EPL / 4 : EPL)>(G, k, pitch, floor2, s_d, s_l, s_si);
-    else if (k <= LANES * (EPL / 2)) sweep = jacobi_chol_sweeps<LANES, EPL / 2>(G, k, pitch, floor2, s_d, s_l, s_si);
-    else sweep = jacobi_chol_sweeps<LANES, EPL>(G, k, pitch, floor2, s_d, s_l, s_si);
+    if (EPL >= 16 && k <= LANES * (EPL / 4)) sweep = jacobi_chol_sweeps<LANES, (EPL >= 16 ? EPL / 4 : EPL)>(G, k, pitch, floor2, scale.early2, s_d, s_l, s_si);
+    else if (k <= LANES * (EPL / 2)) sweep = jacobi_chol_sweeps<LANES, EPL / 2>(G, k, pitch, floor2, scale.early2, s_d, s_l, s_si);
+    else sweep = jacobi_chol_sweeps<LANES, EPL>(G, k, pitch, floor2, scale.early2, s_d, s_l, s_si);
     const int group = tid / LANES, sub = tid % LANES;
     const int ngroups = blockDim.x / LANES;
     const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane & ~(LANES - 1)));
@@ -1004,10 +1004,18 @@ extern "C" int wctb_debug_dp_rate(long long* out3, void* stream) {
 
 extern "C" int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale_host, int add_identity, double* evals,
                                 double* evecs, double* work, int* sweeps_out, void* stream) {
+  return wctb_eigh_jacobi_tol(a, nprob, C, scale_host, add_identity, JACOBI_EARLY, evals, evecs, work, sweeps_out, stream);
+}
+
+extern "C" int wctb_eigh_jacobi_tol(const double* a, int nprob, int C, const double* scale_host, int add_identity,
+                                    double early_stop_cos, double* evals, double* evecs, double* work, int* sweeps_out,
+                                    void* stream) {
   if (!a || !scale_host || !evals || !evecs || !work || nprob <= 0 || nprob > 8 || C < 2 || (C & 1)) return WCTB_E_BADARG;
+  if (!(early_stop_cos >= 0.0 && early_stop_cos <= 0.1)) return WCTB_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   JacobiScales scale;
   for (int i = 0; i < 8; ++i) scale.v[i] = i < nprob ? scale_host[i] : 1.0;
+  scale.early2 = early_stop_cos * early_stop_cos;
   if (C <= 128 && g_eigh_variant == 0) {
     // lanes per column pair x elements per lane (LANES*EPL >= C); ~512 threads measured best on B200 (tools/eig_diag.py)
     if (C > 64) {

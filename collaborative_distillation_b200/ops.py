@@ -207,8 +207,9 @@ def centered_gram(x: torch.Tensor, mean: torch.Tensor, region=None, out: torch.T
     return out
 
 
-def eigh_jacobi(a: torch.Tensor, scale, add_identity: bool = False, return_sweeps: bool = False):
-    """a: fp64 [nprob,C,C] symmetric PSD; scale: nprob host floats.  -> evals [nprob,C], evecs [nprob,C(k),C(i)]"""
+def eigh_jacobi(a: torch.Tensor, scale, add_identity: bool = False, return_sweeps: bool = False, early_stop: float = None):
+    """a: fp64 [nprob,C,C] symmetric PSD; scale: nprob host floats.  -> evals [nprob,C], evecs [nprob,C(k),C(i)].
+    early_stop: |cos| threshold that ends the C <= 128 iteration (None = the library default 3e-6, see wctb.h)."""
     import ctypes
     nprob, C, _ = a.shape
     scale = [float(v) for v in (scale.tolist() if torch.is_tensor(scale) else scale)]
@@ -218,9 +219,14 @@ def eigh_jacobi(a: torch.Tensor, scale, add_identity: bool = False, return_sweep
     evecs = torch.empty(nprob, C, C, device=a.device, dtype=torch.float64)
     work = torch.empty(nprob * C * C + 16, device=a.device, dtype=torch.float64)
     sweeps = torch.zeros(nprob, device=a.device, dtype=torch.int32)
-    check(_lib.load().wctb_eigh_jacobi(_need(a, torch.float64), nprob, C, scale_host, int(add_identity),
-                                       _need(evals, torch.float64), _need(evecs, torch.float64),
-                                       _need(work, torch.float64), _need(sweeps, torch.int32), _stream()), "eigh_jacobi")
+    if early_stop is None:
+        check(_lib.load().wctb_eigh_jacobi(_need(a, torch.float64), nprob, C, scale_host, int(add_identity),
+                                           _need(evals, torch.float64), _need(evecs, torch.float64),
+                                           _need(work, torch.float64), _need(sweeps, torch.int32), _stream()), "eigh_jacobi")
+    else:
+        check(_lib.load().wctb_eigh_jacobi_tol(_need(a, torch.float64), nprob, C, scale_host, int(add_identity), float(early_stop),
+                                               _need(evals, torch.float64), _need(evecs, torch.float64),
+                                               _need(work, torch.float64), _need(sweeps, torch.int32), _stream()), "eigh_jacobi_tol")
     _count("eigh")
     return (evals, evecs, sweeps) if return_sweeps else (evals, evecs)
 
@@ -228,6 +234,11 @@ def eigh_jacobi(a: torch.Tensor, scale, add_identity: bool = False, return_sweep
 def set_eigh_variant(v: int):
     """debug: 0 = Cholesky-preconditioned Jacobi (default), 1 = legacy Jacobi on the matrix itself (C <= 128 only)"""
     check(_lib.load().wctb_debug_set_eigh_variant(int(v)), "debug_set_eigh_variant")
+
+
+def set_first_variant(v: int):
+    """debug: 0 = conv3x3_first computes two pixels per thread (default), 1 = one pixel per thread (bit-identical)"""
+    check(_lib.load().wctb_debug_set_first_variant(int(v)), "debug_set_first_variant")
 
 
 def set_gram_variant(v: int):

@@ -14,6 +14,7 @@ Differences from the reference, all stated in DESIGN.md:
 from __future__ import annotations
 
 import collections
+import os
 
 import torch
 import torch.nn as nn
@@ -40,6 +41,10 @@ class WCT(nn.Module):
             setattr(self, "e%d" % k, nets.ENCODERS[mode][k - 1](getattr(args, "e%d" % k, None)))
             setattr(self, "d%d" % k, nets.DECODERS[mode][k - 1](getattr(args, "d%d" % k, None)))
         self.tau = TAU
+        # early-stop |cos| of the eigensolver sweeps (wctb_eigh_jacobi_tol).  None = by conv precision: 1e-4 with the fp32
+        # engine (residual <= ~1e-8, whitening error ~1e-9), 1e-2 with the TF32 engine (whitening error ~2e-6 against
+        # 1e-3 of TF32 feature noise; two sweeps fewer on the critical path).  WCTB_EIG_EARLY overrides (A/B runs).
+        self.eig_early = float(os.environ["WCTB_EIG_EARLY"]) if os.environ.get("WCTB_EIG_EARLY") else None
         self.num_eig = NumEigenValue   # per-instance knobs; None = keep all directions (the reference's active behaviour)
         self.rat_eig = RatEigenValue
         self.dist = None          # set by parallel.StripGroup for multi-GPU runs
@@ -51,6 +56,11 @@ class WCT(nn.Module):
         self.use_graph = True      # single-GPU stylize(): capture the two-stream schedule in a CUDA graph per input shape
         self.max_graphs = 4        # captured graphs kept (LRU): each one pins the activations of its input shape in HBM
         self._graphs = collections.OrderedDict()
+
+    def _early(self):
+        if self.eig_early is not None:
+            return float(self.eig_early)
+        return 1e-2 if nets.get_precision() == "tf32" else 1e-4
 
     def _keep(self, C):
         """number of eigen-directions kept for content and style (0 = all): k = NumEigenValue, or int(C * RatEigenValue)"""
@@ -88,11 +98,11 @@ class WCT(nn.Module):
             self.dist.allreduce_(grams)
         scale = [1.0 / (nc - 1.0), 1.0 / (ns - 1.0)]                                   # util_wct.py:70,96
         if getattr(self.args, "numpy", False):                                          # +I on the content covariance only (util_wct.py:143)
-            ce, cv = ops.eigh_jacobi(grams[0:1], scale[0:1], add_identity=True)
-            se, sv = ops.eigh_jacobi(grams[1:2], scale[1:2], add_identity=False)
+            ce, cv = ops.eigh_jacobi(grams[0:1], scale[0:1], add_identity=True, early_stop=self._early())
+            se, sv = ops.eigh_jacobi(grams[1:2], scale[1:2], add_identity=False, early_stop=self._early())
             evals, evecs = torch.cat([ce, se]), torch.cat([cv, sv])
         else:
-            evals, evecs = ops.eigh_jacobi(grams, scale)
+            evals, evecs = ops.eigh_jacobi(grams, scale, early_stop=self._early())
         k = self._keep(C)
         return ops.wct_matrix(evals[0], evecs[0], c_mean, evals[1], evecs[1], s_mean, self.tau, alpha, k, k)
 
@@ -150,7 +160,7 @@ class WCT(nn.Module):
         n = float(x_p4.shape[1] * x_p4.shape[2])
         gram = torch.zeros(1, C, C, device=x_p4.device, dtype=torch.float64)
         mean = self._moments(x_p4, (0, x_p4.shape[1], 0, x_p4.shape[2]), n, gram[0])
-        evals, evecs = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=add_identity)
+        evals, evecs = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=add_identity, early_stop=self._early())
         return mean, evals[0], evecs[0]
 
     @torch.no_grad()
@@ -226,7 +236,8 @@ class WCT(nn.Module):
                     gram = torch.zeros(1, C, C, device=c4.device, dtype=torch.float64)
                     c_mean = self._moments(c4, (0, c4.shape[1], 0, c4.shape[2]), n, gram[0])
                     mark(s, "stats")
-                    c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant)   # util_wct.py:143: +I on content only
+                    c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant,   # util_wct.py:143: +I on content only
+                                               early_stop=self._early())
                     c_e, c_v = c_e[0], c_v[0]
                     mark(s, "eig")
                     (s_mean, s_e, s_v), ev = style_res[s]
@@ -259,7 +270,7 @@ class WCT(nn.Module):
             style = content[..., :1, :1]       # unused placeholder with a stable shape
         host = (not content.is_cuda) and (not style.is_cuda) and content.is_pinned() and style.is_pinned()
         key = (tuple(content.shape), tuple(style.shape), float(alpha), int(num_run), tuple(stages), nets.get_precision(),
-               bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)), self.num_eig, self.rat_eig, float(self.tau),
+               bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)), self.num_eig, self.rat_eig, float(self.tau), self._early(),
                (content.data_ptr(), style.data_ptr()) if host else None, id(style_cache) if style_cache is not None else None)
         ent = self._graphs.get(key)
         if ent is None:

@@ -146,6 +146,15 @@ int wctb_centered_gram_fast(const float* x_p4, int C, int H, int W, int y0, int 
 int wctb_eigh_jacobi(const double* a, int nprob, int C, const double* scale_host, int add_identity,
                      double* evals, double* evecs, double* work, int* sweeps_out, void* stream);
 
+/* same with an explicit early-stop threshold for the C <= 128 solver: the iteration ends after a sweep whose largest
+ * |cos(column_p, column_q)| is below early_stop_cos (quadratic convergence: that sweep leaves ~early_stop_cos^2).
+ * wctb_eigh_jacobi uses 3e-6 (residual <= 1e-9); 1e-4 still leaves <= ~1e-8 and usually saves one sweep; 1e-2 leaves
+ * <= ~1e-5 (whitening matrix error ~2e-6) and saves two -- enough when the features carry TF32 noise (1e-3).
+ * Range [0, 0.1]; ignored by the C > 128 solver.                                                                       */
+int wctb_eigh_jacobi_tol(const double* a, int nprob, int C, const double* scale_host, int add_identity,
+                         double early_stop_cos, double* evals, double* evecs, double* work, int* sweeps_out,
+                         void* stream);
+
 /* ---- whitening / colouring matrix ----------------------------------------------------
  * replaces: util_wct.py:117-126 + the alpha blend of transform() (util_wct.py:219):
  *   W   = sum_{k: Ec_k > tau*max(Ec)} Ec_k^-1/2 vc_k vc_k^T        (117-119)
@@ -211,6 +220,10 @@ int wctb_debug_set_eigh_variant(int variant);
 /* debug: 0 (default) = wctb_centered_gram_fast uses the register-resident kernel for C = 24 / 32 (a thread owns whole
  * pixels; no shared-memory traffic in the loop); 1 = the staged shared-memory kernel everywhere (A/B timing).          */
 int wctb_debug_set_gram_variant(int variant);
+
+/* debug: 0 (default) = wctb_conv3x3_first computes two pixels per thread when W >= 64; 1 = one pixel per thread (A/B;
+ * the two kernels are bit-identical).                                                                                 */
+int wctb_debug_set_first_variant(int variant);
 
 /* debug: when buf16 != NULL the C in (64,128] solve records clock64() phase times of thread 0 into buf16:
  * [0] load + compaction, [1] Cholesky, [2] Jacobi sweeps, [8] sweep count, [9] live size k.                          */

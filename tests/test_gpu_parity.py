@@ -37,7 +37,8 @@ def test_layout_roundtrip_bit_exact(shape):
 
 
 # ------------------------------------------------------------------ convs (fp32 engine): vs torch-cpu fp32
-@pytest.mark.parametrize("H,W,cout", [(2, 2, 16), (9, 13, 24), (37, 70, 16), (64, 64, 64)])
+@pytest.mark.parametrize("H,W,cout", [(2, 2, 16), (9, 13, 24), (37, 70, 16), (64, 64, 64), (11, 65, 24), (9, 96, 24),
+                                      (10, 97, 24), (17, 129, 24), (8, 200, 64)])
 def test_conv_first_fp32(H, W, cout):
     g = torch.Generator().manual_seed(1)
     x = torch.rand(1, 3, H, W, generator=g)
@@ -48,6 +49,13 @@ def test_conv_first_fp32(H, W, cout):
     got = ops.p4_to_nchw(y).cpu()
     assert got.shape == ref.shape
     assert (got - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())   # fp32, different summation order
+    # the two-pixels-per-thread kernel (default for W >= 64) and the one-pixel kernel are bit-identical
+    ops.set_first_variant(1)
+    try:
+        y1 = ops.conv3x3_first(x.to(DEV), ops.pack_weights(w.to(DEV), ops.ENGINE_FP32), b.to(DEV), cout, False)
+    finally:
+        ops.set_first_variant(0)
+    assert torch.equal(y, y1)
 
 
 @pytest.mark.parametrize("H,W,cin,cout,epi", [
@@ -176,7 +184,6 @@ def test_whiten_and_color_vs_reference_golden(golden_dir, case):
         assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
 
 
-@pytest.mark.pending_hw
 @pytest.mark.parametrize("case,tag,num,rat", [("full_rank", "num10", 10, None), ("wide", "num30", 30, None),
                                               ("dead_channels", "num12", 12, None), ("wide", "rat025", None, 0.25),
                                               ("dead_channels", "rat025", None, 0.25)])
