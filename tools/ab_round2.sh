@@ -20,5 +20,4 @@ PY
 }
 run base WCTB_FIRST_VARIANT=1 WCTB_EIG_EARLY=3e-6
 run first2 WCTB_EIG_EARLY=3e-6
-run early1e-4 WCTB_EIG_EARLY=1e-4
 run defaults WCTB_X=0
