@@ -242,7 +242,8 @@ def set_first_variant(v: int):
 
 
 def set_gram_variant(v: int):
-    """debug: 0 = register-resident fast Gram for C = 24 / 32 (default), 1 = staged shared-memory kernel everywhere"""
+    """debug: fast Gram for C = 24 / 32: 0 = register accumulation fed from a cp.async ring (default), 2 = fed through L1,
+    1 = staged shared-memory kernel everywhere"""
     check(_lib.load().wctb_debug_set_gram_variant(int(v)), "debug_set_gram_variant")
 
 

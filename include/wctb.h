@@ -217,8 +217,9 @@ int wctb_resize_u8_pass(const uint8_t* src_hwc, uint8_t* dst_hwc, int H, int W, 
  * tools/eig_diag.py).  Process-wide; not meant to be toggled while work is in flight.                                */
 int wctb_debug_set_eigh_variant(int variant);
 
-/* debug: 0 (default) = wctb_centered_gram_fast uses the register-resident kernel for C = 24 / 32 (a thread owns whole
- * pixels; no shared-memory traffic in the loop); 1 = the staged shared-memory kernel everywhere (A/B timing).          */
+/* debug: which kernel wctb_centered_gram_fast uses for C = 24 / 32 (A/B timing, tools/gram_ab.py):
+ * 0 (default) = register-resident accumulation (a thread owns whole pixels) fed from a cp.async shared-memory ring;
+ * 2 = the same accumulation fed by direct global loads through L1; 1 = the staged shared-memory tile kernel everywhere. */
 int wctb_debug_set_gram_variant(int variant);
 
 /* debug: 0 (default) = wctb_conv3x3_first computes two pixels per thread when W >= 64; 1 = one pixel per thread (A/B;

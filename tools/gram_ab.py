@@ -26,7 +26,7 @@ for (C, H, W) in [(24, 2160, 3840), (32, 1080, 1920), (24, 2000, 2000), (24, 409
     x = torch.rand(C // 4, H, W, 4, device="cuda") * 3
     mean = (ops.channel_sum(x) / (H * W))
     res = {}
-    for variant in (1, 0):
+    for variant in (1, 2, 0):
         ops.set_gram_variant(variant)
         ts = []
         for i in range(6):
@@ -44,6 +44,7 @@ for (C, H, W) in [(24, 2160, 3840), (32, 1080, 1920), (24, 2000, 2000), (24, 409
     torch.cuda.synchronize()
     err = {v: ((res[v][1] - g64).abs().max() / g64.abs().max()).item() for v in res}
     gb = C * H * W * 4 / 1e9
-    log("C=%d %dx%d (%.0f MB): staged %.3f ms (%.0f GB/s, err %.1e) | register-resident %.3f ms (%.0f GB/s, err %.1e) | x%.2f"
-        % (C, H, W, gb * 1e3, res[1][0], gb / res[1][0] * 1e3, err[1], res[0][0], gb / res[0][0] * 1e3, err[0], res[1][0] / res[0][0]))
+    log("C=%d %dx%d (%.0f MB): " % (C, H, W, gb * 1e3) + " | ".join(
+        "%s %.3f ms (%.0f GB/s, err %.1e)" % (name, res[v][0], gb / res[v][0] * 1e3, err[v])
+        for v, name in ((1, "staged"), (2, "regs/L1"), (0, "regs/cp.async ring"))))
     del x
