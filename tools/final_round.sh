@@ -15,6 +15,6 @@ for n in ("bench_final", "bench_final_gram2"):
         print(n, "failed", e)
 PY
 timeout 25 python tools/io_bench.py 2>&1 | tail -1 | cut -c1-900
-timeout ${1:-45} python -m pytest tests -q -m gpu -x -p no:cacheprovider -v 2>&1 | grep -E "PASSED|FAILED|ERROR|passed|failed" | sed 's/ PASSED//' > gpurun_out/pytest_gpu_final.log
+timeout ${1:-45} python -m pytest tests/test_gpu_parity.py tests/test_image_io_gpu.py tests/test_gpu_umma.py -q -m gpu -x -p no:cacheprovider -v 2>&1 | grep -E "PASSED|FAILED|ERROR|passed|failed" | sed 's/ PASSED//' > gpurun_out/pytest_gpu_final.log
 tail -3 gpurun_out/pytest_gpu_final.log
 grep -c "::" gpurun_out/pytest_gpu_final.log
