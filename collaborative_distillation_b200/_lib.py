@@ -43,6 +43,8 @@ SIGNATURES = {
     "wctb_wct_matrix_topk": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _i, _i, _p, _p, _p, _p, _p],
     "wctb_wct_apply": [_p, _p, _p, _p, _p, _i, _ll, _i, _p],
     "wctb_fold_wct_into_conv": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "wctb_halo_pack": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "wctb_halo_unpack": [_p, _p, _i, _i, _i, _i, _i, _p],
     "wctb_u8hwc_to_nchw": [_p, _p, _i, _i, _p],
     "wctb_nchw_to_u8hwc": [_p, _p, _i, _i, _p],
     "wctb_resize_ksize": [_i, _i],
@@ -61,6 +63,7 @@ SIGNATURES = {
 WCTB_OK = 0
 EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3 = 0, 1, 2, 3
 ENGINE_FP32, ENGINE_TF32 = 0, 1
+WS_EIGH, WS_WCT_MATRIX = 0, 1
 
 
 class WctbError(RuntimeError):
@@ -88,6 +91,8 @@ def load():
         fn.restype = _i
     lib.wctb_error_string.argtypes = [_i]
     lib.wctb_error_string.restype = ctypes.c_char_p
+    lib.wctb_workspace_doubles.argtypes = [_i, _i, _i]
+    lib.wctb_workspace_doubles.restype = _ll
     if lib.wctb_abi_version() != 1:
         raise WctbError("libwctb ABI version mismatch")
     if os.environ.get("WCTB_GRAM_VARIANT"):          # A/B switch for tools / bench runs (see wctb.h, debug section)

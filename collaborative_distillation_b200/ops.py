@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3, ENGINE_FP32, ENGINE_TF32, check  # noqa: F401
 
 _launches = 0  # number of libwctb kernel-launching calls (bench.py reports kernels via its own table)
-KERNELS_PER_CALL = {"nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
+KERNELS_PER_CALL = {"halo": 1, "nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
                     "conv_last": 1, "conv_head": 1, "conv_head_tc": 1, "conv_tail": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
                     "fold": 2}
 
@@ -58,6 +58,23 @@ def p4_to_nchw(x: torch.Tensor) -> torch.Tensor:
     check(_lib.load().wctb_p4_to_nchw(_need(x), _need(y), C4 * 4, H, W, _stream()), "p4_to_nchw")
     _count("p4_to_nchw")
     return y
+
+
+def halo_pack(img: torch.Tensor, x0: int, w: int) -> torch.Tensor:
+    """columns [x0, x0+w) of an NCHW strip [1,C,H,W] -> contiguous [1,C,H,w] (the buffer a rank sends to a neighbour)"""
+    _, C, H, W = img.shape
+    buf = torch.empty(1, C, H, w, device=img.device, dtype=torch.float32)
+    check(_lib.load().wctb_halo_pack(_need(img), _need(buf), C, H, W, int(x0), int(w), _stream()), "halo_pack")
+    _count("halo")
+    return buf
+
+
+def halo_unpack(buf: torch.Tensor, ext: torch.Tensor, x0: int) -> None:
+    """write a contiguous [1,C,H,w] buffer into columns [x0, x0+w) of the extended strip ext [1,C,H,We]"""
+    _, C, H, w = buf.shape
+    We = ext.shape[-1]
+    check(_lib.load().wctb_halo_unpack(_need(buf), _need(ext), C, H, We, int(x0), int(w), _stream()), "halo_unpack")
+    _count("halo")
 
 
 def tf32_supported(cin: int, cout: int) -> bool:
@@ -217,7 +234,7 @@ def eigh_jacobi(a: torch.Tensor, scale, add_identity: bool = False, return_sweep
     scale_host = (ctypes.c_double * nprob)(*scale)
     evals = torch.empty(nprob, C, device=a.device, dtype=torch.float64)
     evecs = torch.empty(nprob, C, C, device=a.device, dtype=torch.float64)
-    work = torch.empty(nprob * C * C + 16, device=a.device, dtype=torch.float64)
+    work = torch.empty(_lib.load().wctb_workspace_doubles(_lib.WS_EIGH, C, nprob), device=a.device, dtype=torch.float64)
     sweeps = torch.zeros(nprob, device=a.device, dtype=torch.int32)
     if early_stop is None:
         check(_lib.load().wctb_eigh_jacobi(_need(a, torch.float64), nprob, C, scale_host, int(add_identity),
@@ -280,7 +297,7 @@ def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, a
     m = torch.empty(C, C, device=dev, dtype=torch.float32)
     b = torch.empty(C, device=dev, dtype=torch.float32)
     mc = torch.empty(C, device=dev, dtype=torch.float32)
-    work = torch.empty(3 * C * C + 8, device=dev, dtype=torch.float64)
+    work = torch.empty(_lib.load().wctb_workspace_doubles(_lib.WS_WCT_MATRIX, C, 1), device=dev, dtype=torch.float64)
     f64 = torch.float64
     if keep_c > 0 or keep_s > 0:
         check(_lib.load().wctb_wct_matrix_topk(_need(c_evals, f64), _need(c_evecs, f64), _need(c_mean, f64), _need(s_evals, f64),

@@ -51,10 +51,14 @@ class StripGroup:
     """Strip-parallel driver.  `stage_fn(stage, content_ext, style_ext, alpha, c_region, s_region, c_count, s_count) -> image_ext`
     is `WCT.style_transfer_stage` in production (with `wct.dist = self`), or a CPU restatement in the gloo tests."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, native_halo=False):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        # native_halo: pack the send buffers and assemble the extended strip with libwctb's halo kernels
+        # (wctb_halo_pack / wctb_halo_unpack) instead of torch slicing + cat.  Same bytes either way; off until its first
+        # multi-GPU run is on record (the kernels themselves are covered by the single-GPU tests).
+        self.native_halo = native_halo
 
     # ---- collectives used by WCT._moments
     def allreduce_(self, t: torch.Tensor):
@@ -75,19 +79,35 @@ class StripGroup:
         if w < halo:
             raise ValueError("strip width %d < halo %d: use fewer GPUs for this image" % (w, halo))
         r, n = self.rank, self.world
+        native = self.native_halo and own.is_cuda
+        if native:
+            from . import ops as K
+            own = own.contiguous()
+            pack = lambda x0: K.halo_pack(own, x0, halo)
+        else:
+            pack = lambda x0: own[..., x0:x0 + halo].contiguous()
         ops, left, right = [], None, None
         if r > 0:
             left = torch.empty(own.shape[:-1] + (halo,), dtype=own.dtype, device=own.device)
-            ops += [dist.P2POp(dist.isend, own[..., :halo].contiguous(), r - 1, self.group),
+            ops += [dist.P2POp(dist.isend, pack(0), r - 1, self.group),
                     dist.P2POp(dist.irecv, left, r - 1, self.group)]
         if r < n - 1:
             right = torch.empty(own.shape[:-1] + (halo,), dtype=own.dtype, device=own.device)
-            ops += [dist.P2POp(dist.isend, own[..., -halo:].contiguous(), r + 1, self.group),
+            ops += [dist.P2POp(dist.isend, pack(w - halo), r + 1, self.group),
                     dist.P2POp(dist.irecv, right, r + 1, self.group)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+        lh, rh = (halo if left is not None else 0), (halo if right is not None else 0)
+        if native:
+            ext = torch.empty(own.shape[:-1] + (lh + w + rh,), dtype=own.dtype, device=own.device)
+            if left is not None:
+                K.halo_unpack(left, ext, 0)
+            K.halo_unpack(own, ext, lh)
+            if right is not None:
+                K.halo_unpack(right, ext, lh + w)
+            return ext, lh, rh
         parts = [p for p in (left, own, right) if p is not None]
-        return torch.cat(parts, dim=-1).contiguous(), (halo if left is not None else 0), (halo if right is not None else 0)
+        return torch.cat(parts, dim=-1).contiguous(), lh, rh
 
     @staticmethod
     def own_slice(full: torch.Tensor, cuts, rank: int):

@@ -190,6 +190,19 @@ int wctb_fold_wct_into_conv(const float* w_oihw, const float* bias, const float*
                             const float* mean_c, float* w_out, float* b_out, int Cin, int Cout,
                             void* stream);
 
+/* ---- workspace sizes -----------------------------------------------------------------------------------------
+ * HOST query (no GPU): doubles of scratch the `work` argument of an entry point must hold, so that a caller can size one
+ * persistent arena instead of allocating per call (the reference frees and re-allocates through empty_cache(), WCT.py:99-105). */
+enum { WCTB_WS_EIGH = 0 /* wctb_eigh_jacobi[_tol]: nprob*C*C + 16 */, WCTB_WS_WCT_MATRIX = 1 /* wctb_wct_matrix[_topk]: 3*C*C + 8 */ };
+long long wctb_workspace_doubles(int op, int C, int nprob);
+
+/* ---- strip halos of the multi-GPU path (no counterpart in the single-GPU reference) ------------------
+ * An image strip is NCHW [C][H][W] fp32.  pack: columns [x0, x0+w) -> contiguous send buffer [C][H][w].
+ * unpack: buffer [C][H][w] -> columns [x0, x0+w) of the extended strip [C][H][We] (also used to place the rank's own
+ * columns).  Plain copies (bit-exact); the buffers are what the host hands to NCCL send/recv.                          */
+int wctb_halo_pack(const float* img_nchw, float* buf, int C, int H, int W, int x0, int w, void* stream);
+int wctb_halo_unpack(const float* buf, float* ext_nchw, int C, int H, int We, int x0, int w, void* stream);
+
 /* ---- image I/O around the path: byte / integer kernels, bit-exact --------------------
  * Images here are interleaved 8-bit RGB, [H][W][3] (what PIL / nvJPEG produce and consume).
  *

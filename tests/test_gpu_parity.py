@@ -390,3 +390,19 @@ def test_style_cache_equals_full_path(golden_dir):
     torch.cuda.synchronize()
     assert (a - full).abs().max().item() <= 1e-5
     assert (b - c).abs().max().item() <= 1e-5
+
+
+# ------------------------------------------------------------------ strip halos (multi-GPU data movement, single-GPU check)
+@pytest.mark.pending_hw
+@pytest.mark.parametrize("C,H,W,halo", [(3, 37, 200, 16), (3, 64, 160, 160), (3, 5, 33, 1), (24, 9, 70, 32)])
+def test_halo_pack_unpack_bit_exact(C, H, W, halo):
+    """wctb_halo_pack / wctb_halo_unpack == torch slicing + cat (what StripGroup.exchange does by default)"""
+    x = torch.randn(1, C, H, W, device=DEV)
+    left, right = ops.halo_pack(x, 0, halo), ops.halo_pack(x, W - halo, halo)
+    assert torch.equal(left, x[..., :halo]) and torch.equal(right, x[..., W - halo:])
+    nl, nr = torch.randn(1, C, H, halo, device=DEV), torch.randn(1, C, H, halo, device=DEV)
+    ext = torch.full((1, C, H, halo + W + halo), float("nan"), device=DEV)
+    ops.halo_unpack(nl, ext, 0)
+    ops.halo_unpack(x, ext, halo)
+    ops.halo_unpack(nr, ext, halo + W)
+    assert torch.equal(ext, torch.cat([nl, x, nr], dim=-1))

@@ -84,7 +84,11 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), "libwctb.so does not export %s" % name
-    assert declared == set(_lib.SIGNATURES) | {"wctb_error_string"}
+    assert declared == set(_lib.SIGNATURES) | {"wctb_error_string", "wctb_workspace_doubles"}
+    lib2 = _lib.load()
+    assert lib2.wctb_workspace_doubles(_lib.WS_EIGH, 128, 2) == 2 * 128 * 128 + 16
+    assert lib2.wctb_workspace_doubles(_lib.WS_WCT_MATRIX, 64, 1) == 3 * 64 * 64 + 8
+    assert lib2.wctb_workspace_doubles(7, 64, 1) == -1 and lib2.wctb_workspace_doubles(_lib.WS_EIGH, 0, 1) == -1
     assert _lib.load().wctb_abi_version() == 1
     assert _lib.load().wctb_error_string(-2) == b"unsupported configuration"
 
@@ -269,3 +273,27 @@ def test_jacobi_owner_visitor_schedule(k):
             for g in range(1, ng):
                 assert 1 <= (own[g] - (r + 1)) % m <= h
     assert len(seen) == k * (k - 1) // 2
+
+
+def test_wct_knobs_defaults_and_overrides(monkeypatch):
+    """host-side knobs of the WCT container: eigensolver early stop by conv precision, eigenvalue truncation
+    (util_wct.py:26-27), bounded CUDA-graph cache"""
+    w = P.WCT(SimpleNamespace(mode="16x", numpy=False))
+    old = P.get_precision()
+    try:
+        P.set_precision("tf32")
+        assert w._early() == 1e-2
+        P.set_precision("fp32")
+        assert w._early() == 1e-4
+        w.eig_early = 3e-6
+        assert w._early() == 3e-6
+    finally:
+        P.set_precision(old)
+    assert w._keep(128) == 0                                    # the shipped reference keeps every direction
+    w.rat_eig = 0.25
+    assert w._keep(128) == 32 and w._keep(24) == 6              # int(C * RatEigenValue)
+    w.num_eig = 30
+    assert w._keep(128) == 30                                   # NumEigenValue wins
+    assert w.max_graphs >= 1 and len(w._graphs) == 0
+    monkeypatch.setenv("WCTB_EIG_EARLY", "1e-3")
+    assert P.WCT(SimpleNamespace(mode="16x", numpy=False))._early() == 1e-3
