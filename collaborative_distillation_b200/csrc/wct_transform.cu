@@ -466,7 +466,7 @@ __device__ __forceinline__ void gram_ring_step(float (&acc)[GramDeal<NCH, SPLIT>
   }
 }
 
-template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW>
+template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW, bool PEEL>
 __device__ __forceinline__ void gram_ring_body(float4* __restrict__ ring, const float4* __restrict__ x, long long HW, int W, int y0,
                                                int x0, unsigned wreg, unsigned npix, unsigned iters,
                                                const float4* __restrict__ s_mh, double* __restrict__ G) {
@@ -488,7 +488,10 @@ __device__ __forceinline__ void gram_ring_body(float4* __restrict__ ring, const 
     if ((unsigned)t < iters) gram_ring_issue<NCH, SPLIT, PIX, FULLROW>(ring + t * TILE, x, HW, W, y0, x0, wreg, npix, cta_base + t * stride);
     cp_async_commit();
   }
-  for (unsigned it = 0; it < iters; ++it) {
+  // PEEL (variant 3, not yet the default): the range-checked last tile is handled after the loop, which halves the loop's
+  // code (ncu: 0.59 warps stalled on instruction fetch per issue in the unpeeled loop, profiles/r01_gram_ring_ncu_full.txt)
+  const unsigned loop_iters = PEEL ? iters - 1 : iters;
+  for (unsigned it = 0; it < loop_iters; ++it) {
     cp_async_wait<RING - 2>();       // this thread's copies of tile `it` have landed
     // CTA-wide named barrier (the groups sit in different branches of the dispatch): everybody's copies of tile `it` are
     // visible, and everybody has finished computing tile it-1, whose slot is refilled next
@@ -497,11 +500,17 @@ __device__ __forceinline__ void gram_ring_body(float4* __restrict__ ring, const 
     if (tn < iters) gram_ring_issue<NCH, SPLIT, PIX, FULLROW>(ring + (tn % RING) * TILE, x, HW, W, y0, x0, wreg, npix, cta_base + tn * stride);
     cp_async_commit();
     const float4* tile = ring + (it % RING) * TILE;
-    if (it + 1 < iters) {
+    if (PEEL || it + 1 < iters) {
       gram_ring_step<NCH, SPLIT, PART, PIX, false>(acc, tile, j, true, s_mh);
     } else {
       gram_ring_step<NCH, SPLIT, PART, PIX, true>(acc, tile, j, cta_base + it * stride + j < npix, s_mh);
     }
+  }
+  if (PEEL) {
+    const unsigned it = iters - 1;
+    cp_async_wait<0>();
+    asm volatile("bar.sync 1, %0;" ::"r"(PIX * SPLIT) : "memory");
+    gram_ring_step<NCH, SPLIT, PART, PIX, true>(acc, ring + (it % RING) * TILE, j, cta_base + it * stride + j < npix, s_mh);
   }
   cp_async_wait<0>();
   // flush
@@ -533,18 +542,18 @@ __device__ __forceinline__ void gram_ring_body(float4* __restrict__ ring, const 
   }
 }
 
-template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW>
+template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW, bool PEEL>
 __device__ __forceinline__ void gram_ring_dispatch(int part, float4* __restrict__ ring, const float4* __restrict__ x, long long HW,
                                                    int W, int y0, int x0, unsigned wreg, unsigned npix, unsigned iters,
                                                    const float4* s_mh, double* __restrict__ G) {
   if (part == PART) {
-    gram_ring_body<NCH, SPLIT, PART, PIX, RING, FULLROW>(ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
+    gram_ring_body<NCH, SPLIT, PART, PIX, RING, FULLROW, PEEL>(ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
   } else if constexpr (PART + 1 < SPLIT) {
-    gram_ring_dispatch<NCH, SPLIT, PART + 1, PIX, RING, FULLROW>(part, ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
+    gram_ring_dispatch<NCH, SPLIT, PART + 1, PIX, RING, FULLROW, PEEL>(part, ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
   }
 }
 
-template <int NCH, int SPLIT, int PIX, int RING, bool FULLROW>
+template <int NCH, int SPLIT, int PIX, int RING, bool FULLROW, bool PEEL>
 __global__ void __launch_bounds__(PIX* SPLIT, 1) gram_ring_kernel(const float4* __restrict__ x, int H, int W, int y0, int x0,
                                                                    unsigned wreg, unsigned npix, unsigned iters,
                                                                    const double* __restrict__ mean, double* __restrict__ G) {
@@ -555,11 +564,11 @@ __global__ void __launch_bounds__(PIX* SPLIT, 1) gram_ring_kernel(const float4* 
   __shared__ float4 s_mh[NCH];
   if (threadIdx.x < NCH * 4) reinterpret_cast<float*>(s_mh)[threadIdx.x] = (float)mean[threadIdx.x];
   __syncthreads();
-  gram_ring_dispatch<NCH, SPLIT, 0, PIX, RING, FULLROW>(threadIdx.x / PIX, ring, x, (long long)H * W, W, y0, x0, wreg, npix, iters,
+  gram_ring_dispatch<NCH, SPLIT, 0, PIX, RING, FULLROW, PEEL>(threadIdx.x / PIX, ring, x, (long long)H * W, W, y0, x0, wreg, npix, iters,
                                                         s_mh, G);
 }
 
-template <int NCH, int SPLIT, int PIX, int RING>
+template <int NCH, int SPLIT, int PIX, int RING, bool PEEL>
 static int launch_gram_ring(const float* x, int H, int W, int y0, int y1, int x0, int x1, const double* mean, double* gram_out,
                             cudaStream_t st) {
   const long long npix = (long long)(y1 - y0) * (x1 - x0);
@@ -572,24 +581,25 @@ static int launch_gram_ring(const float* x, int H, int W, int y0, int y1, int x0
   const size_t smem = (size_t)RING * NCH * PIX * sizeof(float4);
   static bool attr_done = false;
   if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, true, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, false, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   if (x0 == 0 && x1 == W)
-    gram_ring_kernel<NCH, SPLIT, PIX, RING, true><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                             (unsigned)npix, iters, mean, gram_out);
+    gram_ring_kernel<NCH, SPLIT, PIX, RING, true, PEEL><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
+                                                                                                   (unsigned)npix, iters, mean, gram_out);
   else
-    gram_ring_kernel<NCH, SPLIT, PIX, RING, false><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                              (unsigned)npix, iters, mean, gram_out);
+    gram_ring_kernel<NCH, SPLIT, PIX, RING, false, PEEL><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
+                                                                                                    (unsigned)npix, iters, mean, gram_out);
   WCTB_RETURN_LAUNCH();
 }
 
 // 0: register accumulation fed from a cp.async ring for C = 24 / 32 (default); 2: register accumulation fed by direct
-// global loads through L1 (the first version); 1: staged shared-memory kernel everywhere.  A/B timing, tools/gram_ab.py.
+// global loads through L1 (the first version); 1: staged shared-memory kernel everywhere; 3: variant 0 with the last
+// iteration peeled out of the loop (written after the round's last GPU slot: not yet run on hardware).  tools/gram_ab.py.
 static int g_gram_variant = 0;
 extern "C" int wctb_debug_set_gram_variant(int v) {
-  if (v < 0 || v > 2) return WCTB_E_BADARG;
+  if (v < 0 || v > 3) return WCTB_E_BADARG;
   g_gram_variant = v;
   return WCTB_OK;
 }
@@ -603,8 +613,11 @@ extern "C" int wctb_centered_gram_fast(const float* x, int C, int H, int W, int 
   cudaStream_t st = (cudaStream_t)stream;
   if (g_gram_variant != 1 && (long long)(y1 - y0) * (x1 - x0) < (1LL << 31) - (1LL << 24)) {
     if (g_gram_variant == 0) {
-      if (C == 24) return launch_gram_ring<6, 4, 96, 6>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-      if (C == 32) return launch_gram_ring<8, 6, 64, 6>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+      if (C == 24) return launch_gram_ring<6, 4, 96, 6, false>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+      if (C == 32) return launch_gram_ring<8, 6, 64, 6, false>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+    } else if (g_gram_variant == 3) {
+      if (C == 24) return launch_gram_ring<6, 4, 96, 6, true>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+      if (C == 32) return launch_gram_ring<8, 6, 64, 6, true>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
     } else {
       if (C == 24) return launch_gram_regs<6, 4, 96>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
       if (C == 32) return launch_gram_regs<8, 6, 64>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);

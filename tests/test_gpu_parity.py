@@ -123,6 +123,26 @@ def test_moments_match_fp64(C, H, W, region):
     assert (gf - gf.t()).abs().max().item() <= 1e-13 * ref.abs().max().item()
 
 
+@pytest.mark.pending_hw
+@pytest.mark.parametrize("C,H,W,region", [(24, 31, 47, None), (24, 300, 310, None), (32, 257, 300, None), (24, 40, 50, (3, 37, 8, 50)),
+                                          (32, 33, 70, (0, 33, 5, 64)), (24, 3, 5, None), (32, 700, 900, (10, 690, 0, 900))])
+def test_gram_ring_peeled_variant(C, H, W, region):
+    """variant 3 (last iteration peeled out of the ring loop; written after the round's last GPU slot) == variant 0"""
+    x = (torch.randn(C, H, W, generator=torch.Generator().manual_seed(5)) * 3 + 1.5).relu()
+    p4 = ops.nchw_to_p4(x.to(DEV))
+    y0, y1, x0, x1 = region or (0, H, 0, W)
+    xr = x[:, y0:y1, x0:x1].double().reshape(C, -1)
+    mean = xr.mean(1)
+    xc = xr - mean[:, None]
+    ref = xc @ xc.t()
+    ops.set_gram_variant(3)
+    try:
+        g3 = ops.centered_gram(p4, mean.to(DEV), region, fast=True).cpu()
+    finally:
+        ops.set_gram_variant(0)
+    assert (g3 - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+
+
 # ------------------------------------------------------------------ eigensolver
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("C,rank", [(24, 24), (32, 20), (64, 64), (100, 37), (128, 51), (128, 128), (256, 200), (512, 512)])

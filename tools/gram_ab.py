@@ -26,7 +26,8 @@ for (C, H, W) in [(24, 2160, 3840), (32, 1080, 1920), (24, 2000, 2000), (24, 409
     x = torch.rand(C // 4, H, W, 4, device="cuda") * 3
     mean = (ops.channel_sum(x) / (H * W))
     res = {}
-    for variant in (1, 2, 0):
+    variants = ((1, "staged"), (2, "regs/L1"), (0, "regs/cp.async ring")) + (((3, "ring, peeled"),) if "--peeled" in sys.argv else ())
+    for variant, _ in variants:
         ops.set_gram_variant(variant)
         ts = []
         for i in range(6):
@@ -46,5 +47,5 @@ for (C, H, W) in [(24, 2160, 3840), (32, 1080, 1920), (24, 2000, 2000), (24, 409
     gb = C * H * W * 4 / 1e9
     log("C=%d %dx%d (%.0f MB): " % (C, H, W, gb * 1e3) + " | ".join(
         "%s %.3f ms (%.0f GB/s, err %.1e)" % (name, res[v][0], gb / res[v][0] * 1e3, err[v])
-        for v, name in ((1, "staged"), (2, "regs/L1"), (0, "regs/cp.async ring"))))
+        for v, name in variants))
     del x
