@@ -23,14 +23,17 @@ def build(verbose=False, force=False):
     out = os.path.join(HERE, "libwctb.so")
     hdrs = [os.path.join(HERE, "common.cuh"), os.path.join(ROOT, "include", "wctb.h")]
     hdrs += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
-    objs = []
+    objs, cmds = [], []
     for src in SOURCES:
         s = os.path.join(HERE, src)
         o = os.path.join(HERE, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + hdrs):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
-            subprocess.check_call(cmd)
+            cmds.append([NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
         objs.append(o)
+    if cmds:   # translation units are independent: compile them side by side (wct_transform.cu alone takes ~2 min)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as pool:
+            list(pool.map(subprocess.check_call, cmds))
     if force or _stale(out, objs):
         subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-lcudart"])
     build_io(force=force)
