@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """Which TF32 pieces contribute how much error?  5-stage stylize vs the CPU oracle on (a) the smoke case (uniform-noise
-96x128 / 64x80) and (b) a smoothed 256x320 / 200x240 case, toggling the optional tensor-core pieces."""
+96x128 / 64x80) and (b) a smoothed 256x320 / 200x240 case, toggling the optional tensor-core pieces.
+Lives under tests/ because it uses the oracle as the checker (the oracle is test infrastructure only)."""
 import os, sys
 from types import SimpleNamespace
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import collaborative_distillation_b200 as P
 from collaborative_distillation_b200 import nets
 from oracle import wct_oracle as O
-root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 wpath = os.path.join(root, "tests", "golden", "weights_16x.npz")
 ow = O.load_weights_npz(wpath)
 g = torch.Generator().manual_seed(0)
