@@ -60,7 +60,9 @@ class WCT(nn.Module):
     def _early(self):
         if self.eig_early is not None:
             return float(self.eig_early)
-        return 1e-2 if nets.get_precision() == "tf32" else 1e-4
+        # sharded runs keep the tight setting: with 1e-2 a last-bit difference in the all-reduced statistics could flip the
+        # sweep count and move the whitening matrix by ~1e-5 between partitions; at 1e-4 such a flip is worth <= 1e-8
+        return 1e-2 if (nets.get_precision() == "tf32" and self.dist is None) else 1e-4
 
     def _keep(self, C):
         """number of eigen-directions kept for content and style (0 = all): k = NumEigenValue, or int(C * RatEigenValue)"""

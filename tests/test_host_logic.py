@@ -283,6 +283,9 @@ def test_wct_knobs_defaults_and_overrides(monkeypatch):
     try:
         P.set_precision("tf32")
         assert w._early() == 1e-2
+        w.dist = object()                     # sharded: tight setting regardless of the conv precision (tile invariance)
+        assert w._early() == 1e-4
+        w.dist = None
         P.set_precision("fp32")
         assert w._early() == 1e-4
         w.eig_early = 3e-6
