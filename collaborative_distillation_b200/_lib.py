@@ -41,6 +41,8 @@ SIGNATURES = {
     "wctb_eigh_jacobi_tol": [_p, _i, _i, ctypes.POINTER(ctypes.c_double), _i, _d, _p, _p, _p, _p, _p],
     "wctb_wct_matrix": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p],
     "wctb_wct_matrix_topk": [_p, _p, _p, _p, _p, _p, _i, _d, _d, _i, _i, _p, _p, _p, _p, _p],
+    "wctb_whiten_ns": [_p, _d, _i, _i, _p, _p, _p, _p],
+    "wctb_wct_matrix_w": [_p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p],
     "wctb_wct_apply": [_p, _p, _p, _p, _p, _i, _ll, _i, _p],
     "wctb_fold_wct_into_conv": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "wctb_halo_pack": [_p, _p, _i, _i, _i, _i, _i, _p],
@@ -63,7 +65,7 @@ SIGNATURES = {
 WCTB_OK = 0
 EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3 = 0, 1, 2, 3
 ENGINE_FP32, ENGINE_TF32 = 0, 1
-WS_EIGH, WS_WCT_MATRIX = 0, 1
+WS_EIGH, WS_WCT_MATRIX, WS_WHITEN_NS = 0, 1, 2
 
 
 class WctbError(RuntimeError):

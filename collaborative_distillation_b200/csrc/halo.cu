@@ -45,7 +45,8 @@ extern "C" long long wctb_workspace_doubles(int op, int C, int nprob) {
   if (C <= 0 || nprob <= 0) return WCTB_E_BADARG;
   switch (op) {
     case WCTB_WS_EIGH: return (long long)nprob * C * C + 16;        // wctb_eigh_jacobi / _tol: `work`
-    case WCTB_WS_WCT_MATRIX: return 3LL * C * C + 8;                // wctb_wct_matrix / _topk: `work` (nprob ignored)
+    case WCTB_WS_WCT_MATRIX: return 3LL * C * C + 8;                // wctb_wct_matrix / _topk / _w: `work` (nprob ignored)
+    case WCTB_WS_WHITEN_NS: return 8LL * C * C + 8;                 // wctb_whiten_ns: `work` (nprob ignored)
     default: return WCTB_E_BADARG;
   }
 }

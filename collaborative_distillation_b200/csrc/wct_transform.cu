@@ -1427,6 +1427,24 @@ extern "C" int wctb_wct_matrix(const double* c_evals, const double* c_evecs, con
   WCTB_RETURN_LAUNCH();
 }
 
+// M, b, mean_c from a ready whitening matrix (wctb_whiten_ns) and the style eigensystem
+extern "C" int wctb_wct_matrix_w(const double* w_whiten, const double* c_mean, const double* s_evals, const double* s_evecs,
+                                 const double* s_mean, int C, double tau, double alpha, float* m_out, float* b_out,
+                                 float* mean_c_out, double* work, void* stream) {
+  if (!w_whiten || !c_mean || !s_evals || !s_evecs || !s_mean || !m_out || !b_out || !mean_c_out || !work || C <= 0 || C > 1024)
+    return WCTB_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long CC = (long long)C * C;
+  double* col = work + CC;      // same slots as wctb_wct_matrix
+  double* m64 = work + 2 * CC;
+  double* emax = work + 3 * CC;
+  eig_max_kernel<<<1, 256, 0, st>>>(s_evals, C, emax + 1);
+  dim3 blk(16, 16), grd((C + 15) / 16, (C + 15) / 16);
+  spectral_fn_kernel<<<grd, blk, 0, st>>>(s_evals, s_evecs, C, tau, emax + 1, 0.5, col);
+  wct_matrix_kernel<<<grd, blk, 0, st>>>(col, w_whiten, C, alpha, c_mean, s_mean, m_out, b_out, mean_c_out, m64);
+  WCTB_RETURN_LAUNCH();
+}
+
 // ------------------------------------------------------------------------------------------
 // apply: y = M (x - mean_c) + b  on a P4 map.  CTA: 128 pixels x 32 output channels (blockIdx.y),
 // the [C][32] slab of M^T in smem; thread = 1 pixel x 32 outputs... 2 pixels per thread to halve LDS/FMA.

@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3, ENGINE_FP32, ENGINE_TF32, check  # noqa: F401
 
 _launches = 0  # number of libwctb kernel-launching calls (bench.py reports kernels via its own table)
-KERNELS_PER_CALL = {"halo": 1, "nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
+KERNELS_PER_CALL = {"whiten_ns": 1, "wct_matrix_w": 3, "halo": 1, "nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
                     "conv_last": 1, "conv_head": 1, "conv_head_tc": 1, "conv_tail": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
                     "fold": 2}
 
@@ -310,6 +310,36 @@ def wct_matrix(c_evals, c_evecs, c_mean, s_evals, s_evecs, s_mean, tau: float, a
                                       _need(s_evecs, f64), _need(s_mean, f64), C, float(tau), float(alpha), _need(m),
                                       _need(b), _need(mc), _need(work, f64), _stream()), "wct_matrix")
     _count("wct_matrix")
+    return m, b, mc
+
+
+def whiten_ns(gram: torch.Tensor, scale: float, add_identity: bool = False, return_info: bool = False):
+    """fp64 centred Gram [C,C] -> whitening matrix W = (scale*gram [+I])^-1/2 (pseudo-inverse on the range), fp64 [C,C],
+    by pivoted Cholesky + Newton-Schulz on a cooperative grid (wctb_whiten_ns; C <= 128).  Opt-in path, see wctb.h."""
+    C = gram.shape[-1]
+    g = gram.reshape(C, C)
+    w = torch.empty(C, C, device=g.device, dtype=torch.float64)
+    work = torch.empty(_lib.load().wctb_workspace_doubles(_lib.WS_WHITEN_NS, C, 1), device=g.device, dtype=torch.float64)
+    info = torch.zeros(4, device=g.device, dtype=torch.int32)
+    check(_lib.load().wctb_whiten_ns(_need(g, torch.float64), float(scale), int(add_identity), C, _need(w, torch.float64),
+                                     _need(work, torch.float64), _need(info, torch.int32), _stream()), "whiten_ns")
+    _count("whiten_ns")
+    return (w, info) if return_info else w
+
+
+def wct_matrix_w(w_whiten, c_mean, s_evals, s_evecs, s_mean, tau: float, alpha: float):
+    """like wct_matrix, with the content side given as a ready whitening matrix (whiten_ns)"""
+    C = s_evals.numel()
+    dev = s_evals.device
+    m = torch.empty(C, C, device=dev, dtype=torch.float32)
+    b = torch.empty(C, device=dev, dtype=torch.float32)
+    mc = torch.empty(C, device=dev, dtype=torch.float32)
+    work = torch.empty(_lib.load().wctb_workspace_doubles(_lib.WS_WCT_MATRIX, C, 1), device=dev, dtype=torch.float64)
+    f64 = torch.float64
+    check(_lib.load().wctb_wct_matrix_w(_need(w_whiten, f64), _need(c_mean, f64), _need(s_evals, f64), _need(s_evecs, f64),
+                                        _need(s_mean, f64), C, float(tau), float(alpha), _need(m), _need(b), _need(mc),
+                                        _need(work, f64), _stream()), "wct_matrix_w")
+    _count("wct_matrix_w")
     return m, b, mc
 
 

@@ -45,6 +45,9 @@ class WCT(nn.Module):
         # engine (residual <= ~1e-8, whitening error ~1e-9), 1e-2 with the TF32 engine (whitening error ~2e-6 against
         # 1e-3 of TF32 feature noise; two sweeps fewer on the critical path).  WCTB_EIG_EARLY overrides (A/B runs).
         self.eig_early = float(os.environ["WCTB_EIG_EARLY"]) if os.environ.get("WCTB_EIG_EARLY") else None
+        # content-side whitening solver: "jacobi" (default: eigendecomposition, one CTA) or "ns" (pivoted Cholesky +
+        # Newton-Schulz on a cooperative grid, C <= 128, no eigenvalue-truncation knobs; opt-in until it has run on hardware)
+        self.whiten_solver = os.environ.get("WCTB_WHITEN", "jacobi")
         self.num_eig = NumEigenValue   # per-instance knobs; None = keep all directions (the reference's active behaviour)
         self.rat_eig = RatEigenValue
         self.dist = None          # set by parallel.StripGroup for multi-GPU runs
@@ -63,6 +66,9 @@ class WCT(nn.Module):
         # sharded runs keep the tight setting: with 1e-2 a last-bit difference in the all-reduced statistics could flip the
         # sweep count and move the whitening matrix by ~1e-5 between partitions; at 1e-4 such a flip is worth <= 1e-8
         return 1e-2 if (nets.get_precision() == "tf32" and self.dist is None) else 1e-4
+
+    def _use_ns(self, C):
+        return self.whiten_solver == "ns" and C <= 128 and self._keep(C) == 0
 
     def _keep(self, C):
         """number of eigen-directions kept for content and style (0 = all): k = NumEigenValue, or int(C * RatEigenValue)"""
@@ -99,6 +105,10 @@ class WCT(nn.Module):
         if self.dist is not None:
             self.dist.allreduce_(grams)
         scale = [1.0 / (nc - 1.0), 1.0 / (ns - 1.0)]                                   # util_wct.py:70,96
+        if self._use_ns(C):
+            w_c = ops.whiten_ns(grams[0], scale[0], add_identity=bool(getattr(self.args, "numpy", False)))
+            se, sv = ops.eigh_jacobi(grams[1:2], scale[1:2], early_stop=self._early())
+            return ops.wct_matrix_w(w_c, c_mean, se[0], sv[0], s_mean, self.tau, alpha)
         if getattr(self.args, "numpy", False):                                          # +I on the content covariance only (util_wct.py:143)
             ce, cv = ops.eigh_jacobi(grams[0:1], scale[0:1], add_identity=True, early_stop=self._early())
             se, sv = ops.eigh_jacobi(grams[1:2], scale[1:2], add_identity=False, early_stop=self._early())
@@ -238,14 +248,21 @@ class WCT(nn.Module):
                     gram = torch.zeros(1, C, C, device=c4.device, dtype=torch.float64)
                     c_mean = self._moments(c4, (0, c4.shape[1], 0, c4.shape[2]), n, gram[0])
                     mark(s, "stats")
-                    c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant,   # util_wct.py:143: +I on content only
-                                               early_stop=self._early())
-                    c_e, c_v = c_e[0], c_v[0]
+                    use_ns = self._use_ns(C)
+                    if use_ns:
+                        w_c = ops.whiten_ns(gram[0], 1.0 / (n - 1.0), add_identity=numpy_variant)
+                    else:
+                        c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant,   # util_wct.py:143: +I on content only
+                                                   early_stop=self._early())
+                        c_e, c_v = c_e[0], c_v[0]
                     mark(s, "eig")
                     (s_mean, s_e, s_v), ev = style_res[s]
                     if ev is not None:
                         main.wait_event(ev)
-                    m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha), self._keep(C), self._keep(C))
+                    if use_ns:
+                        m, b, mc = ops.wct_matrix_w(w_c, c_mean, s_e, s_v, s_mean, self.tau, float(alpha))
+                    else:
+                        m, b, mc = ops.wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, self.tau, float(alpha), self._keep(C), self._keep(C))
                     if self.fold_into_decoder:
                         L0 = getattr(dec, dec.layers[0]["name"])
                         w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
@@ -272,7 +289,7 @@ class WCT(nn.Module):
             style = content[..., :1, :1]       # unused placeholder with a stable shape
         host = (not content.is_cuda) and (not style.is_cuda) and content.is_pinned() and style.is_pinned()
         key = (tuple(content.shape), tuple(style.shape), float(alpha), int(num_run), tuple(stages), nets.get_precision(),
-               bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)), self.num_eig, self.rat_eig, float(self.tau), self._early(),
+               bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)), self.num_eig, self.rat_eig, float(self.tau), self._early(), self.whiten_solver,
                (content.data_ptr(), style.data_ptr()) if host else None, id(style_cache) if style_cache is not None else None)
         ent = self._graphs.get(key)
         if ent is None:

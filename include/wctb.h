@@ -176,6 +176,20 @@ int wctb_wct_matrix_topk(const double* c_evals, const double* c_evecs, const dou
                          int C, double tau, double alpha, int keep_c, int keep_s, float* m_out, float* b_out,
                          float* mean_c_out, double* work, void* stream);
 
+/* ---- whitening matrix without an eigendecomposition (opt-in; not yet run on hardware, see csrc/whiten_ns.cu) --------
+ * W = (scale*gram [+ I])^-1/2, pseudo-inverse on the range (rank-revealing pivoted Cholesky + coupled Newton-Schulz on
+ * L^T L, GEMMs only, cooperative grid of 16 CTAs): the content half of util_wct.py:74,117-119 in one launch.
+ * gram: fp64 [C][C] centred Gram (as produced by wctb_centered_gram*), C <= 128; w_out: fp64 [C][C] symmetric, zero
+ * rows/columns for dead channels; work: wctb_workspace_doubles(WCTB_WS_WHITEN_NS, C, 1) doubles;
+ * info_out (optional): int[3] = {rank, iterations, converged}.                                                         */
+int wctb_whiten_ns(const double* gram, double scale_host, int add_identity, int C, double* w_out, double* work,
+                   int* info_out, void* stream);
+/* M, b, mean_c from a ready whitening matrix W (wctb_whiten_ns) and the style eigensystem: M = alpha*Col*W + (1-alpha) I.
+ * work: wctb_workspace_doubles(WCTB_WS_WCT_MATRIX, C, 1) doubles.                                                      */
+int wctb_wct_matrix_w(const double* w_whiten, const double* c_mean, const double* s_evals, const double* s_evecs,
+                      const double* s_mean, int C, double tau, double alpha, float* m_out, float* b_out,
+                      float* mean_c_out, double* work, void* stream);
+
 /* csF = M (cF - mean_c) + b on a P4 map of npix pixels (whole extended strip).
  * replaces: torch.mm(step2, cF), torch.mm(..., whiten_cF), + s_mean (util_wct.py:120,125,126). */
 int wctb_wct_apply(const float* x_p4, const float* m, const float* b, const float* mean_c,
@@ -193,7 +207,8 @@ int wctb_fold_wct_into_conv(const float* w_oihw, const float* bias, const float*
 /* ---- workspace sizes -----------------------------------------------------------------------------------------
  * HOST query (no GPU): doubles of scratch the `work` argument of an entry point must hold, so that a caller can size one
  * persistent arena instead of allocating per call (the reference frees and re-allocates through empty_cache(), WCT.py:99-105). */
-enum { WCTB_WS_EIGH = 0 /* wctb_eigh_jacobi[_tol]: nprob*C*C + 16 */, WCTB_WS_WCT_MATRIX = 1 /* wctb_wct_matrix[_topk]: 3*C*C + 8 */ };
+enum { WCTB_WS_EIGH = 0 /* wctb_eigh_jacobi[_tol]: nprob*C*C + 16 */, WCTB_WS_WCT_MATRIX = 1 /* wctb_wct_matrix[_topk|_w]: 3*C*C + 8 */,
+       WCTB_WS_WHITEN_NS = 2 /* wctb_whiten_ns: 8*C*C + 8 */ };
 long long wctb_workspace_doubles(int op, int C, int nprob);
 
 /* ---- strip halos of the multi-GPU path (no counterpart in the single-GPU reference) ------------------

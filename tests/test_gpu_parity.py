@@ -426,3 +426,77 @@ def test_halo_pack_unpack_bit_exact(C, H, W, halo):
     ops.halo_unpack(x, ext, halo)
     ops.halo_unpack(nr, ext, halo + W)
     assert torch.equal(ext, torch.cat([nl, x, nr], dim=-1))
+
+
+# ------------------------------------------------------------------ whitening without an eigendecomposition (opt-in, csrc/whiten_ns.cu)
+def _pinv_sqrt(S, tau=1e-10):
+    w, v = torch.linalg.eigh(S)
+    keep = w > tau * w.max()
+    return (v[:, keep] * w[keep].pow(-0.5)) @ v[:, keep].t()
+
+
+@pytest.mark.pending_hw
+@pytest.mark.parametrize("kind", ["golden5", "golden4", "golden3", "syn128", "syn24", "syn32_illcond", "plus_identity", "zero"])
+def test_whiten_ns_vs_lapack(golden_dir, kind):
+    """wctb_whiten_ns (pivoted Cholesky + Newton-Schulz, cooperative grid) == LAPACK pseudo-inverse square root.
+    numpy model: tools/ns_invsqrt_prototype.py (1e-14..2e-13 there)."""
+    g = torch.Generator().manual_seed(11)
+    add_identity = False
+    if kind.startswith("golden"):
+        f = torch.from_numpy(np.load(os.path.join(golden_dir, "golden_16x.npz"))["a10.cF" + kind[-1]]).double()
+        f = f.reshape(f.shape[0], -1)                       # dead channels and (stage 5) HW < C: rank-deficient
+        fc = f - f.mean(1, keepdim=True)
+        gram, n = fc @ fc.t(), f.shape[1]
+    elif kind == "zero":
+        gram, n = torch.zeros(32, 32, dtype=torch.float64), 100
+    else:
+        C, lo = {"syn128": (128, 2e-3), "syn24": (24, 4e-4), "syn32_illcond": (32, 1e-7), "plus_identity": (64, 1e-12)}[kind]
+        Q, _ = torch.linalg.qr(torch.randn(C, C, generator=g, dtype=torch.float64))
+        lam = torch.logspace(0, float(np.log10(lo)), C, dtype=torch.float64)
+        n = 1000
+        gram = (Q * lam) @ Q.t() * (n - 1)
+        add_identity = kind == "plus_identity"
+    scale = 1.0 / (n - 1)
+    S = gram * scale + (torch.eye(len(gram), dtype=torch.float64) if add_identity else 0)
+    W, info = ops.whiten_ns(gram.to(DEV), scale, add_identity=add_identity, return_info=True)
+    W, info = W.cpu(), info.cpu().tolist()
+    if kind == "zero":
+        assert info[0] == 0 and float(W.abs().max()) == 0.0
+        return
+    ref = _pinv_sqrt(S)
+    assert info[2] == 1 and info[1] < 40, info
+    tol = 1e-7 if kind == "syn32_illcond" else 1e-10
+    assert (W - ref).abs().max().item() <= tol * ref.abs().max().item(), (info, (W - ref).abs().max().item() / ref.abs().max().item())
+    assert (W - W.t()).abs().max().item() <= 1e-11 * ref.abs().max().item()
+
+
+@pytest.mark.pending_hw
+@pytest.mark.parametrize("case", ["full_rank", "wide", "dead_channels", "hw_lt_c"])
+def test_whiten_and_color_ns_solver_vs_reference_golden(golden_dir, case):
+    g = np.load(os.path.join(golden_dir, "golden_wct.npz"))
+    cF, sF = torch.from_numpy(g[case + ".cF"]), torch.from_numpy(g[case + ".sF"])
+    w = _wct16()
+    w.whiten_solver = "ns"
+    for numpy_flag, key in ((False, ".out_torch"), (True, ".out_numpy")):
+        w.args.numpy = numpy_flag
+        ref = torch.from_numpy(g[case + key])
+        got = w.whiten_and_color(cF, sF).cpu()
+        # the numpy model reproduces even the rank-deficient, unregularised case (3.7e-8); fp32 apply limits the GPU path
+        assert relerr(got, ref) <= 2e-6
+        assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+@pytest.mark.pending_hw
+def test_five_stage_ns_solver_equals_jacobi_solver(golden_dir):
+    g = np.load(os.path.join(golden_dir, "golden_16x.npz"))
+    content, style = torch.from_numpy(g["content"]).to(DEV), torch.from_numpy(g["style"]).to(DEV)
+    w = _wct16("fp32")
+    P.weights.load_npz_into(w, os.path.join(golden_dir, "weights_16x.npz"))
+    w = w.to(DEV)
+    a = w.stylize(content, style).clone()
+    w.whiten_solver = "ns"
+    b = w.stylize(content, style).clone()
+    P.set_precision("tf32")
+    ref = torch.from_numpy(g["a10.img1"]).to(DEV)
+    assert (a - b).abs().max().item() <= 1e-4
+    assert (b - ref).pow(2).mean().sqrt().item() <= 5e-5

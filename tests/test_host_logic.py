@@ -88,6 +88,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib2 = _lib.load()
     assert lib2.wctb_workspace_doubles(_lib.WS_EIGH, 128, 2) == 2 * 128 * 128 + 16
     assert lib2.wctb_workspace_doubles(_lib.WS_WCT_MATRIX, 64, 1) == 3 * 64 * 64 + 8
+    assert lib2.wctb_workspace_doubles(_lib.WS_WHITEN_NS, 128, 1) == 8 * 128 * 128 + 8
     assert lib2.wctb_workspace_doubles(7, 64, 1) == -1 and lib2.wctb_workspace_doubles(_lib.WS_EIGH, 0, 1) == -1
     assert _lib.load().wctb_abi_version() == 1
     assert _lib.load().wctb_error_string(-2) == b"unsupported configuration"
@@ -298,5 +299,10 @@ def test_wct_knobs_defaults_and_overrides(monkeypatch):
     w.num_eig = 30
     assert w._keep(128) == 30                                   # NumEigenValue wins
     assert w.max_graphs >= 1 and len(w._graphs) == 0
+    assert w.whiten_solver == "jacobi" and not w._use_ns(128)
+    w.whiten_solver = "ns"
+    assert not w._use_ns(128)                                   # truncation knobs need eigenvalues: stays on the eigensolver
+    w.num_eig = w.rat_eig = None
+    assert w._use_ns(128) and w._use_ns(24) and not w._use_ns(256)
     monkeypatch.setenv("WCTB_EIG_EARLY", "1e-3")
     assert P.WCT(SimpleNamespace(mode="16x", numpy=False))._early() == 1e-3
