@@ -306,3 +306,74 @@ def test_wct_knobs_defaults_and_overrides(monkeypatch):
     assert w._use_ns(128) and w._use_ns(24) and not w._use_ns(256)
     monkeypatch.setenv("WCTB_EIG_EARLY", "1e-3")
     assert P.WCT(SimpleNamespace(mode="16x", numpy=False))._early() == 1e-3
+
+
+@pytest.mark.parametrize("solver,numpy_flag,alpha", [("jacobi", False, 1.0), ("jacobi", True, 0.6), ("ns", False, 1.0), ("ns", True, 0.6)])
+def test_wct_params_plumbing_with_cpu_stand_ins(monkeypatch, solver, numpy_flag, alpha):
+    """WCT._wct_params (statistics -> solver -> matrix) with the libwctb calls replaced by torch-cpu stand-ins that
+    follow the documented contracts of include/wctb.h: checks the host-side composition (argument order, scales, +I on the
+    content side only, both solver branches) against the oracle's transform on CPU.  The kernels themselves are covered
+    by the GPU suite."""
+    from collaborative_distillation_b200 import ops, util_wct
+
+    def to_p4(x):                                   # [C,H,W] -> [C/4,H,W,4]
+        C, H, W = x.shape
+        return x.view(C // 4, 4, H, W).permute(0, 2, 3, 1).contiguous()
+
+    def flat(x_p4, region):
+        y0, y1, x0, x1 = region if region is not None else (0, x_p4.shape[1], 0, x_p4.shape[2])
+        return x_p4[:, y0:y1, x0:x1, :].permute(0, 3, 1, 2).reshape(x_p4.shape[0] * 4, -1).double()
+
+    def channel_sum(x, region=None):
+        return flat(x, region).sum(1)
+
+    def centered_gram(x, mean, region=None, out=None, fast=False):
+        xc = flat(x, region) - mean[:, None]
+        out += xc @ xc.t()
+        return out
+
+    def eigh(a, scale, add_identity=False, return_sweeps=False, early_stop=None):
+        assert early_stop is not None
+        ev, evec = [], []
+        for p in range(a.shape[0]):
+            S = a[p] * float(scale[p]) + (torch.eye(a.shape[1], dtype=torch.float64) if add_identity else 0)
+            w, v = torch.linalg.eigh(S)
+            ev.append(w.clamp_min(0))
+            evec.append(v.t().contiguous())          # row k = eigenvector k (evecs[k*C + i])
+        return torch.stack(ev), torch.stack(evec)
+
+    def spectral(e, v, tau, power):
+        keep = e > tau * e.max()
+        return (v.t()[:, keep] * e[keep].pow(power)) @ v[keep]
+
+    def finish(W, Col, c_mean, s_mean, alpha):
+        C = len(c_mean)
+        M = alpha * Col @ W + (1 - alpha) * torch.eye(C, dtype=torch.float64)
+        return M.float(), (alpha * s_mean + (1 - alpha) * c_mean).float(), c_mean.float()
+
+    def wct_matrix(c_e, c_v, c_mean, s_e, s_v, s_mean, tau, alpha, keep_c=0, keep_s=0):
+        assert keep_c == 0 and keep_s == 0
+        return finish(spectral(c_e, c_v, tau, -0.5), spectral(s_e, s_v, tau, 0.5), c_mean, s_mean, alpha)
+
+    def whiten_ns(gram, scale, add_identity=False, return_info=False):
+        S = gram * scale + (torch.eye(len(gram), dtype=torch.float64) if add_identity else 0)
+        w, v = torch.linalg.eigh(S)
+        keep = w > 1e-10 * w.max()
+        return (v[:, keep] * w[keep].pow(-0.5)) @ v[:, keep].t()
+
+    def wct_matrix_w(W, c_mean, s_e, s_v, s_mean, tau, alpha):
+        return finish(W, spectral(s_e, s_v, tau, 0.5), c_mean, s_mean, alpha)
+
+    for name, fn in (("channel_sum", channel_sum), ("centered_gram", centered_gram), ("eigh_jacobi", eigh), ("wct_matrix", wct_matrix),
+                     ("whiten_ns", whiten_ns), ("wct_matrix_w", wct_matrix_w)):
+        monkeypatch.setattr(ops, name, fn)
+    g = torch.Generator().manual_seed(5)
+    C = 24
+    cF = torch.relu(torch.randn(C, C, generator=g) @ torch.randn(C, 20 * 30, generator=g) + 0.5).view(C, 20, 30)
+    sF = torch.relu(torch.randn(C, C, generator=g) @ torch.randn(C, 16 * 18, generator=g) * 2 + 1.0).view(C, 16, 18)
+    w = util_wct.WCT(SimpleNamespace(mode="16x", numpy=numpy_flag))
+    w.whiten_solver = solver
+    m, b, mc = w._wct_params(to_p4(cF), to_p4(sF), alpha)
+    got = (m.double() @ (cF.view(C, -1).double() - mc.double()[:, None]) + b.double()[:, None]).view(1, C, 20, 30)
+    ref = O.transform(cF, sF, alpha, numpy_variant=numpy_flag).double()
+    assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
