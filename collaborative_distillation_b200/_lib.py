@@ -114,6 +114,7 @@ IO_SIGNATURES = {
     "wctb_io_abi_version": [],
     "wctb_io_last_status": [],
     "wctb_io_create": [ctypes.POINTER(_p)],
+    "wctb_io_create_ex": [_i, ctypes.c_uint, ctypes.POINTER(_p)],
     "wctb_io_jpeg_info": [_p, _p, _sz, _pi, _pi, _pi, _pi],
     "wctb_io_jpeg_decode": [_p, _p, _sz, _p, _i, _i, _p],
     "wctb_io_jpeg_encode": [_p, _p, _i, _i, _i, _i, _p, _psz],

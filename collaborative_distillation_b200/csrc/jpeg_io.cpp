@@ -56,20 +56,36 @@ extern "C" void wctb_io_destroy(wctb_io_codec* c) {
   delete c;
 }
 
-static int create_impl(wctb_io_codec* c) {
-  NVJ_TRY(nvjpegCreateSimple(&c->handle));
+static int create_impl(wctb_io_codec* c, int backend, unsigned flags) {
+  nvjpegBackend_t be;
+  switch (backend) {
+    case WCTB_IO_BACKEND_DEFAULT: be = NVJPEG_BACKEND_DEFAULT; break;
+    case WCTB_IO_BACKEND_HYBRID: be = NVJPEG_BACKEND_HYBRID; break;
+    case WCTB_IO_BACKEND_GPU_HYBRID: be = NVJPEG_BACKEND_GPU_HYBRID; break;
+    default: return WCTB_IO_E_BADARG;
+  }
+  unsigned nvflags = NVJPEG_FLAGS_DEFAULT;
+  if (flags & WCTB_IO_FLAG_INTERP_UPSAMPLING) nvflags |= NVJPEG_FLAGS_UPSAMPLING_WITH_INTERPOLATION;
+  if (flags & ~(unsigned)WCTB_IO_FLAG_INTERP_UPSAMPLING) return WCTB_IO_E_BADARG;
+  if (backend == WCTB_IO_BACKEND_DEFAULT && nvflags == NVJPEG_FLAGS_DEFAULT) {
+    NVJ_TRY(nvjpegCreateSimple(&c->handle));        // the configuration that ran on hardware in round 1
+  } else {
+    NVJ_TRY(nvjpegCreateEx(be, nullptr, nullptr, nvflags, &c->handle));
+  }
   NVJ_TRY(nvjpegJpegStateCreate(c->handle, &c->dec_state));
   NVJ_TRY(nvjpegEncoderStateCreate(c->handle, &c->enc_state, nullptr));
   NVJ_TRY(nvjpegEncoderParamsCreate(c->handle, &c->enc_params, nullptr));
   return WCTB_IO_OK;
 }
 
-extern "C" int wctb_io_create(wctb_io_codec** out) {
+extern "C" int wctb_io_create(wctb_io_codec** out) { return wctb_io_create_ex(WCTB_IO_BACKEND_DEFAULT, 0u, out); }
+
+extern "C" int wctb_io_create_ex(int backend, unsigned flags, wctb_io_codec** out) {
   if (!out) return WCTB_IO_E_BADARG;
   *out = nullptr;
   wctb_io_codec* c = new (std::nothrow) wctb_io_codec();
   if (!c) return WCTB_IO_E_BADARG;
-  int rc = create_impl(c);
+  int rc = create_impl(c, backend, flags);
   if (rc != WCTB_IO_OK) {
     wctb_io_destroy(c);
     return rc;

@@ -131,10 +131,16 @@ SUBSAMPLING = {"444": 0, "4:4:4": 0, "422": 1, "4:2:2": 1, "420": 2, "4:2:0": 2}
 class JpegCodec:
     """One nvJPEG handle + decoder / encoder state (include/wctb_io.h).  Not thread-safe: one per host thread."""
 
-    def __init__(self):
+    BACKENDS = {"default": 0, "hybrid": 1, "gpu_hybrid": 2}
+
+    def __init__(self, backend: str = "default", interp_upsampling: bool = False):
+        """backend / interp_upsampling other than the defaults go through wctb_io_create_ex (not yet run on hardware)."""
         self._lib = _lib.load_io()
         h = ctypes.c_void_p()
-        check_io(self._lib.wctb_io_create(ctypes.byref(h)), "io_create")
+        if backend == "default" and not interp_upsampling:
+            check_io(self._lib.wctb_io_create(ctypes.byref(h)), "io_create")
+        else:
+            check_io(self._lib.wctb_io_create_ex(self.BACKENDS[backend], 1 if interp_upsampling else 0, ctypes.byref(h)), "io_create_ex")
         self._h = h
 
     def close(self):

@@ -139,3 +139,19 @@ def test_load_and_save_image_mirror_the_reference_loader(tmp_path):
     image_io.save_image(got, out_jpg)
     back = np.asarray(Image.open(out_jpg).convert("RGB")).astype(np.float64)
     assert back.shape == (300, 420, 3) and np.abs(back - img).mean() <= 4.0
+
+
+@pytest.mark.pending_hw
+@pytest.mark.parametrize("backend,interp", [("gpu_hybrid", False), ("hybrid", False), ("default", True)])
+def test_jpeg_decode_other_backends(backend, interp):
+    """wctb_io_create_ex: GPU-assisted Huffman backend / interpolated chroma upsampling decode the same picture"""
+    from PIL import Image
+    img = _smooth(360, 500)
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, format="JPEG", quality=90, subsampling=2)
+    ref = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")).astype(np.int32)
+    codec = image_io.JpegCodec(backend=backend, interp_upsampling=interp)
+    got = codec.decode(buf.getvalue()).cpu().numpy().astype(np.int32)
+    d = np.abs(got - ref)
+    assert d.mean() <= 1.5, (backend, interp, d.max(), d.mean())
+    codec.close()

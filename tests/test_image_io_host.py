@@ -118,7 +118,7 @@ def test_io_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "wctb_io.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(wctb_io_[a-z0-9_]+)\s*\(", hdr))
-    assert len(declared) == 9
+    assert len(declared) == 10
     lib = ctypes.CDLL(_lib.IO_LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), "libwctb_io.so does not export %s" % name
@@ -127,6 +127,7 @@ def test_io_library_exports_every_declared_symbol():
     assert io.wctb_io_abi_version() == 1
     assert io.wctb_io_error_string(-2) == b"JPEG variant not supported by the GPU decoder"
     assert io.wctb_io_jpeg_info(None, None, 0, None, None, None, None) == -1
+    assert io.wctb_io_create_ex(0, 0, None) == -1
 
 
 def test_device_loader_pairs_like_the_reference_dataset(tmp_path):
