@@ -8,6 +8,8 @@ One "step" = one full pass of the hot path over one synthetic content/style pair
 encoder(style), encoder(content), whiten-and-colour transform, decoder (WCT.py:120-125).
   value : content megapixels / second with inputs already resident in HBM (CUDA events, max over ranks)
   e2e   : the same through the public API from pinned HOST buffers, H2D + D2H inside the timed region
+  e2e_u8 : (extra key, N=1) the same step fed with 8-bit interleaved RGB host buffers through the image-I/O row
+           (ToTensor / save_image quantisation on the device): what `WCT.py --gpu_io` moves over PCIe
   roofline : the dominant kernel (by time) measured live with CUDA events on the launch stream
   cpu_baseline : the CPU oracle (port of the reference path, torch-cpu fp32 convs + fp64 transform) on a bounded sample
 Default workload (N=1): BASELINE.json configs[2] = 3840x2160 content / 2000x2000 style, --mode 16x --UHD
@@ -318,6 +320,32 @@ def main():
         cpu_base = {"value": round(mps, 4), "unit": "MP/s", "cores": threads, "host_cpus": usable_cpus(), "kind": "port",
                     "sample": "%dx%d content / %dx%d style (BASELINE configs[1]), 16x, 5 stages, 1 warm-up + 2 timed passes of the CPU oracle" % (bw, bh, sw_, sh_)}
 
+    # ---- extra (not part of the contract keys): the same end-to-end step through the image-I/O row -- 8-bit interleaved
+    # RGB pinned host buffers up, ToTensor on the device, stylize, save_image quantisation on the device, 8-bit image down
+    # (what WCT.py --gpu_io moves; 4x fewer PCIe bytes than the fp32 tensors of the reference-facing API).  Measured last
+    # and guarded: a failure here can only lose this key.
+    e2e_u8 = None
+    if N == 1:
+        try:
+            from collaborative_distillation_b200 import image_io
+            cu8 = (content_h[0].permute(1, 2, 0) * 255).round().to(torch.uint8).contiguous().pin_memory()
+            su8 = (style_h[0].permute(1, 2, 0) * 255).round().to(torch.uint8).contiguous().pin_memory()
+            out_u8 = torch.empty((Hc >> 4) << 4, (Wc >> 4) << 4, 3, dtype=torch.uint8).pin_memory()
+
+            def u8_step():
+                c = image_io.to_tensor(cu8.to(dev, non_blocking=True))
+                s_ = image_io.to_tensor(su8.to(dev, non_blocking=True))
+                q = image_io.quantize(step(c, s_))
+                out_u8[:q.shape[0], :q.shape[1]].copy_(q, non_blocking=True)
+            for _ in range(2):
+                u8_step()
+            u8_ms = timed(u8_step, args.steps) / args.steps
+            e2e_u8 = {"value": round(mp / (u8_ms / 1e3), 2), "unit": "MP/s", "ms_per_step": round(u8_ms, 3),
+                      "h2d_bytes_per_step": cu8.numel() + su8.numel(), "d2h_bytes_per_step": out_u8.numel(),
+                      "note": "uint8 HWC host buffers through collaborative_distillation_b200.image_io (to_tensor / quantize on the device)"}
+        except Exception as ex:  # noqa: BLE001
+            e2e_u8 = {"error": repr(ex)[:200]}
+
     if rank == 0:
         flops = algorithmic_conv_flops("16x", Hc, Wc, Hs, Ws)
         line = {
@@ -339,6 +367,8 @@ def main():
             line["roofline"] = roof
         if cpu_base:
             line["cpu_baseline"] = cpu_base
+        if e2e_u8:
+            line["e2e_u8"] = e2e_u8
         print(json.dumps(line))
     if N > 1:
         dist.destroy_process_group()
