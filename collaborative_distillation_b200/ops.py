@@ -260,7 +260,7 @@ def set_first_variant(v: int):
 
 def set_gram_variant(v: int):
     """debug: fast Gram for C = 24 / 32: 0 = register accumulation fed from a cp.async ring (default), 2 = fed through L1,
-    1 = staged shared-memory kernel everywhere"""
+    1 = staged shared-memory kernel everywhere, 3 / 4 = later ring variants that have not run on hardware yet (wctb.h)"""
     check(_lib.load().wctb_debug_set_gram_variant(int(v)), "debug_set_gram_variant")
 
 

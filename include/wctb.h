@@ -248,7 +248,8 @@ int wctb_debug_set_eigh_variant(int variant);
 /* debug: which kernel wctb_centered_gram_fast uses for C = 24 / 32 (A/B timing, tools/gram_ab.py):
  * 0 (default) = register-resident accumulation (a thread owns whole pixels) fed from a cp.async shared-memory ring;
  * 2 = the same accumulation fed by direct global loads through L1; 1 = the staged shared-memory tile kernel everywhere;
- * 3 = variant 0 with the range-checked last iteration peeled out of the loop (not yet run on hardware).               */
+ * 3 = variant 0 with the range-checked last iteration peeled out of the loop; 4 = two pixels per thread and iteration,
+ * peeled (3 and 4 are not yet run on hardware).                                                                       */
 int wctb_debug_set_gram_variant(int variant);
 
 /* debug: 0 (default) = wctb_conv3x3_first computes two pixels per thread when W >= 64; 1 = one pixel per thread (A/B;

@@ -124,10 +124,13 @@ def test_moments_match_fp64(C, H, W, region):
 
 
 @pytest.mark.pending_hw
+@pytest.mark.parametrize("variant", [3, 4])
 @pytest.mark.parametrize("C,H,W,region", [(24, 31, 47, None), (24, 300, 310, None), (32, 257, 300, None), (24, 40, 50, (3, 37, 8, 50)),
-                                          (32, 33, 70, (0, 33, 5, 64)), (24, 3, 5, None), (32, 700, 900, (10, 690, 0, 900))])
-def test_gram_ring_peeled_variant(C, H, W, region):
-    """variant 3 (last iteration peeled out of the ring loop; written after the round's last GPU slot) == variant 0"""
+                                          (32, 33, 70, (0, 33, 5, 64)), (24, 3, 5, None), (32, 700, 900, (10, 690, 0, 900)),
+                                          (24, 13, 191, None), (24, 14, 193, None), (32, 2, 129, None)])
+def test_gram_ring_later_variants(C, H, W, region, variant):
+    """variants 3 (last iteration peeled out of the ring loop) and 4 (two pixels per thread and iteration + peeled), both
+    written after the round's last GPU slot, meet the contract of the fast Gram"""
     x = (torch.randn(C, H, W, generator=torch.Generator().manual_seed(5)) * 3 + 1.5).relu()
     p4 = ops.nchw_to_p4(x.to(DEV))
     y0, y1, x0, x1 = region or (0, H, 0, W)
@@ -135,7 +138,7 @@ def test_gram_ring_peeled_variant(C, H, W, region):
     mean = xr.mean(1)
     xc = xr - mean[:, None]
     ref = xc @ xc.t()
-    ops.set_gram_variant(3)
+    ops.set_gram_variant(variant)
     try:
         g3 = ops.centered_gram(p4, mean.to(DEV), region, fast=True).cpu()
     finally:
