@@ -26,7 +26,7 @@ for (C, H, W) in [(24, 2160, 3840), (32, 1080, 1920), (24, 2000, 2000), (24, 409
     x = torch.rand(C // 4, H, W, 4, device="cuda") * 3
     mean = (ops.channel_sum(x) / (H * W))
     res = {}
-    variants = ((1, "staged"), (2, "regs/L1"), (0, "regs/cp.async ring")) + (((3, "ring, peeled"),) if "--peeled" in sys.argv else ())
+    variants = ((1, "staged"), (2, "regs/L1"), (0, "regs/cp.async ring")) + (((3, "ring, peeled"), (4, "ring, 2 px/thread")) if "--peeled" in sys.argv else ())
     for variant, _ in variants:
         ops.set_gram_variant(variant)
         ts = []
