@@ -6,6 +6,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "gram_small.cuh"
 namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------
@@ -202,554 +203,7 @@ extern "C" int wctb_centered_gram(const float* x, int C, int H, int W, int y0, i
   return launch_gram<4, 16, double>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
 }
 
-// ------------------------------------------------------------------------------------------
-// Register-resident fp32 Gram for the small-channel, many-pixel stages (C = 24: stage 1, C = 32: stage 2).
-// The staged kernel above is shared-memory bound there (6 LDS.32 per 9 FFMA: CUDA events put it at ~5x its FFMA and
-// HBM floors).  Here a thread owns whole PIXELS: it loads the chunks (float4 = 4 channels) of its pixel straight from
-// global memory (a warp reads 512 contiguous bytes per chunk plane), centres them with a split (hi, lo) fp32 mean and
-// accumulates 4x4 outer-product blocks of the upper block triangle in registers.  The NCH(NCH+1)/2 blocks are dealt in
-// contiguous runs to SPLIT warp groups ("parts") of the CTA; a part only loads the chunks its blocks touch, all parts
-// walk the same pixels (re-reads hit L1; a barrier every 4th iteration keeps the parts inside the L1 window), and each
-// part prefetches its lines two iterations ahead.  No shared-memory traffic in the loop.  Register budget: 12 warps/SM
-// (3 per scheduler) -> <= 168 registers: <= 96 accumulators + <= 32 operands.
-// Flush: warp-shuffle reduction in fp64, then fp64 atomics (same accumulate-into-G contract as the staged kernel).
-// Accuracy: per-thread fp32 sums over npix/(gridDim*PIX) pixels (hundreds..2e3) -> ~1e-6 each, averaging over the
-// >= 1e4 threads to ~1e-8 relative in G; the contract of the fast variant is 1e-6 (tests/test_gpu_parity.py).
-// ------------------------------------------------------------------------------------------
-template <int NCH, int SPLIT>
-struct GramDeal {
-  static constexpr int NPAIR = NCH * (NCH + 1) / 2;
-  static constexpr int BASE = NPAIR / SPLIT, REM = NPAIR % SPLIT;
-  __host__ __device__ static constexpr int begin(int part) { return part * BASE + (part < REM ? part : REM); }
-  __host__ __device__ static constexpr int count(int part) { return BASE + (part < REM ? 1 : 0); }
-  static constexpr int MAXCOUNT = BASE + (REM ? 1 : 0);
-  __host__ __device__ static constexpr bool owns(int part, int q) { return q >= begin(part) && q < begin(part) + count(part); }
-  __host__ __device__ static constexpr bool uses_chunk(int part, int c) {
-    int q = 0;
-    for (int i = 0; i < NCH; ++i)
-      for (int j = i; j < NCH; ++j, ++q)
-        if (owns(part, q) && (i == c || j == c)) return true;
-    return false;
-  }
-};
-
-// one pixel per thread: load the chunks this part touches, centre, accumulate its blocks.  CHECK = last iteration (slots
-// beyond npix contribute zero); FULLROW = the region spans whole rows, so pixel p of the region is pixel y0*W + p of the plane.
-template <int NCH, int SPLIT, int PART, bool FULLROW, bool CHECK>
-__device__ __forceinline__ void gram_regs_step(float (&acc)[GramDeal<NCH, SPLIT>::MAXCOUNT][16], const float4* __restrict__ x,
-                                               long long HW, int W, int y0, int x0, unsigned wreg, unsigned npix, unsigned p,
-                                               const float4* __restrict__ s_mh) {
-  using D = GramDeal<NCH, SPLIT>;
-  float4 cur[NCH];
-  const bool have = !CHECK || p < npix;
-  long long off;
-  if (FULLROW) {
-    off = (long long)y0 * W + p;
-  } else {
-    const unsigned pp = have ? p : 0u;
-    const unsigned r = pp / wreg, cc = pp - r * wreg;
-    off = (long long)(y0 + r) * W + (x0 + cc);
-  }
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    cur[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (D::uses_chunk(PART, c) && have) {
-      const float4 v = __ldg(x + (long long)c * HW + off);
-      const float4 mh = s_mh[c];
-      // fp32 mean: its rounding error d (<= 2^-24 |mean|) only adds N d_i d_j to G, ~1e-14 relative
-      cur[c] = make_float4(v.x - mh.x, v.y - mh.y, v.z - mh.z, v.w - mh.w);
-    }
-  }
-  int q = 0;
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-    for (int j = i; j < NCH; ++j) {
-      if (D::owns(PART, q)) {
-        const int slot = q - D::begin(PART);
-        const float a[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
-        const float b[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[slot][u * 4 + v] = fmaf(a[u], b[v], acc[slot][u * 4 + v]);
-      }
-      ++q;
-    }
-  }
-}
-
-template <int NCH, int SPLIT, int PART, int PIX, bool FULLROW>
-__device__ __forceinline__ void gram_regs_body(const float4* __restrict__ x, long long HW, int W, int y0, int x0, unsigned wreg,
-                                               unsigned npix, unsigned iters, const float4* __restrict__ s_mh,
-                                               double* __restrict__ G) {
-  using D = GramDeal<NCH, SPLIT>;
-  constexpr int C = NCH * 4;
-  constexpr int NP = D::MAXCOUNT;
-  float acc[NP][16];
-#pragma unroll
-  for (int s = 0; s < NP; ++s)
-#pragma unroll
-    for (int e = 0; e < 16; ++e) acc[s][e] = 0.f;
-  const unsigned stride = gridDim.x * PIX;
-  const unsigned pbase = blockIdx.x * PIX + (threadIdx.x % PIX);
-  // iterations 0 .. iters-2 are in range for every thread (see launch_gram_regs); only the last one needs the range check.
-  // Uniform trip count: the barrier is reached by every thread of the CTA.
-  for (unsigned it = 0; it + 1 < iters; ++it) {
-    const unsigned p = pbase + it * stride;          // no 32-bit overflow: the host checks npix < 2^31 - 2^24
-    {   // prefetch two iterations ahead
-      const unsigned pf = p + 2 * stride;
-      if (pf < npix) {
-        long long off;
-        if (FULLROW) {
-          off = (long long)y0 * W + pf;
-        } else {
-          const unsigned r = pf / wreg, cc = pf - r * wreg;
-          off = (long long)(y0 + r) * W + (x0 + cc);
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-          if (D::uses_chunk(PART, c)) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + (long long)c * HW + off));
-      }
-    }
-    gram_regs_step<NCH, SPLIT, PART, FULLROW, false>(acc, x, HW, W, y0, x0, wreg, npix, p, s_mh);
-    // named barrier over the whole CTA: the parts sit in different branches of the dispatch (warp-uniform), so this is
-    // written as bar.sync <id>, <count> rather than __syncthreads()
-    if ((it & 3) == 3) asm volatile("bar.sync 1, %0;" ::"r"(PIX * SPLIT) : "memory");
-  }
-  gram_regs_step<NCH, SPLIT, PART, FULLROW, true>(acc, x, HW, W, y0, x0, wreg, npix, pbase + (iters - 1) * stride, s_mh);
-  // flush
-  const int lane = threadIdx.x & 31;
-  {
-    int q = 0;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-      for (int j = i; j < NCH; ++j) {
-        if (D::owns(PART, q)) {
-          const int slot = q - D::begin(PART);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              double sum = (double)acc[slot][u * 4 + v];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-              if (lane == 0) {
-                atomicAdd(G + (long long)(i * 4 + u) * C + (j * 4 + v), sum);
-                if (i != j) atomicAdd(G + (long long)(j * 4 + v) * C + (i * 4 + u), sum);
-              }
-            }
-        }
-        ++q;
-      }
-    }
-  }
-}
-
-template <int NCH, int SPLIT, int PART, int PIX, bool FULLROW>
-__device__ __forceinline__ void gram_regs_dispatch(int part, const float4* __restrict__ x, long long HW, int W, int y0, int x0,
-                                                   unsigned wreg, unsigned npix, unsigned iters, const float4* s_mh,
-                                                   double* __restrict__ G) {
-  if (part == PART) {
-    gram_regs_body<NCH, SPLIT, PART, PIX, FULLROW>(x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
-  } else if constexpr (PART + 1 < SPLIT) {
-    gram_regs_dispatch<NCH, SPLIT, PART + 1, PIX, FULLROW>(part, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
-  }
-}
-
-template <int NCH, int SPLIT, int PIX, bool FULLROW>
-__global__ void __launch_bounds__(PIX* SPLIT, 1) gram_regs_kernel(const float4* __restrict__ x, int H, int W, int y0, int x0,
-                                                                   unsigned wreg, unsigned npix, unsigned iters,
-                                                                   const double* __restrict__ mean, double* __restrict__ G) {
-  static_assert(PIX % 32 == 0, "a warp must not straddle two parts");
-  __shared__ float4 s_mh[NCH];
-  if (threadIdx.x < NCH * 4) reinterpret_cast<float*>(s_mh)[threadIdx.x] = (float)mean[threadIdx.x];
-  __syncthreads();
-  // every part runs the same number of barriers (iters is uniform), so the divergent dispatch is barrier-safe
-  gram_regs_dispatch<NCH, SPLIT, 0, PIX, FULLROW>(threadIdx.x / PIX, x, (long long)H * W, W, y0, x0, wreg, npix, iters, s_mh, G);
-}
-
-template <int NCH, int SPLIT, int PIX>
-static int launch_gram_regs(const float* x, int H, int W, int y0, int y1, int x0, int x1, const double* mean, double* gram_out,
-                            cudaStream_t st) {
-  const long long npix = (long long)(y1 - y0) * (x1 - x0);
-  long long ctas = (npix + PIX - 1) / PIX;
-  const long long cap = wctb_num_sms();          // one CTA per SM (register-limited), persistent over its pixels
-  if (ctas > cap) ctas = cap;
-  // iters = ceil(npix / stride), stride = ctas*PIX  =>  (iters-1)*stride < npix, so slot pbase + it*stride (pbase < stride)
-  // is in range for every thread while it <= iters-2; only the last iteration is range-checked in the kernel.
-  const long long stride = ctas * PIX;
-  const unsigned iters = (unsigned)((npix + stride - 1) / stride);
-  const unsigned wreg = (unsigned)(x1 - x0);
-  if (x0 == 0 && x1 == W)
-    gram_regs_kernel<NCH, SPLIT, PIX, true><<<(unsigned)ctas, PIX * SPLIT, 0, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                    (unsigned)npix, iters, mean, gram_out);
-  else
-    gram_regs_kernel<NCH, SPLIT, PIX, false><<<(unsigned)ctas, PIX * SPLIT, 0, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                     (unsigned)npix, iters, mean, gram_out);
-  WCTB_RETURN_LAUNCH();
-}
-
-// ------------------------------------------------------------------------------------------
-// Same register-resident accumulation, fed from a cp.async ring in shared memory (variant 0, default).
-// gram_regs_kernel re-reads every pixel once per warp group through L1 and consumes each load immediately, which leaves
-// it latency-bound at a third of the HBM rate.  Here the CTA copies each pixel tile ([NCH][PIX] float4) exactly once
-// with cp.async.cg (16 B per thread and copy, coalesced) into a RING-deep ring; all groups read their pixel's chunks from
-// it with conflict-free LDS.128 (lane j <-> pixel j).  One barrier per iteration: wait for tile `it`, barrier, refill the
-// slot that was computed in iteration it-1, compute tile `it`.  RING-1 tiles (~45 KB) are in flight per SM.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// copy pixel tile `t` (pixels blockIdx.x*PIX + t*stride + [0,PIX)) into ring slot t % RING; pixels beyond npix are skipped
-// (their slots are never used: the compute step range-checks the last tile).  Executed by all PIX*SPLIT threads.
-template <int NCH, int SPLIT, int PIX, bool FULLROW>
-__device__ __forceinline__ void gram_ring_issue(float4* __restrict__ ring_slot, const float4* __restrict__ x, long long HW,
-                                                int W, int y0, int x0, unsigned wreg, unsigned npix, unsigned tile_base) {
-  constexpr int NT = PIX * SPLIT;
-#pragma unroll
-  for (int e0 = 0; e0 < NCH * PIX; e0 += NT) {
-    const int e = e0 + (int)threadIdx.x;
-    if (e < NCH * PIX) {
-      const int c = e / PIX, j = e - c * PIX;
-      const unsigned p = tile_base + j;
-      if (p < npix) {
-        long long off;
-        if (FULLROW) {
-          off = (long long)y0 * W + p;
-        } else {
-          const unsigned r = p / wreg, cc = p - r * wreg;
-          off = (long long)(y0 + r) * W + (x0 + cc);
-        }
-        cp_async16(ring_slot + e, x + (long long)c * HW + off);
-      }
-    }
-  }
-}
-
-template <int NCH, int SPLIT, int PART, int PIX, bool CHECK>
-__device__ __forceinline__ void gram_ring_step(float (&acc)[GramDeal<NCH, SPLIT>::MAXCOUNT][16], const float4* __restrict__ tile,
-                                               int j, bool have, const float4* __restrict__ s_mh) {
-  using D = GramDeal<NCH, SPLIT>;
-  float4 cur[NCH];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    cur[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (D::uses_chunk(PART, c) && (!CHECK || have)) {
-      const float4 v = tile[c * PIX + j];
-      const float4 mh = s_mh[c];
-      cur[c] = make_float4(v.x - mh.x, v.y - mh.y, v.z - mh.z, v.w - mh.w);
-    }
-  }
-  int q = 0;
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-    for (int jj = i; jj < NCH; ++jj) {
-      if (D::owns(PART, q)) {
-        const int slot = q - D::begin(PART);
-        const float a[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
-        const float b[4] = {cur[jj].x, cur[jj].y, cur[jj].z, cur[jj].w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[slot][u * 4 + v] = fmaf(a[u], b[v], acc[slot][u * 4 + v]);
-      }
-      ++q;
-    }
-  }
-}
-
-template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW, bool PEEL>
-__device__ __forceinline__ void gram_ring_body(float4* __restrict__ ring, const float4* __restrict__ x, long long HW, int W, int y0,
-                                               int x0, unsigned wreg, unsigned npix, unsigned iters,
-                                               const float4* __restrict__ s_mh, double* __restrict__ G) {
-  using D = GramDeal<NCH, SPLIT>;
-  constexpr int C = NCH * 4;
-  constexpr int NP = D::MAXCOUNT;
-  constexpr int TILE = NCH * PIX;   // float4 per ring slot
-  float acc[NP][16];
-#pragma unroll
-  for (int s = 0; s < NP; ++s)
-#pragma unroll
-    for (int e = 0; e < 16; ++e) acc[s][e] = 0.f;
-  const unsigned stride = gridDim.x * PIX;
-  const unsigned cta_base = blockIdx.x * PIX;
-  const int j = threadIdx.x % PIX;
-  // prologue: tiles 0 .. RING-2 (one commit group per tile, empty groups keep the count uniform)
-#pragma unroll
-  for (int t = 0; t < RING - 1; ++t) {
-    if ((unsigned)t < iters) gram_ring_issue<NCH, SPLIT, PIX, FULLROW>(ring + t * TILE, x, HW, W, y0, x0, wreg, npix, cta_base + t * stride);
-    cp_async_commit();
-  }
-  // PEEL (variant 3, not yet the default): the range-checked last tile is handled after the loop, which halves the loop's
-  // code (ncu: 0.59 warps stalled on instruction fetch per issue in the unpeeled loop, profiles/r01_gram_ring_ncu_full.txt)
-  const unsigned loop_iters = PEEL ? iters - 1 : iters;
-  for (unsigned it = 0; it < loop_iters; ++it) {
-    cp_async_wait<RING - 2>();       // this thread's copies of tile `it` have landed
-    // CTA-wide named barrier (the groups sit in different branches of the dispatch): everybody's copies of tile `it` are
-    // visible, and everybody has finished computing tile it-1, whose slot is refilled next
-    asm volatile("bar.sync 1, %0;" ::"r"(PIX * SPLIT) : "memory");
-    const unsigned tn = it + (RING - 1);
-    if (tn < iters) gram_ring_issue<NCH, SPLIT, PIX, FULLROW>(ring + (tn % RING) * TILE, x, HW, W, y0, x0, wreg, npix, cta_base + tn * stride);
-    cp_async_commit();
-    const float4* tile = ring + (it % RING) * TILE;
-    if (PEEL || it + 1 < iters) {
-      gram_ring_step<NCH, SPLIT, PART, PIX, false>(acc, tile, j, true, s_mh);
-    } else {
-      gram_ring_step<NCH, SPLIT, PART, PIX, true>(acc, tile, j, cta_base + it * stride + j < npix, s_mh);
-    }
-  }
-  if (PEEL) {
-    const unsigned it = iters - 1;
-    cp_async_wait<0>();
-    asm volatile("bar.sync 1, %0;" ::"r"(PIX * SPLIT) : "memory");
-    gram_ring_step<NCH, SPLIT, PART, PIX, true>(acc, ring + (it % RING) * TILE, j, cta_base + it * stride + j < npix, s_mh);
-  }
-  cp_async_wait<0>();
-  // flush
-  const int lane = threadIdx.x & 31;
-  {
-    int q = 0;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-      for (int jj = i; jj < NCH; ++jj) {
-        if (D::owns(PART, q)) {
-          const int slot = q - D::begin(PART);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              double sum = (double)acc[slot][u * 4 + v];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-              if (lane == 0) {
-                atomicAdd(G + (long long)(i * 4 + u) * C + (jj * 4 + v), sum);
-                if (i != jj) atomicAdd(G + (long long)(jj * 4 + v) * C + (i * 4 + u), sum);
-              }
-            }
-        }
-        ++q;
-      }
-    }
-  }
-}
-
-template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW, bool PEEL>
-__device__ __forceinline__ void gram_ring_dispatch(int part, float4* __restrict__ ring, const float4* __restrict__ x, long long HW,
-                                                   int W, int y0, int x0, unsigned wreg, unsigned npix, unsigned iters,
-                                                   const float4* s_mh, double* __restrict__ G) {
-  if (part == PART) {
-    gram_ring_body<NCH, SPLIT, PART, PIX, RING, FULLROW, PEEL>(ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
-  } else if constexpr (PART + 1 < SPLIT) {
-    gram_ring_dispatch<NCH, SPLIT, PART + 1, PIX, RING, FULLROW, PEEL>(part, ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
-  }
-}
-
-template <int NCH, int SPLIT, int PIX, int RING, bool FULLROW, bool PEEL>
-__global__ void __launch_bounds__(PIX* SPLIT, 1) gram_ring_kernel(const float4* __restrict__ x, int H, int W, int y0, int x0,
-                                                                   unsigned wreg, unsigned npix, unsigned iters,
-                                                                   const double* __restrict__ mean, double* __restrict__ G) {
-  static_assert(PIX % 32 == 0, "a warp must not straddle two groups");
-  static_assert(RING >= 3, "ring too shallow");
-  extern __shared__ __align__(16) unsigned char ring_raw[];
-  float4* ring = reinterpret_cast<float4*>(ring_raw);   // [RING][NCH][PIX]
-  __shared__ float4 s_mh[NCH];
-  if (threadIdx.x < NCH * 4) reinterpret_cast<float*>(s_mh)[threadIdx.x] = (float)mean[threadIdx.x];
-  __syncthreads();
-  gram_ring_dispatch<NCH, SPLIT, 0, PIX, RING, FULLROW, PEEL>(threadIdx.x / PIX, ring, x, (long long)H * W, W, y0, x0, wreg, npix, iters,
-                                                        s_mh, G);
-}
-
-template <int NCH, int SPLIT, int PIX, int RING, bool PEEL>
-static int launch_gram_ring(const float* x, int H, int W, int y0, int y1, int x0, int x1, const double* mean, double* gram_out,
-                            cudaStream_t st) {
-  const long long npix = (long long)(y1 - y0) * (x1 - x0);
-  long long ctas = (npix + PIX - 1) / PIX;
-  const long long cap = wctb_num_sms();          // one persistent CTA per SM (register-limited)
-  if (ctas > cap) ctas = cap;
-  const long long stride = ctas * PIX;
-  const unsigned iters = (unsigned)((npix + stride - 1) / stride);   // (iters-1)*stride < npix: only the last tile is partial
-  const unsigned wreg = (unsigned)(x1 - x0);
-  const size_t smem = (size_t)RING * NCH * PIX * sizeof(float4);
-  static bool attr_done = false;
-  if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, true, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, false, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
-  if (x0 == 0 && x1 == W)
-    gram_ring_kernel<NCH, SPLIT, PIX, RING, true, PEEL><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                                   (unsigned)npix, iters, mean, gram_out);
-  else
-    gram_ring_kernel<NCH, SPLIT, PIX, RING, false, PEEL><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                                    (unsigned)npix, iters, mean, gram_out);
-  WCTB_RETURN_LAUNCH();
-}
-
-// ------------------------------------------------------------------------------------------
-// Variant 4 (written after the round's last GPU slot: not yet run on hardware).  Same ring-fed register accumulation with
-// TWO pixels per thread and iteration (pixels j and j + PIX of a 2*PIX-pixel tile, processed one after the other so the
-// register budget is unchanged) and the range-checked last tile peeled out of the loop: half the barriers, copy-issue
-// and loop overhead per pixel, and a loop body without the inlined checked copy -- the three stall sources ncu shows for
-// variant 0 (profiles/r01_gram_ring_ncu_full.txt).  Kept as a separate copy so that the validated kernels stay
-// byte-identical.
-// ------------------------------------------------------------------------------------------
-template <int NCH, int SPLIT, int PIX, bool FULLROW>
-__device__ __forceinline__ void gram_ring2_issue(float4* __restrict__ ring_slot, const float4* __restrict__ x, long long HW,
-                                                 int W, int y0, int x0, unsigned wreg, unsigned npix, unsigned tile_base) {
-  constexpr int NT = PIX * SPLIT;
-  constexpr int TP = 2 * PIX;                       // pixels per tile
-#pragma unroll
-  for (int e0 = 0; e0 < NCH * TP; e0 += NT) {
-    const int e = e0 + (int)threadIdx.x;
-    if (e < NCH * TP) {
-      const int c = e / TP, jj = e - c * TP;
-      const unsigned p = tile_base + jj;
-      if (p < npix) {
-        long long off;
-        if (FULLROW) {
-          off = (long long)y0 * W + p;
-        } else {
-          const unsigned r = p / wreg, cc = p - r * wreg;
-          off = (long long)(y0 + r) * W + (x0 + cc);
-        }
-        cp_async16(ring_slot + e, x + (long long)c * HW + off);
-      }
-    }
-  }
-}
-
-template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW>
-__device__ __forceinline__ void gram_ring2_body(float4* __restrict__ ring, const float4* __restrict__ x, long long HW, int W, int y0,
-                                                int x0, unsigned wreg, unsigned npix, unsigned iters,
-                                                const float4* __restrict__ s_mh, double* __restrict__ G) {
-  using D = GramDeal<NCH, SPLIT>;
-  constexpr int C = NCH * 4;
-  constexpr int NP = D::MAXCOUNT;
-  constexpr int TP = 2 * PIX;
-  constexpr int TILE = NCH * TP;    // float4 per ring slot
-  float acc[NP][16];
-#pragma unroll
-  for (int s = 0; s < NP; ++s)
-#pragma unroll
-    for (int e = 0; e < 16; ++e) acc[s][e] = 0.f;
-  const unsigned stride = gridDim.x * TP;
-  const unsigned cta_base = blockIdx.x * TP;
-  const int j = threadIdx.x % PIX;
-#pragma unroll
-  for (int t = 0; t < RING - 1; ++t) {
-    if ((unsigned)t < iters) gram_ring2_issue<NCH, SPLIT, PIX, FULLROW>(ring + t * TILE, x, HW, W, y0, x0, wreg, npix, cta_base + t * stride);
-    cp_async_commit();
-  }
-  for (unsigned it = 0; it + 1 < iters; ++it) {      // full tiles: every pixel slot is in range (see launch_gram_ring2)
-    cp_async_wait<RING - 2>();
-    asm volatile("bar.sync 1, %0;" ::"r"(PIX * SPLIT) : "memory");
-    const unsigned tn = it + (RING - 1);
-    if (tn < iters) gram_ring2_issue<NCH, SPLIT, PIX, FULLROW>(ring + (tn % RING) * TILE, x, HW, W, y0, x0, wreg, npix, cta_base + tn * stride);
-    cp_async_commit();
-    const float4* tile = ring + (it % RING) * TILE;
-    // the step reads chunk c of pixel jpix at tile[c * PIXROW + jpix]; gram_ring_step uses PIX as the row length, so it is
-    // instantiated with the tile's row length TP and called once per pixel
-    gram_ring_step<NCH, SPLIT, PART, TP, false>(acc, tile, j, true, s_mh);
-    gram_ring_step<NCH, SPLIT, PART, TP, false>(acc, tile, j + PIX, true, s_mh);
-  }
-  {
-    const unsigned it = iters - 1;
-    cp_async_wait<0>();
-    asm volatile("bar.sync 1, %0;" ::"r"(PIX * SPLIT) : "memory");
-    const float4* tile = ring + (it % RING) * TILE;
-    const unsigned tb = cta_base + it * stride;
-    gram_ring_step<NCH, SPLIT, PART, TP, true>(acc, tile, j, tb + j < npix, s_mh);
-    gram_ring_step<NCH, SPLIT, PART, TP, true>(acc, tile, j + PIX, tb + j + PIX < npix, s_mh);
-  }
-  const int lane = threadIdx.x & 31;
-  {
-    int q = 0;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-      for (int jj = i; jj < NCH; ++jj) {
-        if (D::owns(PART, q)) {
-          const int slot = q - D::begin(PART);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              double sum = (double)acc[slot][u * 4 + v];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-              if (lane == 0) {
-                atomicAdd(G + (long long)(i * 4 + u) * C + (jj * 4 + v), sum);
-                if (i != jj) atomicAdd(G + (long long)(jj * 4 + v) * C + (i * 4 + u), sum);
-              }
-            }
-        }
-        ++q;
-      }
-    }
-  }
-}
-
-template <int NCH, int SPLIT, int PART, int PIX, int RING, bool FULLROW>
-__device__ __forceinline__ void gram_ring2_dispatch(int part, float4* __restrict__ ring, const float4* __restrict__ x, long long HW,
-                                                    int W, int y0, int x0, unsigned wreg, unsigned npix, unsigned iters,
-                                                    const float4* s_mh, double* __restrict__ G) {
-  if (part == PART) {
-    gram_ring2_body<NCH, SPLIT, PART, PIX, RING, FULLROW>(ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
-  } else if constexpr (PART + 1 < SPLIT) {
-    gram_ring2_dispatch<NCH, SPLIT, PART + 1, PIX, RING, FULLROW>(part, ring, x, HW, W, y0, x0, wreg, npix, iters, s_mh, G);
-  }
-}
-
-template <int NCH, int SPLIT, int PIX, int RING, bool FULLROW>
-__global__ void __launch_bounds__(PIX* SPLIT, 1) gram_ring2_kernel(const float4* __restrict__ x, int H, int W, int y0, int x0,
-                                                                    unsigned wreg, unsigned npix, unsigned iters,
-                                                                    const double* __restrict__ mean, double* __restrict__ G) {
-  static_assert(PIX % 32 == 0, "a warp must not straddle two groups");
-  static_assert(RING >= 3, "ring too shallow");
-  extern __shared__ __align__(16) unsigned char ring_raw[];
-  float4* ring = reinterpret_cast<float4*>(ring_raw);   // [RING][NCH][2*PIX]
-  __shared__ float4 s_mh[NCH];
-  if (threadIdx.x < NCH * 4) reinterpret_cast<float*>(s_mh)[threadIdx.x] = (float)mean[threadIdx.x];
-  __syncthreads();
-  gram_ring2_dispatch<NCH, SPLIT, 0, PIX, RING, FULLROW>(threadIdx.x / PIX, ring, x, (long long)H * W, W, y0, x0, wreg, npix, iters,
-                                                         s_mh, G);
-}
-
-template <int NCH, int SPLIT, int PIX, int RING>
-static int launch_gram_ring2(const float* x, int H, int W, int y0, int y1, int x0, int x1, const double* mean, double* gram_out,
-                             cudaStream_t st) {
-  const long long npix = (long long)(y1 - y0) * (x1 - x0);
-  constexpr int TP = 2 * PIX;
-  long long ctas = (npix + TP - 1) / TP;
-  const long long cap = wctb_num_sms();
-  if (ctas > cap) ctas = cap;
-  const long long stride = ctas * TP;
-  const unsigned iters = (unsigned)((npix + stride - 1) / stride);   // (iters-1)*stride < npix: only the last tile is partial
-  const unsigned wreg = (unsigned)(x1 - x0);
-  const size_t smem = (size_t)RING * NCH * TP * sizeof(float4);
-  static bool attr_done = false;
-  if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring2_kernel<NCH, SPLIT, PIX, RING, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring2_kernel<NCH, SPLIT, PIX, RING, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
-  if (x0 == 0 && x1 == W)
-    gram_ring2_kernel<NCH, SPLIT, PIX, RING, true><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                              (unsigned)npix, iters, mean, gram_out);
-  else
-    gram_ring2_kernel<NCH, SPLIT, PIX, RING, false><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,
-                                                                                               (unsigned)npix, iters, mean, gram_out);
-  WCTB_RETURN_LAUNCH();
-}
+// (the register-resident kernels for C = 24 / 32 live in gram_small.cuh, gram_ring.cu and gram_alt.cu)
 
 // 0: register accumulation fed from a cp.async ring for C = 24 / 32 (default); 2: register accumulation fed by direct
 // global loads through L1 (the first version); 1: staged shared-memory kernel everywhere; 3: variant 0 with the last
@@ -770,18 +224,11 @@ extern "C" int wctb_centered_gram_fast(const float* x, int C, int H, int W, int 
     return WCTB_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_gram_variant != 1 && (long long)(y1 - y0) * (x1 - x0) < (1LL << 31) - (1LL << 24)) {
-    if (g_gram_variant == 0) {
-      if (C == 24) return launch_gram_ring<6, 4, 96, 6, false>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-      if (C == 32) return launch_gram_ring<8, 6, 64, 6, false>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-    } else if (g_gram_variant == 3) {
-      if (C == 24) return launch_gram_ring<6, 4, 96, 6, true>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-      if (C == 32) return launch_gram_ring<8, 6, 64, 6, true>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-    } else if (g_gram_variant == 4) {
-      if (C == 24) return launch_gram_ring2<6, 4, 96, 4>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-      if (C == 32) return launch_gram_ring2<8, 6, 64, 4>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-    } else {
-      if (C == 24) return launch_gram_regs<6, 4, 96>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
-      if (C == 32) return launch_gram_regs<8, 6, 64>(x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+    if (C == 24 || C == 32) {
+      if (g_gram_variant == 0) return wctb_gram_ring_launch(C, 0, x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+      if (g_gram_variant == 3) return wctb_gram_ring_launch(C, 1, x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+      if (g_gram_variant == 4) return wctb_gram_ring2_launch(C, x, H, W, y0, y1, x0, x1, mean, gram_out, st);
+      return wctb_gram_regs_launch(C, x, H, W, y0, y1, x0, x1, mean, gram_out, st);
     }
   }
   if (C <= 16) return launch_gram<2, 8, float>(x, C, H, W, y0, y1, x0, x1, mean, gram_out, st);
