@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU tile-invariance check (run under torchrun on N GPUs):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py [--native-halo]
 The strip-sharded stylization must equal the single-GPU result (same kernels per pixel; statistics differ only by
 fp64 summation order)."""
 import os
@@ -35,8 +35,9 @@ def main():
         if rank == 0:
             wct.dist = None
             wct.fast_stats = False             # the sharded path always uses the fp64 Gram (partition independent)
+            wct.eig_early = 1e-4               # ... and the tight eigensolver early stop (WCT._early)
             ref = wct.stylize(content.to(dev), style.to(dev))
-        grp = parallel.StripGroup()
+        grp = parallel.StripGroup(native_halo="--native-halo" in sys.argv)   # libwctb halo pack/unpack instead of torch slicing
         wct.dist = grp
         own = grp.stylize(wct.style_transfer_stage, "16x",
                           grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev),
