@@ -29,6 +29,13 @@ SIGNATURES = {
     "wctb_conv3x3_first": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "wctb_conv3x3_p4": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "wctb_conv3x3_last": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "wctb_h2_supported": [_i, _i],
+    "wctb_pack_weights_h2": [_p, _p, _p, _i, _i, _p],
+    "wctb_conv3x3_h2": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "wctb_conv3x3_first_h2": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "wctb_nchw_to_h8": [_p, _p, _i, _i, _i, _p],
+    "wctb_h8_to_nchw": [_p, _p, _i, _i, _i, _p],
+    "wctb_p4_to_h8": [_p, _p, _i, _i, _i, _p],
     "wctb_conv_head_supported": [_i, _i],
     "wctb_conv_head_tc": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "wctb_conv_tail_supported": [_i, _i],
@@ -64,7 +71,7 @@ SIGNATURES = {
 
 WCTB_OK = 0
 EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3 = 0, 1, 2, 3
-ENGINE_FP32, ENGINE_TF32 = 0, 1
+ENGINE_FP32, ENGINE_TF32, ENGINE_H2 = 0, 1, 2
 WS_EIGH, WS_WCT_MATRIX, WS_WHITEN_NS = 0, 1, 2
 
 
@@ -95,6 +102,8 @@ def load():
     lib.wctb_error_string.restype = ctypes.c_char_p
     lib.wctb_workspace_doubles.argtypes = [_i, _i, _i]
     lib.wctb_workspace_doubles.restype = _ll
+    lib.wctb_h2_packed_halves.argtypes = [_i, _i]
+    lib.wctb_h2_packed_halves.restype = _ll
     if lib.wctb_abi_version() != 1:
         raise WctbError("libwctb ABI version mismatch")
     if os.environ.get("WCTB_GRAM_VARIANT"):          # A/B switch for tools / bench runs (see wctb.h, debug section)

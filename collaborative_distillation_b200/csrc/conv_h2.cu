@@ -1,0 +1,687 @@
+// libwctb: "h2" convolution engine -- fp32-accurate 3x3 convolutions on the 5th-gen tensor cores (sm_100a).
+//
+//   y = [pool2 | up2]( ReLU( conv3x3( reflect_pad1(x) ) + bias ) )
+//
+// Why.  Single-pass TF32 (10-bit mantissa operands) does not meet the precision contract of the path: chained through
+// the five whiten/colour stages its operand rounding is amplified to 2.1e-2 RMS on the images bench.py feeds
+// (tools/precision_probe.py).  Here every fp32 operand is carried as a PAIR of fp16 numbers, x = hi + lo with
+// hi = fp16(x), lo = fp16(x - hi) (22 significand bits), and a product is evaluated as hi*w_hi + lo*w_hi + hi*w_lo with
+// tcgen05.mma.kind::f16 into fp32 TMEM accumulators (the dropped lo*w_lo term is 2^-22 relative).  Weights are scaled
+// per layer by a power of two (device side, no host sync) so that w_lo stays in the fp16 normal range; the epilogue
+// multiplies by the inverse.  kind::f16 has K = 16 per instruction against K = 8 for kind::tf32 and the N <= 64 layers
+// are bound by the A-operand fetch (one 4 KB slab per MMA whatever N is), so the pair costs the same number of MMAs
+// as single-pass TF32 when the two weight halves are stacked along N:
+//      D[:, 0:N)  += A_hi * W_hi^T + A_lo * W_hi^T          D[:, N:2N) += A_hi * W_lo^T        (2 MMAs per tap / 16 ch)
+// and the HBM footprint of an activation is unchanged (2 + 2 bytes per element).
+//
+// Activation layout "H8": [C/8 chunks][2 (hi, lo)][H][W][8] fp16 -- one 16-byte unit = 8 consecutive channels of a
+// pixel, i.e. already the tcgen05 K-major / no-swizzle core-matrix row, so a rectangular halo tile copied into shared
+// memory IS the A operand and the nine filter taps are nine descriptor start addresses (linear-pitch trick, row pitch
+// 64 pixels, the two rightmost positions of a row are masked garbage).
+//
+// Kernel structure (persistent, one CTA per SM, 192 threads):
+//   warp 0   producer: per 16-channel K group ONE tensor-map TMA box (cp.async.bulk.tensor.4d, 4 planes x (TH+2) rows x
+//            64 px) + one bulk copy of the weight slab; tiles touching a true image border use per-row bulk copies with
+//            the reflection resolved in the source address instead (5 % of the tiles at UHD).
+//   warp 1   single-thread tcgen05.mma issuer; accumulators double-buffered in TMEM (2 x NB blocks of 128 px), so the
+//            MMAs of tile t+1 overlap the epilogue of tile t inside the CTA.
+//   warps 2-5 epilogue: tcgen05.ld -> (main + minor) * 1/s + bias -> ReLU -> [pool | up2] -> hi/lo split -> 16-byte
+//            stores (H8 for the next conv and/or fp32 P4 for the statistics kernels / public API).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "umma.cuh"
+
+namespace {
+using namespace wctb_umma;
+
+// ---------------------------------------------------------------------------------- geometry
+template <int N_, int NB_, int STACK_>
+struct H2Cfg {
+  static constexpr int N = N_, NB = NB_, STACK = STACK_;
+  static constexpr int NACC = 2;                                 // accumulator sets (double buffer)
+  static constexpr int TH = 2 * NB;                              // output rows per tile
+  static constexpr int ROWS = TH + 2;
+  static constexpr int PLANE_BYTES = ROWS * PW * 16;             // one 8-channel half-plane of the halo tile
+  static constexpr int IN_BYTES = 4 * PLANE_BYTES;               // hi0, lo0, hi1, lo1
+  static constexpr int W_BYTES = 9 * 2 * (2 * N) * 16;           // [tap][kchunk][hi N rows | lo N rows][8 halves]
+  static constexpr int STAGE_BYTES = IN_BYTES + W_BYTES;
+  static constexpr int COLS = STACK ? 2 * N : N;                 // TMEM columns per accumulator block
+  static constexpr int ACC_COLS = NB * COLS;
+  static constexpr int POOL_BYTES = 2 * 64 * 20 * 4;
+  static constexpr int AUX_BYTES = 1024;
+  static constexpr int NSTAGE_MAX = (227 * 1024 - POOL_BYTES - AUX_BYTES - 128) / STAGE_BYTES;
+  static constexpr int NSTAGE = NSTAGE_MAX > 4 ? 4 : NSTAGE_MAX;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + POOL_BYTES + AUX_BYTES + 128;
+  static_assert(NSTAGE >= 2, "pipeline needs two stages");
+  static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
+  static_assert(STAGE_BYTES % 128 == 0, "TMA destination alignment");
+  static_assert(COLS <= 256, "tcgen05.mma N <= 256");
+};
+
+struct H2Args {
+  const __half* x;        // H8 [C8in][2][H][W][8]
+  const __half* w;        // packed, see pack_w_h2_kernel
+  const float* bias;      // [Cout]
+  const float* wscale;    // device: [1] = 1 / (power-of-two weight scale)
+  __half* y_h8;           // H8 output (nullable)
+  float4* y_p4;           // fp32 P4 output (nullable); EPI_NCHW3: the [3][H][W] image
+  int H, W, Cin, Cout;
+  int tiles_x, tiles_y, ntiles;   // ntiles = nblks * tiles_y * tiles_x
+  int planes_in;                  // 2 * ceil(Cin / 8)
+};
+
+__device__ __forceinline__ uint32_t f2h_sat(float v) {   // fp32 -> fp16 bits, round-to-nearest-even, saturating
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return h;
+}
+__device__ __forceinline__ float h2f(uint32_t h) {
+  float f;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((uint16_t)h));
+  return f;
+}
+// x -> (hi, lo) fp16 pair; 8 values -> two 16-byte units
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = f2h_sat(v[i]);
+    l[i] = f2h_sat(v[i] - h2f(h[i]));
+  }
+  hi = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+  lo = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+}
+
+// ---------------------------------------------------------------------------------- MMA issue (one elected thread)
+// One pipeline stage = 16 input channels: planes [hi0, lo0, hi1, lo1] (K chunk stride = 2 planes) + weight slab.
+// taps outer / accumulator blocks inner, and the MMAs that accumulate into the same columns are issued in separate
+// passes over the blocks, so dependent tcgen05.mma are >= NB instructions apart (accumulate latency ~90 cycles).
+template <class C>
+__device__ __forceinline__ void h2_issue_stage(uint32_t a_base, uint32_t w_base, uint32_t tmem_acc, bool first,
+                                               int a_pitch = PW, uint32_t a_lbo = 2u * C::PLANE_BYTES,
+                                               uint32_t a_lo_off = C::PLANE_BYTES) {
+  constexpr int N = C::N;
+  constexpr uint32_t id_n = umma_idesc_f16(N), id_2n = umma_idesc_f16(2 * N);
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;
+    const uint32_t acc = (first && tap == 0) ? 0u : 1u;
+    const uint32_t wb = w_base + (uint32_t)tap * (2u * 2u * N * 16u);
+    const uint64_t bd = umma_desc(wb, 2u * N * 16u, 128u);                    // rows [0,2N): hi | lo
+    const uint32_t aoff = (uint32_t)(dy * a_pitch + dx) * 16u;
+    if (C::STACK) {
+#pragma unroll
+      for (int b = 0; b < C::NB; ++b)
+        umma_f16(tmem_acc + (uint32_t)(b * C::COLS), umma_desc(a_base + aoff + (uint32_t)b * 2048u, a_lbo, 128u), bd, id_2n, acc);
+#pragma unroll
+      for (int b = 0; b < C::NB; ++b)
+        umma_f16(tmem_acc + (uint32_t)(b * C::COLS), umma_desc(a_base + a_lo_off + aoff + (uint32_t)b * 2048u, a_lbo, 128u), bd, id_n, 1u);
+    } else {
+      const uint64_t bd_lo = umma_desc(wb + (uint32_t)N * 16u, 2u * N * 16u, 128u);
+#pragma unroll
+      for (int b = 0; b < C::NB; ++b)
+        umma_f16(tmem_acc + (uint32_t)(b * C::COLS), umma_desc(a_base + aoff + (uint32_t)b * 2048u, a_lbo, 128u), bd, id_n, acc);
+#pragma unroll
+      for (int b = 0; b < C::NB; ++b)
+        umma_f16(tmem_acc + (uint32_t)(b * C::COLS), umma_desc(a_base + a_lo_off + aoff + (uint32_t)b * 2048u, a_lbo, 128u), bd, id_n, 1u);
+#pragma unroll
+      for (int b = 0; b < C::NB; ++b)
+        umma_f16(tmem_acc + (uint32_t)(b * C::COLS), umma_desc(a_base + aoff + (uint32_t)b * 2048u, a_lbo, 128u), bd_lo, id_n, 1u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- epilogue
+// store 16 consecutive channels (global 16-channel group gg) of one pixel
+__device__ __forceinline__ void h2_store16(const H2Args& a, int gg, long long HWo, long long off, const float* v) {
+  if (a.y_h8) {
+    uint4* base = reinterpret_cast<uint4*>(a.y_h8);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint4 hi, lo;
+      split8(v + 8 * j, hi, lo);
+      const long long pl = (long long)(2 * gg + j) * 2;
+      base[pl * HWo + off] = hi;
+      base[(pl + 1) * HWo + off] = lo;
+    }
+  }
+  if (a.y_p4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      a.y_p4[(long long)(4 * gg + j) * HWo + off] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+
+template <class C, int EPI>
+__device__ __forceinline__ void h2_epilogue_tile(const H2Args& a, uint32_t tmem_acc, float* poolbuf, int q, int lane,
+                                                 int x0, int y0, int nblk, float inv_s, int& it) {
+  constexpr int N = C::N;
+  const int H = a.H, W = a.W;
+  const long long HW = (long long)H * W;
+  const uint32_t tq = tmem_acc + ((uint32_t)(32 * q) << 16);
+#pragma unroll 1
+  for (int g = 0; g < N / 16; ++g) {
+    float bv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bv[i] = __ldg(a.bias + nblk * N + 16 * g + i);
+    const int gg = nblk * (N / 16) + g;
+    // the TMEM loads of block b+1 fly while block b is processed
+    uint32_t mb0[2][16], mb1[2][16];
+    tmem_ld16_issue(tq + (uint32_t)(16 * g), mb0[0]);
+    if (C::STACK) tmem_ld16_issue(tq + (uint32_t)(N + 16 * g), mb1[0]);
+#pragma unroll
+    for (int b = 0; b < C::NB; ++b, ++it) {
+      uint32_t(&m0)[16] = mb0[b & 1];
+      uint32_t(&m1)[16] = mb1[b & 1];
+      tmem_ld16_wait(m0);
+      if (C::STACK) tmem_ld16_wait(m1);
+      if (b + 1 < C::NB) {
+        tmem_ld16_issue(tq + (uint32_t)((b + 1) * C::COLS + 16 * g), mb0[(b + 1) & 1]);
+        if (C::STACK) tmem_ld16_issue(tq + (uint32_t)((b + 1) * C::COLS + N + 16 * g), mb1[(b + 1) & 1]);
+      }
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float s = C::STACK ? (__uint_as_float(m0[i]) + __uint_as_float(m1[i])) : __uint_as_float(m0[i]);
+        v[i] = wctb_relu(fmaf(s, inv_s, bv[i]));
+      }
+      if (EPI == WCTB_EPI_POOL2) {
+        // block b = tile rows 2b (lanes 0..63) and 2b+1 (lanes 64..127): row exchange through shared memory
+        const int Ho = H >> 1, Wo = W >> 1;
+        const int cpos = (q & 1) * 32 + lane;
+        const int oy = (y0 >> 1) + b, ox = (x0 + cpos) >> 1;
+        const bool ok = (cpos < TW) && oy < Ho && ox < Wo && ((lane & 1) == 0);
+        float* pb = poolbuf + (it & 1) * (64 * 20);
+        if (q >= 2) {
+          float4* d = reinterpret_cast<float4*>(pb + cpos * 20);
+          d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+          d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q < 2) {
+          const float4* s = reinterpret_cast<const float4*>(pb + cpos * 20);
+          const float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+          const float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float m = fmaxf(v[i], o[i]);
+            v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          }
+          if (ok) h2_store16(a, gg, (long long)Ho * Wo, (long long)oy * Wo + ox, v);
+        }
+      } else {
+        const int p = 128 * b + 32 * q + lane;
+        const int r = p >> 6, c = p & 63;
+        const int gy = y0 + r, gx = x0 + c;
+        if ((c < TW) && gy < H && gx < W) {
+          if (EPI == WCTB_EPI_NONE) {
+            h2_store16(a, gg, HW, (long long)gy * W + gx, v);
+          } else if (EPI == WCTB_EPI_NCHW3) {
+            if (g == 0 && nblk == 0) {
+              float* img = reinterpret_cast<float*>(a.y_p4);
+              const long long off = (long long)gy * W + gx;
+              img[off] = v[0]; img[HW + off] = v[1]; img[2 * HW + off] = v[2];
+            }
+          } else {   // nearest x2
+            const int Wo = 2 * W;
+            const long long off = (long long)(2 * gy) * Wo + 2 * gx;
+            if (a.y_h8) {
+              uint4* base = reinterpret_cast<uint4*>(a.y_h8);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 hi, lo;
+                split8(v + 8 * j, hi, lo);
+                uint4* ph = base + (long long)(2 * gg + j) * 2 * (4 * HW);
+                uint4* pl = ph + 4 * HW;
+                ph[off] = hi; ph[off + 1] = hi; ph[off + Wo] = hi; ph[off + Wo + 1] = hi;
+                pl[off] = lo; pl[off + 1] = lo; pl[off + Wo] = lo; pl[off + Wo + 1] = lo;
+              }
+            }
+            if (a.y_p4) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                float4* pl = a.y_p4 + (long long)(4 * gg + j) * (4 * HW);
+                pl[off] = o; pl[off + 1] = o; pl[off + Wo] = o; pl[off + Wo + 1] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- producer helpers
+// border tile: (TH+2) rows x 4 planes by bulk row copies, reflection resolved in the source address
+template <class C>
+__device__ __forceinline__ void h2_load_border(const H2Args& a, uint8_t* st, uint64_t* bar, int kg, int x0, int y0,
+                                               const __half* wsrc) {
+  const int H = a.H, W = a.W;
+  const long long HW = (long long)H * W;
+  const int jlo = (x0 == 0) ? 1 : 0;                 // tile col j <-> gx = x0 - 1 + j
+  const int jhi = min(PW, W - x0 + 1);
+  const int ncols = jhi - jlo;
+  const bool left = (x0 == 0);
+  const int jr = W - x0 + 1;                         // tile col of gx == W
+  const bool right = jr < PW;
+  const uint32_t row_bytes = (uint32_t)(ncols + (left ? 1 : 0) + (right ? 1 : 0)) * 16u;
+  mbar_expect_tx(bar, (uint32_t)C::W_BYTES + 4u * C::ROWS * row_bytes);
+  bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, bar);
+  const uint4* xb = reinterpret_cast<const uint4*>(a.x);
+#pragma unroll 1
+  for (int pl = 0; pl < 4; ++pl) {
+    int gp = 4 * kg + pl;
+    if (gp >= a.planes_in) gp -= 2;                  // Cin % 16 == 8: the missing chunk has zero weights; feed finite data
+    const uint4* plane = xb + (long long)gp * HW;
+#pragma unroll 1
+    for (int i = 0; i < C::ROWS; ++i) {
+      const int gy = wctb_reflect(y0 - 1 + i, H);
+      const uint4* src = plane + (long long)gy * W;
+      const uint32_t dst = smem_u32(st + ((size_t)pl * C::ROWS + i) * PW * 16);
+      bulk_g2s(dst + jlo * 16, src + (x0 - 1 + jlo), (uint32_t)ncols * 16u, bar);
+      if (left) bulk_g2s(dst, src + 1, 16u, bar);                           // gx = -1 -> 1
+      if (right) bulk_g2s(dst + jr * 16, src + (W - 2), 16u, bar);          // gx = W  -> W-2
+    }
+  }
+}
+
+template <class C, int EPI>
+__global__ void __launch_bounds__(192, 1) conv_h2_kernel(const __grid_constant__ CUtensorMap tmap, const H2Args a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* stages = smem;
+  float* poolbuf = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES + C::POOL_BYTES);
+  uint64_t* empty = full + C::NSTAGE;
+  uint64_t* acc_full = empty + C::NSTAGE;
+  uint64_t* acc_empty = acc_full + C::NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + C::NACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkg = (a.Cin + 15) / 16;
+  const int tiles_xy = a.tiles_x * a.tiles_y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== producer ===========================
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int nblk = tile / tiles_xy, rem = tile - nblk * tiles_xy;
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int x0 = tx * TW, y0 = ty * C::TH;
+        const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= a.W) || (y0 + C::TH >= a.H);
+        const __half* wblk = a.w + (size_t)nblk * nkg * (C::W_BYTES / 2);
+        for (int kg = 0; kg < nkg; ++kg, ++it) {
+          const int slot = it % C::NSTAGE;
+          mbar_wait(empty + slot, ((it / C::NSTAGE) & 1) ^ 1);
+          uint8_t* st = stages + slot * C::STAGE_BYTES;
+          const __half* wsrc = wblk + (size_t)kg * (C::W_BYTES / 2);
+          if (!border) {
+            mbar_expect_tx(full + slot, (uint32_t)C::STAGE_BYTES);
+            tma_load_4d(smem_u32(st), &tmap, 0, x0 - 1, y0 - 1, 4 * kg, full + slot);   // planes beyond the tensor: zero fill
+            bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, full + slot);
+          } else {
+            h2_load_border<C>(a, st, full + slot, kg, x0, y0, wsrc);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t % C::NACC;
+        mbar_wait(acc_empty + acc, ((t / C::NACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc * C::ACC_COLS;
+        for (int kg = 0; kg < nkg; ++kg, ++it) {
+          const int slot = it % C::NSTAGE;
+          mbar_wait(full + slot, (it / C::NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(stages + slot * C::STAGE_BYTES);
+          h2_issue_stage<C>(a_base, a_base + C::IN_BYTES, tmem_acc, kg == 0);
+          tc_commit(empty + slot);
+        }
+        tc_commit(acc_full + acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;
+    const float inv_s = __ldg(a.wscale + 1);
+    uint32_t t = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++t) {
+      const int nblk = tile / tiles_xy, rem = tile - nblk * tiles_xy;
+      const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+      const uint32_t acc = t % C::NACC;
+      mbar_wait(acc_full + acc, (t / C::NACC) & 1);
+      tc_fence_after();
+      h2_epilogue_tile<C, EPI>(a, tmem_base + acc * C::ACC_COLS, poolbuf, q, lane, tx * TW, ty * C::TH, nblk, inv_s, it);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// H8 tensor [planes][H][W][8] fp16 as a 4-D tensor map; box = 8 x 64 px x rows x 4 planes
+int make_h8_tmap(CUtensorMap* m, const void* base, int planes, int H, int W, int rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return WCTB_E_CUDA;
+  cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[4] = {8, (cuuint32_t)PW, (cuuint32_t)rows, 4};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_wctb_last_cuda_error = (int)r; return WCTB_E_CUDA; }
+  return WCTB_OK;
+}
+
+// cudaFuncSetAttribute once per (kernel, device)
+template <class K>
+int ensure_smem_attr(K kernel, int bytes, bool* done) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!done[dev]) {
+    WCTB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done[dev] = true;
+  }
+  return WCTB_OK;
+}
+
+template <class C, int EPI>
+int launch_h2(H2Args a, cudaStream_t st) {
+  static bool done[64] = {};
+  int rc = ensure_smem_attr(conv_h2_kernel<C, EPI>, C::SMEM_BYTES, done);
+  if (rc != WCTB_OK) return rc;
+  a.tiles_x = (a.W + TW - 1) / TW;
+  a.tiles_y = (a.H + C::TH - 1) / C::TH;
+  a.ntiles = a.tiles_x * a.tiles_y * (a.Cout / C::N);
+  CUtensorMap tmap;
+  rc = make_h8_tmap(&tmap, a.x, a.planes_in, a.H, a.W, C::ROWS);
+  if (rc != WCTB_OK) return rc;
+  const int grid = a.ntiles < wctb_num_sms() ? a.ntiles : wctb_num_sms();
+  conv_h2_kernel<C, EPI><<<grid, 192, C::SMEM_BYTES, st>>>(tmap, a);
+  WCTB_RETURN_LAUNCH();
+}
+template <class C>
+int launch_h2_epi(const H2Args& a, int epi, cudaStream_t st) {
+  switch (epi) {
+    case WCTB_EPI_NONE: return launch_h2<C, WCTB_EPI_NONE>(a, st);
+    case WCTB_EPI_POOL2: return launch_h2<C, WCTB_EPI_POOL2>(a, st);
+    case WCTB_EPI_UP2: return launch_h2<C, WCTB_EPI_UP2>(a, st);
+    default: return WCTB_E_BADARG;
+  }
+}
+inline int h2_pick_n(int Cout) {
+  if (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128) return Cout;
+  if (Cout > 128 && Cout % 128 == 0) return 128;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- weight packing (device-side scale)
+// wscale[0]: max|w| as uint bits (atomicMax; zeroed by the caller), wscale[1]: 1/s, wscale[2]: s
+__global__ void h2_maxabs_kernel(const float* __restrict__ w, long long n, unsigned* __restrict__ wscale) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(wscale, __float_as_uint(m));
+}
+__device__ __forceinline__ float h2_scale_from_max(float m) {
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e;
+  frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 10 - e);          // m * s in [512, 1024)
+}
+// dst index = ((((nb*nkg + kg)*9 + tap)*2 + c)*2N + r)*8 + e ; r < N: hi of co = nb*N + r, r >= N: lo of co = nb*N + r - N
+__global__ void pack_w_h2_kernel(const float* __restrict__ w, __half* __restrict__ dst, float* __restrict__ wscale, int Cin,
+                                 int Cout, int N) {
+  const float s = h2_scale_from_max(__uint_as_float(reinterpret_cast<const unsigned*>(wscale)[0]));
+  const int nkg = (Cin + 15) / 16;
+  const long long total = (long long)(Cout / N) * nkg * 9 * 2 * 2 * N * 8;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i == 0) { wscale[1] = 1.f / s; wscale[2] = s; }
+  if (i >= total) return;
+  const int e = (int)(i & 7);
+  long long t = i >> 3;
+  const int r = (int)(t % (2 * N)); t /= (2 * N);
+  const int c = (int)(t & 1); t >>= 1;
+  const int tap = (int)(t % 9); t /= 9;
+  const int kg = (int)(t % nkg);
+  const int nb = (int)(t / nkg);
+  const int co = nb * N + (r < N ? r : r - N), ci = kg * 16 + c * 8 + e;
+  float v = 0.f;
+  if (ci < Cin) v = w[((long long)co * Cin + ci) * 9 + tap] * s;
+  const __half hi = __float2half_rn(v);
+  dst[i] = (r < N) ? hi : __float2half_rn(v - __half2float(hi));
+}
+
+// ---------------------------------------------------------------------------------- layout conversion
+__global__ void nchw_to_h8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int C, long long HW) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c8 = blockIdx.y;
+  if (i >= HW) return;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (c8 * 8 + e < C) ? src[(long long)(c8 * 8 + e) * HW + i] : 0.f;
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  dst[(long long)(2 * c8) * HW + i] = hi;
+  dst[(long long)(2 * c8 + 1) * HW + i] = lo;
+}
+__global__ void h8_to_nchw_kernel(const uint4* __restrict__ src, float* __restrict__ dst, int C, long long HW) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c8 = blockIdx.y;
+  if (i >= HW) return;
+  const uint4 hi = src[(long long)(2 * c8) * HW + i], lo = src[(long long)(2 * c8 + 1) * HW + i];
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t hh = (h[e >> 1] >> (16 * (e & 1))) & 0xffffu, ll = (l[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+    if (c8 * 8 + e < C) dst[(long long)(c8 * 8 + e) * HW + i] = h2f(hh) + h2f(ll);
+  }
+}
+// fp32 P4 [C/4][HW][4] -> H8 (used when a decoder is fed an fp32 feature, e.g. after wct_apply)
+__global__ void p4_to_h8_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, int C4, long long HW) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c8 = blockIdx.y;
+  if (i >= HW) return;
+  const float4 a = src[(long long)(2 * c8) * HW + i];
+  const float4 b = (2 * c8 + 1 < C4) ? src[(long long)(2 * c8 + 1) * HW + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  dst[(long long)(2 * c8) * HW + i] = hi;
+  dst[(long long)(2 * c8 + 1) * HW + i] = lo;
+}
+
+// ---------------------------------------------------------------------------------- first layer (3 -> Cout), fp32 FFMA
+// Same arithmetic as conv_first2_kernel (conv_fp32.cu): two pixels per thread, bias then taps 0..26 in order; the
+// output goes to H8 (and optionally fp32 P4 as well, when the layer is the last of its encoder).
+__global__ void __launch_bounds__(256) conv_first_h2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, uint4* __restrict__ y_h8,
+                                                            float4* __restrict__ y_p4, int H, int W, int Cout) {
+  extern __shared__ float4 smem4[];
+  float* ws = reinterpret_cast<float*>(smem4);  // [27][Cout]
+  float* bs = ws + 27 * Cout;
+  for (int i = threadIdx.x + threadIdx.y * 32; i < 27 * Cout; i += 256) ws[i] = w[i];
+  for (int i = threadIdx.x + threadIdx.y * 32; i < Cout; i += 256) bs[i] = bias[i];
+  __syncthreads();
+  const int xa = blockIdx.x * 64 + threadIdx.x, xb = xa + 32;
+  const int yy = blockIdx.y * 8 + threadIdx.y;
+  if (xa >= W || yy >= H) return;
+  const bool hasb = xb < W;
+  float ina[27], inb[27];
+  const long long HW = (long long)H * W;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int gy = wctb_reflect(yy + dy - 1, H);
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int gxa = wctb_reflect(xa + dx - 1, W);
+      const int gxb = wctb_reflect(xb + dx - 1, W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ina[(dy * 3 + dx) * 3 + c] = __ldg(x + c * HW + (long long)gy * W + gxa);
+        inb[(dy * 3 + dx) * 3 + c] = __ldg(x + c * HW + (long long)gy * W + gxb);
+      }
+    }
+  }
+  const float4* w4 = reinterpret_cast<const float4*>(ws);
+  const int C4 = Cout >> 2;
+  const long long row = (long long)yy * W;
+  for (int c8 = 0; c8 < (Cout >> 3); ++c8) {
+    float va[8], vb[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c4 = 2 * c8 + h;
+      float4 a = reinterpret_cast<const float4*>(bs)[c4];
+      float4 b = a;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const float4 wv = w4[k * C4 + c4];
+        a.x = fmaf(ina[k], wv.x, a.x); b.x = fmaf(inb[k], wv.x, b.x);
+        a.y = fmaf(ina[k], wv.y, a.y); b.y = fmaf(inb[k], wv.y, b.y);
+        a.z = fmaf(ina[k], wv.z, a.z); b.z = fmaf(inb[k], wv.z, b.z);
+        a.w = fmaf(ina[k], wv.w, a.w); b.w = fmaf(inb[k], wv.w, b.w);
+      }
+      va[4 * h] = wctb_relu(a.x); va[4 * h + 1] = wctb_relu(a.y); va[4 * h + 2] = wctb_relu(a.z); va[4 * h + 3] = wctb_relu(a.w);
+      vb[4 * h] = wctb_relu(b.x); vb[4 * h + 1] = wctb_relu(b.y); vb[4 * h + 2] = wctb_relu(b.z); vb[4 * h + 3] = wctb_relu(b.w);
+      if (y_p4) {
+        float4* pr = y_p4 + (long long)c4 * HW + row;
+        pr[xa] = make_float4(va[4 * h], va[4 * h + 1], va[4 * h + 2], va[4 * h + 3]);
+        if (hasb) pr[xb] = make_float4(vb[4 * h], vb[4 * h + 1], vb[4 * h + 2], vb[4 * h + 3]);
+      }
+    }
+    if (y_h8) {
+      uint4 hi, lo;
+      uint4* ph = y_h8 + (long long)(2 * c8) * HW + row;
+      uint4* pl = ph + HW;
+      split8(va, hi, lo);
+      ph[xa] = hi; pl[xa] = lo;
+      if (hasb) { split8(vb, hi, lo); ph[xb] = hi; pl[xb] = lo; }
+    }
+  }
+}
+
+}  // namespace
+
+// ====================================================================================== C ABI
+extern "C" int wctb_h2_supported(int Cin, int Cout) { return (h2_pick_n(Cout) != 0 && Cin > 0 && (Cin % 8) == 0) ? 1 : 0; }
+
+extern "C" long long wctb_h2_packed_halves(int Cin, int Cout) {
+  if (!wctb_h2_supported(Cin, Cout)) return 0;
+  return (long long)Cout * ((Cin + 15) / 16) * 9 * 2 * 2 * 8;
+}
+
+extern "C" int wctb_pack_weights_h2(const float* w, void* dst, float* wscale, int Cin, int Cout, void* stream) {
+  if (!w || !dst || !wscale) return WCTB_E_BADARG;
+  if (!wctb_h2_supported(Cin, Cout)) return WCTB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = 9LL * Cin * Cout;
+  WCTB_CUDA_TRY(cudaMemsetAsync(wscale, 0, 4 * sizeof(float), st));
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  h2_maxabs_kernel<<<blocks, 256, 0, st>>>(w, n, reinterpret_cast<unsigned*>(wscale));
+  const long long total = wctb_h2_packed_halves(Cin, Cout);
+  pack_w_h2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, (__half*)dst, wscale, Cin, Cout, h2_pick_n(Cout));
+  WCTB_RETURN_LAUNCH();
+}
+
+extern "C" int wctb_conv3x3_h2(const void* x_h8, const void* w_packed, const float* bias, const float* wscale, void* y_h8,
+                               float* y_p4, int H, int W, int Cin, int Cout, int epilogue, void* stream) {
+  if (!x_h8 || !w_packed || !bias || !wscale || (!y_h8 && !y_p4) || H < 2 || W < 2) return WCTB_E_BADARG;
+  if (!wctb_h2_supported(Cin, Cout)) return WCTB_E_UNSUPPORTED;
+  if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  H2Args a{(const __half*)x_h8, (const __half*)w_packed, bias, wscale, (__half*)y_h8, (float4*)y_p4, H, W, Cin, Cout, 0, 0, 0,
+           2 * ((Cin + 7) / 8)};
+  if (epilogue == WCTB_EPI_NCHW3) {
+    if (Cout != 16 || !y_p4) return WCTB_E_BADARG;
+    a.y_h8 = nullptr;
+    return launch_h2<H2Cfg<16, 8, 1>, WCTB_EPI_NCHW3>(a, st);
+  }
+  switch (h2_pick_n(Cout)) {
+    case 16: return launch_h2_epi<H2Cfg<16, 8, 1>>(a, epilogue, st);
+    case 32: return launch_h2_epi<H2Cfg<32, 4, 1>>(a, epilogue, st);
+    case 64: return launch_h2_epi<H2Cfg<64, 4, 0>>(a, epilogue, st);
+    default: return launch_h2_epi<H2Cfg<128, 2, 0>>(a, epilogue, st);
+  }
+}
+
+extern "C" int wctb_nchw_to_h8(const float* src, void* dst, int C, int H, int W, void* stream) {
+  if (!src || !dst || C <= 0 || H <= 0 || W <= 0) return WCTB_E_BADARG;
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 255) / 256), (C + 7) / 8);
+  nchw_to_h8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (uint4*)dst, C, HW);
+  WCTB_RETURN_LAUNCH();
+}
+extern "C" int wctb_h8_to_nchw(const void* src, float* dst, int C, int H, int W, void* stream) {
+  if (!src || !dst || C <= 0 || H <= 0 || W <= 0) return WCTB_E_BADARG;
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 255) / 256), (C + 7) / 8);
+  h8_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, dst, C, HW);
+  WCTB_RETURN_LAUNCH();
+}
+extern "C" int wctb_p4_to_h8(const float* src, void* dst, int C, int H, int W, void* stream) {
+  if (!src || !dst || C <= 0 || (C & 3) || H <= 0 || W <= 0) return WCTB_E_BADARG;
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 255) / 256), (C + 7) / 8);
+  p4_to_h8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (uint4*)dst, C / 4, HW);
+  WCTB_RETURN_LAUNCH();
+}
+
+extern "C" int wctb_conv3x3_first_h2(const float* x, const float* w, const float* bias, void* y_h8, float* y_p4, int H, int W,
+                                     int Cout, void* stream) {
+  if (!x || !w || !bias || (!y_h8 && !y_p4) || H < 2 || W < 2 || Cout <= 0 || (Cout & 7) || Cout > 512) return WCTB_E_BADARG;
+  const size_t smem = (size_t)(27 * Cout + Cout) * sizeof(float);
+  static bool done[64] = {};
+  if (smem > 48 * 1024) {
+    int rc = ensure_smem_attr(conv_first_h2_kernel, (int)smem, done);
+    if (rc != WCTB_OK) return rc;
+  }
+  dim3 block(32, 8), grid((W + 63) / 64, (H + 7) / 8);
+  conv_first_h2_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(x, w, bias, (uint4*)y_h8, (float4*)y_p4, H, W, Cout);
+  WCTB_RETURN_LAUNCH();
+}

@@ -22,13 +22,18 @@ LAST_TC = True        # TF32 mode: an unfused last decoder layer (C -> 3) runs o
 FUSE_TAIL = True      # [x2 upsample +] conv12 + conv11 of the decoders in one kernel when the TF32 engine is active
 HEAD_TC = True        # 16x nets: conv11 of the fused head on the tensor cores too (else FFMA producers)
 FUSE_HEAD = True      # conv11+conv12(+pool) in one kernel when the TF32 engine is active
-_PRECISION = "tf32"   # "tf32": tcgen05 TF32 tensor-core engine where supported; "fp32": CUDA-core fp32 everywhere
+# "h2"  (default): tcgen05 kind::f16 on fp16 hi/lo operand pairs -- fp32-accurate tensor-core convs (csrc/conv_h2.cu)
+# "tf32": single-pass tcgen05 TF32 engine (csrc/conv_umma.cu): 10-bit operands, does NOT meet the 3e-3 RMS contract on
+#         noise-like inputs; kept as the fast / lossy option and as an A/B
+# "fp32": CUDA-core fp32 everywhere (the GPU-side reference of the other two)
+_PRECISION = os.environ.get("WCTB_PRECISION", "h2")
+PRECISIONS = ("h2", "tf32", "fp32")
 
 
 def set_precision(p: str):
     global _PRECISION
-    if p not in ("fp32", "tf32"):
-        raise ValueError("precision must be 'fp32' or 'tf32'")
+    if p not in PRECISIONS:
+        raise ValueError("precision must be one of %s" % (PRECISIONS,))
     _PRECISION = p
 
 
@@ -107,6 +112,8 @@ class _Net(nn.Module):
             wd = w.double()
             b = (b.double() + torch.einsum("ojyx,j->o", wd, b0)).float()
             w = torch.einsum("ojyx,ji->oiyx", wd, w0).float()
+        if precision == "h2":
+            return self._pack_layer_h2(L, w, b, first, last)
         engine = ops.ENGINE_FP32 if (first or last) else self._engine(L, precision)
         out = {"w": ops.pack_weights(w.contiguous(), engine), "b": b.contiguous().float(), "engine": engine}
         if last and precision == "tf32" and LAST_TC and ops.tf32_supported(L["cin"], 16):
@@ -118,6 +125,23 @@ class _Net(nn.Module):
         if first and precision == "tf32" and L["cout"] == 16:
             out["w_tc"] = ops.pack_head_tc_weights(w)       # conv11 on the tensor cores (fused head of the 16x nets)
         return out
+
+    def _pack_layer_h2(self, L, w, b, first, last):
+        """h2 engine: first layer (3 -> C) stays fp32 FFMA; a C -> 3 last layer is zero-padded to 16 outputs"""
+        if first:
+            return {"w": ops.pack_weights(w.contiguous(), ops.ENGINE_FP32), "b": b.contiguous().float(), "engine": ops.ENGINE_H2,
+                    "w_oihw": w.contiguous().float()}
+        cin, cout = w.shape[1], w.shape[0]
+        if last:
+            wp = torch.zeros(16, cin, 3, 3, device=w.device, dtype=torch.float32)
+            wp[:cout] = w
+            bp = torch.zeros(16, device=w.device, dtype=torch.float32)
+            bp[:cout] = b.float()
+            w, b, cout = wp, bp, 16
+        if not ops.h2_supported(cin, cout):
+            raise WctbError("h2 engine: unsupported layer %d -> %d" % (cin, cout))
+        wh, ws = ops.pack_weights_h2(w.contiguous())
+        return {"w": wh, "ws": ws, "b": b.contiguous().float(), "engine": ops.ENGINE_H2, "cin": cin, "cout": cout}
 
     def packed(self, precision=None):
         precision = precision or _PRECISION
@@ -147,8 +171,10 @@ class _Encoder(_Net):
     def forward_p4(self, x, precision=None, round_output=False):
         """x [1,3,H,W] (or [3,H,W]) CUDA fp32 -> P4 feature [C/4,h,w,4].  round_output: store the feature TF32-rounded
         (rna) because a tensor-core layer consumes it directly (WCT matrix folded into the decoder's first conv)."""
-        self._check_cuda(x)
         precision = precision or _PRECISION
+        if precision == "h2":
+            return self.forward_feat(x, want_h8=False)[0]
+        self._check_cuda(x)
         pk = self.packed(precision)
         x = x.detach().contiguous().float()
         H, W = x.shape[-2:]
@@ -176,6 +202,32 @@ class _Encoder(_Net):
             y = ops.conv3x3_p4(y, pk[i]["w"], pk[i]["b"], L["cout"], epi, nxt(i), pk[i]["engine"])
         return y
 
+    def forward_feat(self, x, want_h8=True, want_p4=True, precision=None):
+        """x [1,3,H,W] CUDA fp32 -> (P4 fp32 feature | None, H8 feature | None).  The h2 engine's last layer can write both
+        forms at once: fp32 P4 for the statistics kernels, H8 for the decoder's (WCT-folded) first conv.  With the other
+        engines the P4 tensor serves both purposes and the second element is None."""
+        precision = precision or _PRECISION
+        if precision != "h2":
+            return self.forward_p4(x, precision, round_output=want_h8), None
+        self._check_cuda(x)
+        pk = self.packed(precision)
+        x = x.detach().contiguous().float()
+        H, W = x.shape[-2:]
+        n = len(self.layers)
+        sh, sw = arch.feature_hw(self.STAGE, H, W)
+        if sh < 2 or sw < 2:
+            raise WctbError("input %dx%d too small for stage %d (ReflectionPad2d needs >=2 px at the deepest level)" % (H, W, self.STAGE))
+        L0 = self.layers[0]
+        last = n == 1
+        y8, y4 = ops.conv3x3_first_h2(x, pk[0]["w"], pk[0]["b"], L0["cout"], out_h8=(not last) or want_h8, out_p4=last and want_p4)
+        for i in range(1, n):
+            L = self.layers[i]
+            last = i == n - 1
+            epi = ops.EPI_POOL2 if L["pool_after"] else ops.EPI_NONE
+            y8, y4 = ops.conv3x3_h2(y8, pk[i]["w"], pk[i]["ws"], pk[i]["b"], L["cin"], L["cout"], epi,
+                                    out_h8=(not last) or want_h8, out_p4=last and want_p4)
+        return y4, y8
+
     def forward(self, x):
         return ops.p4_to_nchw(self.forward_p4(x))
 
@@ -192,6 +244,10 @@ class _Decoder(_Net):
         if first_override is not None:
             pk[0] = self._pack_layer(0, precision, first_override[0], first_override[1])
         n = len(self.layers)
+        if precision == "h2":
+            return self._forward_h2(y, pk)
+        if y.dtype == torch.float16:
+            raise WctbError("an H8 feature needs the h2 engine")
         if y.shape[1] < 2 or y.shape[2] < 2:
             raise WctbError("feature map too small for ReflectionPad2d(1)")
         nxt = lambda i: (pk[i + 1]["engine"] == ops.ENGINE_TF32 or "w_last_tc" in pk[i + 1]) if i + 1 < n else False
@@ -211,7 +267,23 @@ class _Decoder(_Net):
             return ops.conv3x3_p4(y, pk[n - 1]["w_last_tc"], pk[n - 1]["b_last_tc"], 16, ops.EPI_NCHW3, False, ops.ENGINE_TF32)
         return ops.conv3x3_last(y, pk[n - 1]["w"], pk[n - 1]["b"])
 
+    def _forward_h2(self, y, pk):
+        """h2 engine: y is an H8 feature (or fp32 P4, converted) -> image [1,3,H,W]"""
+        if y.dtype != torch.float16:
+            y = ops.p4_to_h8(y)
+        if y.shape[2] < 2 or y.shape[3] < 2:
+            raise WctbError("feature map too small for ReflectionPad2d(1)")
+        n = len(self.layers)
+        for i in range(n - 1):
+            L = self.layers[i]
+            epi = ops.EPI_UP2 if L["up_after"] else ops.EPI_NONE
+            y, _ = ops.conv3x3_h2(y, pk[i]["w"], pk[i]["ws"], pk[i]["b"], L["cin"], L["cout"], epi)
+        L = self.layers[n - 1]
+        return ops.conv3x3_h2(y, pk[n - 1]["w"], pk[n - 1]["ws"], pk[n - 1]["b"], L["cin"], 16, ops.EPI_NCHW3)[1]
+
     def first_layer_needs_tf32_input(self, precision=None):
+        if (precision or _PRECISION) == "h2":
+            return False
         pk = self.packed(precision or _PRECISION)
         if len(pk) == 1:
             return "w_last_tc" in pk[0]

@@ -5,12 +5,12 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3, ENGINE_FP32, ENGINE_TF32, check  # noqa: F401
+from ._lib import EPI_NONE, EPI_POOL2, EPI_UP2, EPI_NCHW3, ENGINE_FP32, ENGINE_TF32, ENGINE_H2, check  # noqa: F401
 
 _launches = 0  # number of libwctb kernel-launching calls (bench.py reports kernels via its own table)
 KERNELS_PER_CALL = {"whiten_ns": 1, "wct_matrix_w": 3, "halo": 1, "nchw_to_p4": 1, "p4_to_nchw": 1, "pack_fp32": 1, "pack_tf32": 1, "conv_first": 1, "conv_p4": 1,
                     "conv_last": 1, "conv_head": 1, "conv_head_tc": 1, "conv_tail": 1, "channel_sum": 1, "centered_gram": 1, "eigh": 1, "wct_matrix": 5, "wct_apply": 1,
-                    "fold": 2}
+                    "fold": 2, "pack_h2": 2, "conv_h2": 1, "conv_first_h2": 1, "to_h8": 1, "from_h8": 1, "conv_head_h2": 1, "conv_tail_h2": 1}
 
 
 def launches() -> int:
@@ -360,3 +360,96 @@ def fold_wct_into_conv(w_oihw, bias, m, b, mean_c):
                                               _need(b_out), cin, cout, _stream()), "fold_wct_into_conv")
     _count("fold")
     return w_out, b_out
+
+
+# ------------------------------------------------------------------------------------------------ h2 engine
+# fp32-accurate tensor-core convolutions: activations travel as H8 = [ceil(C/8), 2 (hi, lo), H, W, 8] fp16 tensors
+def h2_supported(cin: int, cout: int) -> bool:
+    return bool(_lib.load().wctb_h2_supported(cin, cout))
+
+
+def _need_h8(t: torch.Tensor):
+    if t.dtype != torch.float16 or t.dim() != 5 or t.shape[1] != 2 or t.shape[4] != 8:
+        raise _lib.WctbError("expected an H8 activation [C/8,2,H,W,8] fp16, got %s %s" % (t.dtype, tuple(t.shape)))
+    return _need(t, torch.float16)
+
+
+def pack_weights_h2(w_oihw: torch.Tensor):
+    """OIHW fp32 -> (packed fp16 halves, wscale fp32[4] device buffer); the power-of-two weight scale is chosen on the device"""
+    cout, cin = w_oihw.shape[:2]
+    w = w_oihw.detach().contiguous().float()
+    n = _lib.load().wctb_h2_packed_halves(cin, cout)
+    if n <= 0:
+        raise _lib.WctbError("h2 engine does not support a %d -> %d layer" % (cin, cout))
+    dst = torch.empty(n, device=w.device, dtype=torch.float16)
+    wscale = torch.empty(4, device=w.device, dtype=torch.float32)
+    check(_lib.load().wctb_pack_weights_h2(_need(w), _need(dst, torch.float16), _need(wscale), cin, cout, _stream()), "pack_weights_h2")
+    _count("pack_h2")
+    return dst, wscale
+
+
+def conv3x3_h2(x_h8: torch.Tensor, w: torch.Tensor, wscale: torch.Tensor, b: torch.Tensor, cin: int, cout: int, epilogue: int,
+               out_h8: bool = True, out_p4: bool = False):
+    """H8 -> (H8 | None, fp32 P4 | None); EPI_NCHW3 -> (None, image [1,3,H,W])"""
+    _, _, H, W, _ = x_h8.shape
+    if epilogue == EPI_POOL2:
+        Ho, Wo = H // 2, W // 2
+    elif epilogue == EPI_UP2:
+        Ho, Wo = 2 * H, 2 * W
+    else:
+        Ho, Wo = H, W
+    dev = x_h8.device
+    y8 = y4 = None
+    if epilogue == EPI_NCHW3:
+        y4 = torch.empty(1, 3, H, W, device=dev, dtype=torch.float32)
+    else:
+        if out_h8:
+            y8 = torch.empty((cout + 7) // 8, 2, Ho, Wo, 8, device=dev, dtype=torch.float16)
+        if out_p4:
+            y4 = torch.empty(cout // 4, Ho, Wo, 4, device=dev, dtype=torch.float32)
+    check(_lib.load().wctb_conv3x3_h2(_need_h8(x_h8), _need(w, torch.float16), _need(b), _need(wscale),
+                                      None if y8 is None else _need(y8, torch.float16), None if y4 is None else _need(y4),
+                                      H, W, cin, cout, epilogue, _stream()), "conv3x3_h2")
+    _count("conv_h2")
+    return y8, y4
+
+
+def conv3x3_first_h2(x_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor, cout: int, out_h8: bool = True, out_p4: bool = False):
+    """x: [1,3,H,W] or [3,H,W]; w packed [9][3][cout] fp32 -> (H8 | None, P4 | None)"""
+    if x_nchw.dim() == 4:
+        x_nchw = x_nchw.squeeze(0)
+    _, H, W = x_nchw.shape
+    dev = x_nchw.device
+    y8 = torch.empty(cout // 8, 2, H, W, 8, device=dev, dtype=torch.float16) if out_h8 else None
+    y4 = torch.empty(cout // 4, H, W, 4, device=dev, dtype=torch.float32) if out_p4 else None
+    check(_lib.load().wctb_conv3x3_first_h2(_need(x_nchw), _need(w), _need(b), None if y8 is None else _need(y8, torch.float16),
+                                            None if y4 is None else _need(y4), H, W, cout, _stream()), "conv3x3_first_h2")
+    _count("conv_first_h2")
+    return y8, y4
+
+
+def nchw_to_h8(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() == 4:
+        x = x.squeeze(0)
+    C, H, W = x.shape
+    y = torch.empty((C + 7) // 8, 2, H, W, 8, device=x.device, dtype=torch.float16)
+    check(_lib.load().wctb_nchw_to_h8(_need(x), _need(y, torch.float16), C, H, W, _stream()), "nchw_to_h8")
+    _count("to_h8")
+    return y
+
+
+def h8_to_nchw(x: torch.Tensor, C: int = None) -> torch.Tensor:
+    C8, _, H, W, _ = x.shape
+    C = C8 * 8 if C is None else C
+    y = torch.empty(1, C, H, W, device=x.device, dtype=torch.float32)
+    check(_lib.load().wctb_h8_to_nchw(_need_h8(x), _need(y), C, H, W, _stream()), "h8_to_nchw")
+    _count("from_h8")
+    return y
+
+
+def p4_to_h8(x: torch.Tensor) -> torch.Tensor:
+    C4, H, W, _ = x.shape
+    y = torch.empty((C4 + 1) // 2, 2, H, W, 8, device=x.device, dtype=torch.float16)
+    check(_lib.load().wctb_p4_to_h8(_need(x), _need(y, torch.float16), C4 * 4, H, W, _stream()), "p4_to_h8")
+    _count("to_h8")
+    return y

@@ -56,6 +56,7 @@ class WCT(nn.Module):
         self._side = None
         self._main = None
         self.fast_stats = True     # TF32 mode, single GPU: fp32-product Gram (see _moments)
+        self.fast_stats_h2 = os.environ.get("WCTB_FAST_STATS_H2", "0") == "1"   # h2 engine: fp64 Gram unless told otherwise
         self.use_graph = True      # single-GPU stylize(): capture the two-stream schedule in a CUDA graph per input shape
         self.max_graphs = 4        # captured graphs kept (LRU): each one pins the activations of its input shape in HBM
         self._graphs = collections.OrderedDict()
@@ -89,7 +90,9 @@ class WCT(nn.Module):
         # fp32-product Gram only on a single GPU: its partial sums depend on the pixel partition (1e-7 relative), which the
         # TF32 pipeline amplifies through the whitening; the sharded path keeps the fp64 Gram so that strips stay
         # tile-invariant (sharded == single GPU to fp64 summation order).
-        ops.centered_gram(x_p4, mean, region, out=gram_out, fast=(self.fast_stats and nets.get_precision() == "tf32" and self.dist is None))
+        prec = nets.get_precision()
+        fast = self.dist is None and ((prec == "tf32" and self.fast_stats) or (prec == "h2" and self.fast_stats_h2))
+        ops.centered_gram(x_p4, mean, region, out=gram_out, fast=fast)
         return mean
 
     def _wct_params(self, c_p4, s_p4, alpha, c_region=None, s_region=None, c_count=None, s_count=None):
@@ -152,17 +155,23 @@ class WCT(nn.Module):
         enc, dec = getattr(self, "e%d" % stage), getattr(self, "d%d" % stage)
         sh = stage - 1
         s4 = enc.forward_p4(style)
-        c4 = enc.forward_p4(content, round_output=self.fold_into_decoder and dec.first_layer_needs_tf32_input())
+        c4, c8 = self._encode_content(enc, dec, content)
         reg = lambda r: None if r is None else tuple(v >> sh for v in r)
         m, b, mc = self._wct_params(c4, s4, float(alpha), reg(c_region), reg(s_region), c_count, s_count)
         del s4
         if self.fold_into_decoder:
             L0 = getattr(dec, dec.layers[0]["name"])
             w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
-            return dec.forward_p4(c4, first_override=(w, bb))
+            return dec.forward_p4(c4 if c8 is None else c8, first_override=(w, bb))
         cs4 = ops.wct_apply(c4, m, b, mc, round_tf32=dec.first_layer_needs_tf32_input())
         del c4
         return dec.forward_p4(cs4)
+
+    def _encode_content(self, enc, dec, img):
+        """content features as (fp32 P4 for the statistics, H8 for the decoder's folded first conv | None)"""
+        if nets.get_precision() == "h2":
+            return enc.forward_feat(img, want_h8=self.fold_into_decoder)
+        return enc.forward_p4(img, round_output=self.fold_into_decoder and dec.first_layer_needs_tf32_input()), None
 
     # ---- two-stream schedule: the style branch (encoder, statistics, eigensolve of every stage) does not depend on the
     # content image, so it runs on a side stream and overlaps the content branch -- in particular the single-CTA
@@ -241,7 +250,7 @@ class WCT(nn.Module):
                     enc, dec = getattr(self, "e%d" % s), getattr(self, "d%d" % s)
                     mark = self._mark
                     mark(s, "start")
-                    c4 = enc.forward_p4(img, round_output=self.fold_into_decoder and dec.first_layer_needs_tf32_input())
+                    c4, c8 = self._encode_content(enc, dec, img)
                     mark(s, "enc")
                     C = c4.shape[0] * 4
                     n = float(c4.shape[1] * c4.shape[2])
@@ -266,7 +275,8 @@ class WCT(nn.Module):
                     if self.fold_into_decoder:
                         L0 = getattr(dec, dec.layers[0]["name"])
                         w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
-                        img = dec.forward_p4(c4, first_override=(w, bb))
+                        img = dec.forward_p4(c4 if c8 is None else c8, first_override=(w, bb))
+                        del c8
                     else:
                         cs4 = ops.wct_apply(c4, m, b, mc, round_tf32=dec.first_layer_needs_tf32_input())
                         del c4

@@ -119,6 +119,32 @@ int wctb_conv_tail(const float* x_p4, const float* w12_packed, const float* b12,
 int wctb_conv3x3_last(const float* x_p4, const float* w, const float* bias, float* y_nchw,
                       int H, int W, int Cin, void* stream);
 
+/* ---- "h2" engine: fp32-accurate tensor-core convolutions (csrc/conv_h2.cu) -----------------------------------
+ * replaces the same reference lines as wctb_conv3x3_p4 above (`self.relu(self.convXY(self.pad(y)))` [+ pool / unpool],
+ * model_cd.py:724-743, 276-294; model_original.py:492-511, 581-599) at fp32 accuracy ON the tensor cores: every fp32
+ * operand is carried as a pair of fp16 numbers (x = hi + lo, 22 significand bits) and a product is evaluated as
+ * hi*w_hi + lo*w_hi + hi*w_lo by tcgen05.mma.kind::f16 with fp32 accumulation.
+ * Activation layout H8: [ceil(C/8)][2 (hi, lo)][H][W][8] fp16 (same bytes as fp32).
+ * Packed weights: [Cout/N][ceil(Cin/16)][tap 9][2 k-chunks][hi N rows | lo N rows][8] fp16 of w * s, with s a power of two
+ * chosen ON THE DEVICE from max|w| (no host sync); wscale is a caller-owned device buffer of 4 floats:
+ * [0] scratch, [1] = 1/s (read by the conv kernel), [2] = s.  N = Cout for Cout in {16,32,64,128}, else 128.
+ * wctb_conv3x3_h2 writes y_h8 (H8, for the next h2 layer) and / or y_p4 (fp32 P4, for the statistics kernels and the
+ * public NCHW API); either may be NULL.  epilogue WCTB_EPI_NCHW3: Cout must be 16 (3 real channels zero-padded by the
+ * caller), y_p4 is the [3][H][W] image.  Supported: Cin % 8 == 0, Cout in {16,32,64,128} or a multiple of 128.          */
+int wctb_h2_supported(int Cin, int Cout);
+long long wctb_h2_packed_halves(int Cin, int Cout);
+int wctb_pack_weights_h2(const float* w_oihw, void* dst_halves, float* wscale, int Cin, int Cout, void* stream);
+int wctb_conv3x3_h2(const void* x_h8, const void* w_packed, const float* bias, const float* wscale, void* y_h8,
+                    float* y_p4, int H, int W, int Cin, int Cout, int epilogue, void* stream);
+/* first layer for the h2 engine: x NCHW [3][H][W] -> H8 and / or fp32 P4, fp32 FFMA (conv0 folded by the host),
+ * same arithmetic as wctb_conv3x3_first.  w: [tap][3][Cout] (wctb_pack_weights_fp32), Cout % 8 == 0.                   */
+int wctb_conv3x3_first_h2(const float* x_nchw, const float* w, const float* bias, void* y_h8, float* y_p4,
+                          int H, int W, int Cout, void* stream);
+/* layout conversion: NCHW fp32 <-> H8, fp32 P4 -> H8 */
+int wctb_nchw_to_h8(const float* src_nchw, void* dst_h8, int C, int H, int W, void* stream);
+int wctb_h8_to_nchw(const void* src_h8, float* dst_nchw, int C, int H, int W, void* stream);
+int wctb_p4_to_h8(const float* src_p4, void* dst_h8, int C, int H, int W, void* stream);
+
 /* ---- WCT statistics ------------------------------------------------------------------
  * replaces: torch.mean(cF,1) / cF - mean / torch.mm(cF, cF.t()) (util_wct.py:68-70, 94-96).
  * x is P4 [C/4][H][W][4]; the sums run over the region rows [y0,y1) x cols [x0,x1) only

@@ -84,7 +84,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), "libwctb.so does not export %s" % name
-    assert declared == set(_lib.SIGNATURES) | {"wctb_error_string", "wctb_workspace_doubles"}
+    assert declared == set(_lib.SIGNATURES) | {"wctb_error_string", "wctb_workspace_doubles", "wctb_h2_packed_halves"}
     lib2 = _lib.load()
     assert lib2.wctb_workspace_doubles(_lib.WS_EIGH, 128, 2) == 2 * 128 * 128 + 16
     assert lib2.wctb_workspace_doubles(_lib.WS_WCT_MATRIX, 64, 1) == 3 * 64 * 64 + 8
