@@ -36,6 +36,13 @@ CONFIGS = {  # name -> (content HxW, style HxW)
     "cfg4": ((4096, 10240), (2160, 3840)),
 }
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_16x.npz")
+DTYPE_TEXT = {
+    "h2": "f32-accurate tensor-core convs: every operand an fp16 hi+lo pair (22 significand bits), tcgen05.mma.kind::f16, f32 accumulate; "
+          "first layers f32 FFMA; f64 statistics + f64 eigensolve",
+    "tf32": "tf32 tensor-core convs (operands rounded to TF32, fp32 accumulate; only the 3->24 first layer of stage 1 is fp32 FFMA), "
+            "fp32-product/f64-accumulate statistics, f64 eigensolve",
+    "fp32": "f32 convs, f64 statistics+eigensolve",
+}
 
 
 def algorithmic_conv_flops(mode, Hc, Wc, Hs, Ws):
@@ -203,7 +210,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, help="cfg2|cfg3|cfg4|weak (default: cfg3 at N=1, weak at N>1)")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="h2", choices=["h2", "tf32", "fp32"],
+                    help="conv engine: h2 = fp32-accurate tensor-core convs on fp16 hi/lo operand pairs (default, meets the precision "
+                         "contract); tf32 = single-pass TF32 (lossy: misses the contract on noise-like inputs); fp32 = CUDA cores")
     ap.add_argument("--fold", type=int, default=1, help="fold the WCT matrix into the decoder's first conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -352,7 +361,7 @@ def main():
             "metric": "megapixels/sec end-to-end WCT stylize (16x VGG, UHD)", "value": round(value, 2), "unit": "MP/s",
             "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 tensor-core convs (operands rounded to TF32, fp32 accumulate; only the 3->24 first layer of stage 1 is fp32 FFMA), fp32-product/f64-accumulate statistics, f64 eigensolve" if args.precision == "tf32" else "f32 convs, f64 statistics+eigensolve",
+            "dtype": DTYPE_TEXT[args.precision],
             "data": "synthetic torch.rand images (seed 0); shipped 16x weights (tests/golden/weights_16x.npz)",
             "config": {"workload": wl, "mode": "16x", "alpha": 1.0, "stages": 5, "parallelism": "strips%d" % N,
                        "l2": "256 MiB flush between timed iterations", "precision": args.precision, "fold": args.fold,
@@ -372,6 +381,11 @@ def main():
         print(json.dumps(line))
     if N > 1:
         dist.destroy_process_group()
+
+
+# cycles per tcgen05.mma.kind::f16 (M=128, K=16) by N -- placeholders until tools/h2_rates.py has run (same A-fetch bound as
+# the TF32 K=8 slab: one 4 KB operand slab per MMA)
+H2_CYC = {16: 39.3, 32: 42.0, 48: 45.0, 64: 48.1, 96: 56.0, 128: 64.2, 256: 128.4}
 
 
 def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
@@ -424,7 +438,28 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
                           lambda y: (2.0 * y.shape[-2] * y.shape[-1] * 9 * (16 * 16 + 16 * 3), 4.0 * (x.numel() + y.numel()),
                                      tiles(y.shape[-2], y.shape[-1], 14, 60) * (144 + 126) * CYC[16]))
 
-    wrappers = {"conv3x3_p4": wrap_p4, "conv_head_tc": wrap_head_tc, "conv_head": wrap_head, "conv_tail": wrap_tail}
+    # h2 engine: cycles per kind::f16 MMA (M=128, K=16) measured by tools/h2_rates.py (profiles/r02_h2_rates.txt)
+    CYC16 = H2_CYC
+
+    def wrap_h2(x, w, ws, b, cin, cout, epilogue, out_h8=True, out_p4=False):
+        _, _, H, W, _ = x.shape
+        n = min(cout, 128)
+        nb = {16: 8, 32: 4, 64: 4, 128: 2}[n]
+        per_tap = (CYC16[2 * n] + CYC16[n]) if n <= 32 else 3 * CYC16[n]
+        mma_cyc = tiles(H, W, 2 * nb, 62) * nb * 9 * ((cin + 15) // 16) * (cout // n) * per_tap
+        ob = {0: 1.0, 1: 0.25, 2: 4.0, 3: 3.0 / 16}[epilogue] * ((1 if out_h8 else 0) + (1 if out_p4 else 0) if epilogue != 3 else 1)
+        return timed_call(("conv_h2", "%d->%d epi%d" % (cin, cout, epilogue)), originals["conv3x3_h2"],
+                          (x, w, ws, b, cin, cout, epilogue, out_h8, out_p4), {},
+                          lambda y: (2.0 * 9 * cin * (3 if epilogue == 3 else cout) * H * W, 4.0 * H * W * (cin + cout * ob), mma_cyc))
+
+    def wrap_first_h2(x, w, b, cout, out_h8=True, out_p4=False):
+        H, W = x.shape[-2:]
+        nout = (1 if out_h8 else 0) + (1 if out_p4 else 0)
+        return timed_call(("conv_first_h2", "3->%d" % cout), originals["conv3x3_first_h2"], (x, w, b, cout, out_h8, out_p4), {},
+                          lambda y: (2.0 * H * W * (9 + 27 * cout), 4.0 * H * W * (3 + cout * nout), 0.0))
+
+    wrappers = {"conv3x3_p4": wrap_p4, "conv_head_tc": wrap_head_tc, "conv_head": wrap_head, "conv_tail": wrap_tail,
+                "conv3x3_h2": wrap_h2, "conv3x3_first_h2": wrap_first_h2}
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     overlap_prev = getattr(wct, "overlap_style", False)
     wct.overlap_style = False                       # single stream, so event pairs bracket exactly one kernel each
@@ -451,7 +486,9 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     rows.sort(key=lambda r: -r["ms"])
     conv_ms = sum(r["ms"] for r in rows)
     top = rows[0]
-    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0        # TF32 dense = half the bf16 rate; no direct TF32 measurement
+    # TF32 dense = half the bf16 rate.  h2 engine: every algorithmic FLOP costs 3 kind::f16 MACs (hi*hi + lo*hi + hi*lo), so the
+    # peak of ALGORITHMIC FLOP/s is the measured f16/bf16 rate / 3
+    tf32_peak = peaks["bf16_tflops_sustained"] / (3.0 if precision == "h2" else 2.0)
     fp32_peak = 148 * 128 * 2 * 1.9e9 / 1e12                # CUDA-core FFMA peak at 1.9 GHz
     ach_tf = top["flops"] / (top["ms"] / 1e3) / 1e12
     ach_gb = top["bytes"] / (top["ms"] / 1e3) / 1e9
@@ -473,7 +510,8 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
         "kernel": "%s %s (%d launches/step, %.1f%% of the single-stream step)" % (top["kernel"], top["shape"], top["launches"],
                                                                                   100 * top["ms"] / step_ms),
         "arith_intensity_flop_per_byte": round(ai, 1), "achieved_tflops": round(ach_tf, 2), "achieved_gbs": round(ach_gb, 1),
-        "tensor_peak_note": "TF32 peak = bf16_tflops_sustained/2 (%s); fp32 engine: 148 SM x 128 FMA x 1.9 GHz" % peaks["source"],
+        "tensor_peak_note": ("h2 engine: peak of algorithmic FLOP/s = bf16_tflops_sustained / 3 (three kind::f16 products per fp32-accurate product) (%s)" if precision == "h2"
+                             else "TF32 peak = bf16_tflops_sustained/2 (%s); fp32 engine: 148 SM x 128 FMA x 1.9 GHz") % peaks["source"],
         "conv_share_of_step": round(conv_ms / step_ms, 4), "single_stream_step_ms": round(step_ms, 3),
         # operand-fetch floor of the top kernel: (#tcgen05.mma it issues) x (measured cycles per MMA for its N) / (148 SMs x
         # sm clock), as a fraction of its measured time -- the bound that actually applies to the N <= 64 layers

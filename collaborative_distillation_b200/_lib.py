@@ -67,6 +67,8 @@ SIGNATURES = {
     "wctb_debug_set_trace": [_p],
     "wctb_debug_mma_rate": [_p, _i, _i, _i, _i, _i, _p],
     "wctb_selftest_umma": [_p, _p, _p, _i, _i, _p],
+    "wctb_debug_mma_rate_f16": [_p, _i, _i, _i, _i, _p],
+    "wctb_debug_ldtm_rate": [_p, _i, _i, _i, _i, _p],
 }
 
 WCTB_OK = 0

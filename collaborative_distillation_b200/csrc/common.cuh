@@ -44,13 +44,29 @@ __device__ __forceinline__ float wctb_tf32(float x) {
 
 __device__ __forceinline__ float wctb_relu(float v) { return v > 0.f ? v : 0.f; }
 
+#define WCTB_MAX_DEVICES 64
+static inline int wctb_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < WCTB_MAX_DEVICES) ? dev : 0;
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device); `flags` is a static
+// bool[WCTB_MAX_DEVICES] owned by the launcher of that instantiation (immutable kernel attributes are the only state)
+#define WCTB_SET_SMEM_ONCE(flags, kernel, bytes)                                                              \
+  do {                                                                                                        \
+    const int slot__ = wctb_device_slot();                                                                    \
+    if (!(flags)[slot__]) {                                                                                   \
+      WCTB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      (flags)[slot__] = true;                                                                                 \
+    }                                                                                                         \
+  } while (0)
+
 static inline int wctb_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[WCTB_MAX_DEVICES] = {};
+  const int slot = wctb_device_slot();
+  if (n[slot] == 0) {
+    cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, slot);
+    if (n[slot] <= 0) n[slot] = 148;
   }
-  return n;
+  return n[slot];
 }

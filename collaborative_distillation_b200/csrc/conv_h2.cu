@@ -605,6 +605,74 @@ __global__ void __launch_bounds__(256) conv_first_h2_kernel(const float* __restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------- microbenchmarks (debug ABI)
+// cycles per tcgen05.mma.kind::f16 (M = 128, K = 16) for a given N with `nacc` independent accumulators, operands in the
+// no-swizzle plane layout the conv kernels use (contents irrelevant).
+template <int N>
+__global__ void __launch_bounds__(128, 1) h2_mma_rate_kernel(long long* out, int nacc, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 1 && elect_one()) {
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + 96 * 1024;
+    constexpr uint32_t idesc = umma_idesc_f16(N);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t ad = umma_desc(a0 + k * 64 * 16, 18432u * 2u, 128u);
+        const uint64_t bd = umma_desc(b0 + k * 2 * N * 16, N * 16u, 128u);
+#pragma unroll 1
+        for (int b = 0; b < nacc; ++b) umma_f16(tmem + (uint32_t)(b * N), ad, bd, idesc, 1u);
+      }
+    }
+    tc_commit(&bar);
+    mbar_wait(&bar, 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+// cycles for `iters` x (tcgen05.ld 32x32b.x16 of `per_iter` different column groups + wait) issued by `nwarps` warps at once
+__global__ void __launch_bounds__(256, 1) h2_ldtm_rate_kernel(long long* out, int per_iter, int iters) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tq = slot + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t sink = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    for (int k = 0; k < per_iter; k += 2) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16_issue(tq + (uint32_t)((16 * k) & 511), r0);
+      tmem_ld16_issue(tq + (uint32_t)((16 * (k + 1)) & 511), r1);
+      tmem_ld16_wait(r0);
+      tmem_ld16_wait(r1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sink ^= r0[i] ^ r1[i];
+    }
+  }
+  const long long dt = clock64() - t0;
+  if (lane == 0) out[blockIdx.x * 8 + warp] = dt;
+  if (sink == 0x12345678u) out[63] = sink;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(slot);
+}
+
 }  // namespace
 
 // ====================================================================================== C ABI
@@ -683,5 +751,22 @@ extern "C" int wctb_conv3x3_first_h2(const float* x, const float* w, const float
   }
   dim3 block(32, 8), grid((W + 63) / 64, (H + 7) / 8);
   conv_first_h2_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(x, w, bias, (uint4*)y_h8, (float4*)y_p4, H, W, Cout);
+  WCTB_RETURN_LAUNCH();
+}
+
+extern "C" int wctb_debug_mma_rate_f16(long long* out_cycles, int N, int nacc, int iters, int ctas, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = 200 * 1024;
+  if (!out_cycles || nacc < 1 || nacc * N > 512 || iters < 1 || ctas < 1) return WCTB_E_BADARG;
+#define WCTB_MR(NN) case NN: WCTB_CUDA_TRY(cudaFuncSetAttribute(h2_mma_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    h2_mma_rate_kernel<NN><<<ctas, 128, smem, st>>>(out_cycles, nacc, iters); break;
+  switch (N) { WCTB_MR(16) WCTB_MR(32) WCTB_MR(48) WCTB_MR(64) WCTB_MR(96) WCTB_MR(128) WCTB_MR(256) default: return WCTB_E_UNSUPPORTED; }
+#undef WCTB_MR
+  WCTB_RETURN_LAUNCH();
+}
+/* out: [ctas][8] cycles per warp; nwarps in {4, 8}; per_iter even */
+extern "C" int wctb_debug_ldtm_rate(long long* out_cycles, int nwarps, int per_iter, int iters, int ctas, void* stream) {
+  if (!out_cycles || (nwarps != 4 && nwarps != 8) || per_iter < 2 || (per_iter & 1) || iters < 1 || ctas < 1) return WCTB_E_BADARG;
+  h2_ldtm_rate_kernel<<<ctas, 32 * nwarps, 0, (cudaStream_t)stream>>>(out_cycles, per_iter, iters);
   WCTB_RETURN_LAUNCH();
 }

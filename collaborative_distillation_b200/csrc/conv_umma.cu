@@ -269,11 +269,8 @@ __global__ void __launch_bounds__(192, Cfg<N>::CTAS_PER_SM) conv_umma_kernel(con
 template <int N, int EPI>
 int launch_conv(const ConvArgs& a, cudaStream_t st) {
   using C = Cfg<N>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel<N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
-  }
+  static bool attr_done[WCTB_MAX_DEVICES] = {};     // per device: one process may drive several GPUs
+  WCTB_SET_SMEM_ONCE(attr_done, (conv_umma_kernel<N, EPI>), C::SMEM_BYTES);
   dim3 grid((a.W + TW - 1) / TW, (a.H + C::TH - 1) / C::TH, a.Cout / N);
   if (grid.y > 65535 || grid.z > 65535) return WCTB_E_UNSUPPORTED;
   conv_umma_kernel<N, EPI><<<grid, 192, C::SMEM_BYTES, st>>>(a);
@@ -435,11 +432,8 @@ template <int C1, int N, int EPI>
 int launch_head(const HeadArgs& h, cudaStream_t st) {
   using C = Cfg<N>;
   using HC = HeadCfg<C1, N>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel<C1, N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, HC::SMEM_BYTES));
-    attr_done = true;
-  }
+  static bool attr_done[WCTB_MAX_DEVICES] = {};
+  WCTB_SET_SMEM_ONCE(attr_done, (conv_head_kernel<C1, N, EPI>), HC::SMEM_BYTES);
   dim3 grid((h.c.W + TW - 1) / TW, (h.c.H + C::TH - 1) / C::TH, 1);
   if (grid.y > 65535) return WCTB_E_UNSUPPORTED;
   conv_head_kernel<C1, N, EPI><<<grid, 320, HC::SMEM_BYTES, st>>>(h);
@@ -640,11 +634,8 @@ template <int EPI>
 int launch_head_tc(const HeadTcArgs& h, cudaStream_t st) {
   using C = Cfg<16>;
   constexpr int SMEM = 2 * C::STAGE_BYTES + HT_IMG_ROWS * HT_PI * 16 + 6 * 2 * 16 * 16 + 256 + 128;
-  static bool attr_done = false;
-  if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_head_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static bool attr_done[WCTB_MAX_DEVICES] = {};
+  WCTB_SET_SMEM_ONCE(attr_done, (conv_head_tc_kernel<EPI>), SMEM);
   dim3 grid((h.c.W + TW - 1) / TW, (h.c.H + C::TH - 1) / C::TH, 1);
   if (grid.y > 65535) return WCTB_E_UNSUPPORTED;
   conv_head_tc_kernel<EPI><<<grid, 192, SMEM, st>>>(h);
@@ -869,11 +860,8 @@ template <bool UPSRC>
 int launch_tail(const TailArgs& t, cudaStream_t st) {
   using C = Cfg<16>;
   constexpr int SMEM = 2 * C::STAGE_BYTES + 2 * C::W_BYTES + 256 + 128;
-  static bool attr_done = false;
-  if (!attr_done) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(conv_tail_kernel<UPSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static bool attr_done[WCTB_MAX_DEVICES] = {};
+  WCTB_SET_SMEM_ONCE(attr_done, (conv_tail_kernel<UPSRC>), SMEM);
   dim3 grid((t.c.W + TAIL_TW - 1) / TAIL_TW, (t.c.H + TAIL_TH - 1) / TAIL_TH, 1);
   if (grid.y > 65535) return WCTB_E_UNSUPPORTED;
   conv_tail_kernel<UPSRC><<<grid, UPSRC ? 320 : 192, SMEM, st>>>(t);

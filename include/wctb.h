@@ -294,6 +294,9 @@ int wctb_debug_set_trace(long long* buf);
 
 /* debug: cycles for iters*4*nacc tcgen05.mma (M=128,K=8 tf32) per CTA; layout 0 = planes (SWIZZLE_NONE), 1 = SWIZZLE_128B, 2 = LBO 16 */
 int wctb_debug_mma_rate(long long* out_cycles, int N, int layout, int nacc, int iters, int ctas, void* stream);
+/* cycles per tcgen05.mma.kind::f16 (M=128, K=16) vs N / number of independent accumulators; tcgen05.ld throughput */
+int wctb_debug_mma_rate_f16(long long* out_cycles, int N, int nacc, int iters, int ctas, void* stream);
+int wctb_debug_ldtm_rate(long long* out_cycles, int nwarps, int per_iter, int iters, int ctas, void* stream);
 
 /* ---- self tests (device-side descriptor / pipeline checks used by tests and smoke) ------- */
 int wctb_selftest_umma(float* out_128xN, const float* a_128xK, const float* b_NxK, int N, int K,

@@ -6,7 +6,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import collaborative_distillation_b200 as P
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-P.set_precision("tf32")
+P.set_precision(sys.argv[1] if len(sys.argv) > 1 else "h2")
+print("precision", P.get_precision())
 w = P.WCT(SimpleNamespace(mode="16x", numpy=False))
 P.weights.load_npz_into(w, os.path.join(root, "tests", "golden", "weights_16x.npz"))
 w = w.cuda()
