@@ -383,9 +383,9 @@ def main():
         dist.destroy_process_group()
 
 
-# cycles per tcgen05.mma.kind::f16 (M=128, K=16) by N -- placeholders until tools/h2_rates.py has run (same A-fetch bound as
-# the TF32 K=8 slab: one 4 KB operand slab per MMA)
-H2_CYC = {16: 39.3, 32: 42.0, 48: 45.0, 64: 48.1, 96: 56.0, 128: 64.2, 256: 128.4}
+# cycles per tcgen05.mma.kind::f16 (M=128, K=16) by N, measured by tools/h2_rates.py (same A-fetch bound as the TF32 K=8
+# slab: one 4 KB operand slab per MMA)
+H2_CYC = {16: 39.1, 32: 40.1, 48: 44.1, 64: 48.1, 96: 56.1, 128: 64.1, 256: 128.3}   # profiles/r02_h2_rates.txt
 
 
 def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
@@ -458,8 +458,24 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
         return timed_call(("conv_first_h2", "3->%d" % cout), originals["conv3x3_first_h2"], (x, w, b, cout, out_h8, out_p4), {},
                           lambda y: (2.0 * H * W * (9 + 27 * cout), 4.0 * H * W * (3 + cout * nout), 0.0))
 
+    def wrap_head_h2(x, w11p, is11, b11, w12p, is12, b12):
+        H, W = x.shape[-2:]
+        # per 32x28 tile: 9 conv11 blocks x 2 MMAs (N=96) + 8 conv12 blocks x 3 x (N=96 + N=48)
+        mma_cyc = tiles(H, W, 32, 28) * (9 * 2 * CYC16[96] + 8 * 3 * (CYC16[96] + CYC16[48]))
+        return timed_call(("conv_head_h2", "3->16->16 pool"), originals["conv_head_h2"], (x, w11p, is11, b11, w12p, is12, b12), {},
+                          lambda y: (2.0 * H * W * (9 + 9 * 3 * 16 + 9 * 16 * 16), 4.0 * (3 * H * W + 16 * (H // 2) * (W // 2)), mma_cyc))
+
+    def wrap_tail_h2(x, w12p, is12, b12, w11p, is11, b11, upsample_input):
+        H, W = (2 * x.shape[2], 2 * x.shape[3]) if upsample_input else (x.shape[2], x.shape[3])
+        mma_cyc = tiles(H, W, 32, 28) * (9 * 3 * (CYC16[96] + CYC16[48]) + 8 * 3 * (CYC16[96] + CYC16[48]))
+        return timed_call(("conv_tail_h2", "16->16->3 up%d" % int(upsample_input)), originals["conv_tail_h2"],
+                          (x, w12p, is12, b12, w11p, is11, b11, upsample_input), {},
+                          lambda y: (2.0 * H * W * 9 * (16 * 16 + 16 * 3), 4.0 * (x.numel() / 2 + 3 * H * W), mma_cyc))
+
     wrappers = {"conv3x3_p4": wrap_p4, "conv_head_tc": wrap_head_tc, "conv_head": wrap_head, "conv_tail": wrap_tail,
-                "conv3x3_h2": wrap_h2, "conv3x3_first_h2": wrap_first_h2}
+                "conv3x3_h2": wrap_h2, "conv3x3_first_h2": wrap_first_h2, "conv_head_h2": wrap_head_h2}
+    if hasattr(ops, "conv_tail_h2"):
+        wrappers["conv_tail_h2"] = wrap_tail_h2
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     overlap_prev = getattr(wct, "overlap_style", False)
     wct.overlap_style = False                       # single stream, so event pairs bracket exactly one kernel each

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["conv_fp32.cu", "conv_umma.cu", "conv_h2.cu", "wct_transform.cu", "gram_ring.cu", "gram_alt.cu", "image_io.cu", "halo.cu", "whiten_ns.cu"]
+SOURCES = ["conv_fp32.cu", "conv_umma.cu", "conv_h2.cu", "conv_h2_fused.cu", "wct_transform.cu", "gram_ring.cu", "gram_alt.cu", "image_io.cu", "halo.cu", "whiten_ns.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]

@@ -30,7 +30,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
-#include "umma.cuh"
+#include "h2.cuh"
 
 namespace {
 using namespace wctb_umma;
@@ -70,28 +70,6 @@ struct H2Args {
   int tiles_x, tiles_y, ntiles;   // ntiles = nblks * tiles_y * tiles_x
   int planes_in;                  // 2 * ceil(Cin / 8)
 };
-
-__device__ __forceinline__ uint32_t f2h_sat(float v) {   // fp32 -> fp16 bits, round-to-nearest-even, saturating
-  uint16_t h;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
-  return h;
-}
-__device__ __forceinline__ float h2f(uint32_t h) {
-  float f;
-  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((uint16_t)h));
-  return f;
-}
-// x -> (hi, lo) fp16 pair; 8 values -> two 16-byte units
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  uint32_t h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = f2h_sat(v[i]);
-    l[i] = f2h_sat(v[i] - h2f(h[i]));
-  }
-  hi = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-  lo = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
-}
 
 // ---------------------------------------------------------------------------------- MMA issue (one elected thread)
 // One pipeline stage = 16 input channels: planes [hi0, lo0, hi1, lo1] (K chunk stride = 2 planes) + weight slab.
@@ -415,19 +393,6 @@ int make_h8_tmap(CUtensorMap* m, const void* base, int planes, int H, int W, int
   return WCTB_OK;
 }
 
-// cudaFuncSetAttribute once per (kernel, device)
-template <class K>
-int ensure_smem_attr(K kernel, int bytes, bool* done) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (!done[dev]) {
-    WCTB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    done[dev] = true;
-  }
-  return WCTB_OK;
-}
-
 template <class C, int EPI>
 int launch_h2(H2Args a, cudaStream_t st) {
   static bool done[64] = {};
@@ -611,7 +576,7 @@ __global__ void __launch_bounds__(256) conv_first_h2_kernel(const float* __restr
 // no-swizzle plane layout the conv kernels use (contents irrelevant).
 template <int N>
 __global__ void __launch_bounds__(128, 1) h2_mma_rate_kernel(long long* out, int nacc, int iters) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;

@@ -1,0 +1,384 @@
+// libwctb: fused two-convolution kernels of the h2 engine (fp16 hi/lo operand pairs on tcgen05.mma.kind::f16).
+//
+//   head:  y = pool2( ReLU(conv12( pad( ReLU(conv11( pad(img) )) ) )) )       img NCHW fp32 3ch  -> y H8 16ch, half res
+//   tail:  img = ReLU(conv11( pad( ReLU(conv12( pad( [up2] x ) )) ) ))       x H8 16ch           -> img NCHW fp32 3ch
+//
+// The 16-channel full-resolution layers of the 16x nets are bound by the A-operand fetch of tcgen05.mma: one 128-row
+// operand slab (4 KB) costs ~40 cycles whatever N is (profiles/r02_h2_rates.txt: N=16 39, N=48 44, N=96 56 cycles).
+// So here the three HORIZONTAL taps of a 3x3 filter are stacked along N instead of being three MMAs:
+//      D[p, dx*16 + co] = sum_{dy, ci} A[p + dy*pitch, ci] * W[co, ci, dy, dx]            (one MMA per dy, N = 3*16 [*2])
+//      out[p, co]       = D[p, 0*16+co] + D[p+1, 1*16+co] + D[p+2, 2*16+co]
+// and the shifted sum is done by the epilogue with two warp shuffles per channel.  That needs p, p+1, p+2 in one warp:
+// the tile pitch is 32 pixels -- a TMEM lane quarter (= one warp) is exactly one tile row, the two rightmost positions
+// of a row are the usual garbage columns, an accumulator block of 128 positions is 4 rows.  With the hi/lo weight halves
+// stacked as well (N = 96: [3 dx][16] main | [3 dx][16] minor) a 16->16 conv costs 3 x (56 + 44) = 300 cycles per 128
+// positions instead of 9 x (40 + 39) = 711.
+//
+// Pipeline.  A tile is 32 output rows x 28 columns.  Inside a tile the two convolutions are pipelined at accumulator-
+// block granularity through two small TMEM rings (2 x 96 columns each): the first conv's block j is converted by its
+// epilogue warps into rows 4j..4j+3 of the second conv's operand tile in shared memory (hi/lo split, reflection of the
+// INTERMEDIATE at true image borders), the second conv's block k starts as soon as rows 4k..4k+5 are there, and its
+// epilogue warps pool / store while the single MMA-issuing thread is already ahead.  Image and operand tiles are double
+// buffered, so the pipeline also runs across tile boundaries; CTAs are persistent (one per SM).
+//   warp 0      weight loader (bulk copies, once)           warp 1      tcgen05.mma issuer (one elected thread)
+//   warps 2-5   epilogue of the second conv                 warps 6-9   epilogue of the first conv -> operand tile
+//   warps 10-13 first-conv input: image loader / converter (head) or upsampling loader (tail, when the input is half res)
+#include "h2.cuh"
+
+namespace {
+using namespace wctb_umma;
+
+constexpr int FP = 32;                              // tile pitch (pixels) = warp width
+constexpr int F_TW = 28;                            // valid output columns after two chained 3x3 convs (32 -> 30 -> 28)
+constexpr int F_TH = 32;                            // output rows per tile
+constexpr int F_NB2 = F_TH / 4;                     // second-conv blocks per full tile
+constexpr int F_NB1 = F_NB2 + 1;                    // first-conv blocks per full tile (rows -1 .. 34 of the tile)
+constexpr int F_ROW = FP * 16;                      // bytes of one 8-channel row
+constexpr int F_MID_ROWS = 4 * F_NB1;               // 36
+constexpr int F_PLANE = F_MID_ROWS * F_ROW;         // 18432
+constexpr int F_MID_BYTES = 4 * F_PLANE;            // planes hi0, lo0, hi1, lo1
+constexpr int F_WB = 2 * 96 * 16;                   // one B tile: [2 k-chunks][96 rows][16 B]
+constexpr int F_ACC1 = 0, F_ACC2 = 192;             // TMEM column bases of the two rings (2 slots x 96 columns each)
+
+// barrier slots
+enum { B_WFULL = 0, B_IN_READY = 1, B_IN_FREE = 3, B_A1_FULL = 5, B_A1_EMPTY = 7, B_A2_FULL = 9, B_A2_EMPTY = 11, B_MID_FREE = 13,
+       B_MID_READY = 15, B_COUNT = 15 + 2 * F_NB1 };
+
+struct FTile { int x0, ya, nb2, nb1; };
+__device__ __forceinline__ FTile f_tile(int tile, int tiles_x, int H) {
+  FTile t;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  t.x0 = tx * F_TW;
+  t.ya = ty * F_TH;
+  const int rows = min(F_TH, H - t.ya);
+  t.nb2 = (rows + 3) >> 2;
+  t.nb1 = t.nb2 + 1;
+  return t;
+}
+
+// out[c] = sum_dx shfl_down(main[dx*16 + c] + minor[dx*16 + c], dx)   for one dx-stacked accumulator block (96 columns)
+__device__ __forceinline__ void f_reduce_dx(uint32_t taddr, float* out) {
+  uint32_t m0[16], n0[16], m1[16], n1[16];
+  tmem_ld16_issue(taddr, m0);
+  tmem_ld16_issue(taddr + 48u, n0);
+  tmem_ld16_wait(m0);
+  tmem_ld16_wait(n0);
+  tmem_ld16_issue(taddr + 16u, m1);
+  tmem_ld16_issue(taddr + 64u, n1);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = __uint_as_float(m0[i]) + __uint_as_float(n0[i]);
+  tmem_ld16_wait(m1);
+  tmem_ld16_wait(n1);
+  tmem_ld16_issue(taddr + 32u, m0);
+  tmem_ld16_issue(taddr + 80u, n0);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(m1[i]) + __uint_as_float(n1[i]), 1);
+  tmem_ld16_wait(m0);
+  tmem_ld16_wait(n0);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(m0[i]) + __uint_as_float(n0[i]), 2);
+}
+
+// second conv of a chain (16 -> 16 or 16 -> 3 padded), dx-stacked: block k of the operand tile `mid` ([hi0, lo0, hi1, lo1]
+// planes, pitch 32) -> TMEM columns [tacc, tacc + 96).  wsm: [3 dy][2 chunks][96 rows][16 B] (rows 0..47 hi, 48..95 lo).
+__device__ __forceinline__ void f_issue_conv16(uint32_t mid, uint32_t wsm, uint32_t tacc, int k) {
+  constexpr uint32_t id96 = umma_idesc_f16(96), id48 = umma_idesc_f16(48);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const uint32_t a = mid + (uint32_t)(4 * k + dy) * F_ROW;
+    const uint64_t bd = umma_desc(wsm + (uint32_t)dy * F_WB, 96u * 16u, 128u);
+    umma_f16(tacc, umma_desc(a, 2u * F_PLANE, 128u), bd, id96, dy > 0 ? 1u : 0u);          // hi x [w_hi | w_lo]
+    umma_f16(tacc, umma_desc(a + F_PLANE, 2u * F_PLANE, 128u), bd, id48, 1u);              // lo x  w_hi
+  }
+}
+
+// write 16 channels of one position into the operand tile (planes hi0, lo0, hi1, lo1)
+__device__ __forceinline__ void f_store_mid(uint8_t* mid, int row, int col, const float* v) {
+  uint4 hi, lo;
+  uint4* p = reinterpret_cast<uint4*>(mid + (size_t)row * F_ROW) + col;
+  split8(v, hi, lo);
+  p[0] = hi;
+  p[F_PLANE / 16] = lo;
+  split8(v + 8, hi, lo);
+  p[2 * (F_PLANE / 16)] = hi;
+  p[3 * (F_PLANE / 16)] = lo;
+}
+__device__ __forceinline__ void f_copy_mid_row(uint8_t* mid, int dst_row, int src_row, int lane) {
+#pragma unroll
+  for (int pl = 0; pl < 4; ++pl) {
+    uint4* base = reinterpret_cast<uint4*>(mid + (size_t)pl * F_PLANE);
+    base[dst_row * FP + lane] = base[src_row * FP + lane];
+  }
+}
+
+// epilogue of the FIRST conv of a chain: accumulator block j -> rows 4j..4j+3 of the operand tile, with the reflection
+// of the intermediate at true image borders (columns by shuffle before the store, rows by a copy after a group barrier)
+__device__ __forceinline__ void f_first_epilogue(uint32_t tacc_q, uint8_t* mid, const FTile& t, int j, int q, int lane,
+                                                 int H, int W, const float* bias, float inv_s, uint64_t* acc_empty) {
+  float v[16];
+  f_reduce_dx(tacc_q, v);
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(acc_empty);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = wctb_relu(fmaf(v[i], inv_s, bias[i]));
+  // tile col c <-> gx = x0 - 1 + c.  gx = -1 takes the value of gx = 1, gx = W the value of gx = W - 2
+  const bool left = (t.x0 == 0);
+  const int cr = W - t.x0 + 1;
+  const bool right = cr < 30;
+  if (left || right) {
+    int src = lane;
+    if (left && lane == 0) src = 2;
+    if (right && lane == cr) src = cr - 2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __shfl_sync(0xffffffffu, v[i], src);
+  }
+  const int row = 4 * j + q;
+  f_store_mid(mid, row, lane, v);
+  // tile row r <-> gy = ya - 1 + r.  gy = -1 takes row gy = 1, gy = H takes row gy = H - 2
+  const bool top = (t.ya == 0) && (j == 0);
+  const int rh = H - t.ya + 1;
+  const bool bottom = (H - t.ya <= F_TH) && (j == (rh >> 2));
+  if (top || bottom) {
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (top && q == 0) f_copy_mid_row(mid, 0, 2, lane);
+    if (bottom && q == (rh & 3)) f_copy_mid_row(mid, rh, rh - 2, lane);
+  }
+}
+
+// ====================================================================================== fused encoder head
+struct HeadH2Args {
+  const float* img;     // [3][H][W]
+  const __half* w11;    // [2 mma][2 chunks][96][8]   (conv0 folded; see ops.pack_head_h2_w11)
+  const __half* w12;    // [3 dy][2 chunks][96][8]
+  const float* b11;     // [16]
+  const float* b12;     // [16]
+  float inv_s11, inv_s12;
+  uint4* y;             // H8 [2 chunks][2][H/2][W/2] 16-byte units
+  int H, W, tiles_x, ntiles;
+};
+constexpr int HD_IN_ROWS = 40;                                // 36 image rows + overrun of the last block's second K chunk
+constexpr int HD_IN_BYTES = HD_IN_ROWS * F_ROW;               // RGB0 hi | RGB0 lo, 16 B per pixel
+constexpr int HD_OFF_MID = 2 * HD_IN_BYTES;
+constexpr int HD_OFF_W11 = HD_OFF_MID + 2 * F_MID_BYTES;
+constexpr int HD_OFF_W12 = HD_OFF_W11 + 2 * F_WB;
+constexpr int HD_OFF_POOL = HD_OFF_W12 + 3 * F_WB;
+constexpr int HD_POOL_BYTES = 2 * 2 * 32 * 20 * 4;            // [parity][row pair][lane][16 + 4 pad] floats
+constexpr int HD_OFF_BAR = HD_OFF_POOL + HD_POOL_BYTES;
+constexpr int HD_SMEM = HD_OFF_BAR + 512 + 128;
+static_assert(B_COUNT * 8 + 8 <= 512, "barrier area");
+static_assert(HD_SMEM <= 227 * 1024, "shared memory budget");
+
+__global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HD_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = h.H, W = h.W;
+  const int ntl = (h.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
+
+  if (threadIdx.x == 0) {
+    mbar_init(bars + B_WFULL, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bars + B_IN_READY + s, 128); mbar_init(bars + B_IN_FREE + s, 1);
+      mbar_init(bars + B_A1_FULL + s, 1);    mbar_init(bars + B_A1_EMPTY + s, 4);
+      mbar_init(bars + B_A2_FULL + s, 1);    mbar_init(bars + B_A2_EMPTY + s, 4);
+      mbar_init(bars + B_MID_FREE + s, 1);
+      for (int j = 0; j < F_NB1; ++j) mbar_init(bars + B_MID_READY + s * F_NB1 + j, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== weights (once) ===========================
+    if (elect_one()) {
+      mbar_expect_tx(bars + B_WFULL, 5u * F_WB);
+      bulk_g2s(smem_u32(smem + HD_OFF_W11), h.w11, 2u * F_WB, bars + B_WFULL);
+      bulk_g2s(smem_u32(smem + HD_OFF_W12), h.w12, 3u * F_WB, bars + B_WFULL);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t id96 = umma_idesc_f16(96);
+      const uint32_t w11s = smem_u32(smem + HD_OFF_W11), w12s = smem_u32(smem + HD_OFF_W12);
+      mbar_wait(bars + B_WFULL, 0);
+      int i1 = 0, j1 = 0, i2 = 0, k2 = 0;          // cursors: (local tile, block) of the next first- / second-conv block
+      uint32_t g1 = 0, g2 = 0, base1 = 0;          // global block counters; first-conv blocks issued before tile i2
+      FTile t1 = f_tile((int)blockIdx.x, h.tiles_x, H), t2 = t1;
+      while (i2 < ntl) {
+        // second-conv block (i2, k2) reads first-conv blocks 0..k2+1 of its tile; stay one more block ahead
+        const uint32_t need = base1 + (uint32_t)k2 + 2u;
+        while (i1 < ntl && g1 < need + 1u) {
+          if (j1 == 0) mbar_wait(bars + B_IN_READY + (i1 & 1), (i1 >> 1) & 1);
+          const uint32_t slot = g1 & 1u;
+          mbar_wait(bars + B_A1_EMPTY + slot, ((g1 >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          // conv11: K chunk 0 = image row r (RGB hi | RGB lo of one pixel), chunk 1 = row r + 1 (LBO = one row)
+          const uint32_t a = smem_u32(smem + (i1 & 1) * HD_IN_BYTES) + (uint32_t)(4 * j1) * F_ROW;
+          const uint32_t tacc = tmem_base + F_ACC1 + slot * 96u;
+          umma_f16(tacc, umma_desc(a, F_ROW, 128u), umma_desc(w11s, 96u * 16u, 128u), id96, 0u);                  // dy 0, 1
+          umma_f16(tacc, umma_desc(a + 2u * F_ROW, F_ROW, 128u), umma_desc(w11s + F_WB, 96u * 16u, 128u), id96, 1u);  // dy 2, (zero)
+          tc_commit(bars + B_A1_FULL + slot);
+          ++g1;
+          if (++j1 == t1.nb1) {
+            tc_commit(bars + B_IN_FREE + (i1 & 1));
+            j1 = 0;
+            ++i1;
+            if (i1 < ntl) t1 = f_tile((int)blockIdx.x + i1 * (int)gridDim.x, h.tiles_x, H);
+          }
+        }
+        {
+          uint64_t* ready = bars + B_MID_READY + (i2 & 1) * F_NB1;
+          mbar_wait(ready + k2, (i2 >> 1) & 1);
+          mbar_wait(ready + k2 + 1, (i2 >> 1) & 1);
+          const uint32_t slot = g2 & 1u;
+          mbar_wait(bars + B_A2_EMPTY + slot, ((g2 >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          f_issue_conv16(smem_u32(smem + HD_OFF_MID + (i2 & 1) * F_MID_BYTES), w12s, tmem_base + F_ACC2 + slot * 96u, k2);
+          tc_commit(bars + B_A2_FULL + slot);
+          ++g2;
+          if (++k2 == t2.nb2) {
+            tc_commit(bars + B_MID_FREE + (i2 & 1));
+            base1 += (uint32_t)t2.nb1;
+            k2 = 0;
+            ++i2;
+            if (i2 < ntl) t2 = f_tile((int)blockIdx.x + i2 * (int)gridDim.x, h.tiles_x, H);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // =========================== epilogue of conv12: pool, split, store ===========================
+    const int q = warp & 3;
+    const uint32_t tq = tmem_base + F_ACC2 + ((uint32_t)(32 * q) << 16);
+    float bv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bv[i] = __ldg(h.b12 + i);
+    float* poolbuf = reinterpret_cast<float*>(smem + HD_OFF_POOL);
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long HWo = (long long)Ho * Wo;
+    uint32_t g2 = 0;
+    for (int i = 0; i < ntl; ++i) {
+      const FTile t = f_tile((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      for (int k = 0; k < t.nb2; ++k, ++g2) {
+        const uint32_t slot = g2 & 1u;
+        mbar_wait(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
+        tc_fence_after();
+        float v[16];
+        f_reduce_dx(tq + slot * 96u, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + B_A2_EMPTY + slot);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = wctb_relu(fmaf(v[c], h.inv_s12, bv[c]));
+        // rows 4k+q: (q, q+1) pool together; odd rows hand their values to the even row's warp
+        float* pb = poolbuf + ((g2 & 1u) * 2u + (uint32_t)(q >> 1)) * (32 * 20) + lane * 20;
+        if (q & 1) {
+          float4* d = reinterpret_cast<float4*>(pb);
+          d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+          d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!(q & 1)) {
+          const float4* s = reinterpret_cast<const float4*>(pb);
+          const float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+          const float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float m = fmaxf(v[c], o[c]);
+            v[c] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          }
+          const int oy = (t.ya + 4 * k + q) >> 1, ox = (t.x0 + lane) >> 1;
+          if (!(lane & 1) && lane < F_TW && oy < Ho && ox < Wo) {
+            const long long off = (long long)oy * Wo + ox;
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            h.y[off] = hi;
+            h.y[HWo + off] = lo;
+            split8(v + 8, hi, lo);
+            h.y[2 * HWo + off] = hi;
+            h.y[3 * HWo + off] = lo;
+          }
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // =========================== epilogue of conv11 -> conv12 operand tile ===========================
+    const int q = warp & 3;
+    const uint32_t tq = tmem_base + F_ACC1 + ((uint32_t)(32 * q) << 16);
+    float bv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bv[i] = __ldg(h.b11 + i);
+    uint32_t g1 = 0;
+    for (int i = 0; i < ntl; ++i) {
+      const FTile t = f_tile((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      uint8_t* mid = smem + HD_OFF_MID + (i & 1) * F_MID_BYTES;
+      if (i >= 2) mbar_wait(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);      // conv12 of tile i-2 has read this buffer
+      for (int j = 0; j < t.nb1; ++j, ++g1) {
+        const uint32_t slot = g1 & 1u;
+        mbar_wait(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
+        tc_fence_after();
+        f_first_epilogue(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s11, bars + B_A1_EMPTY + slot);
+        fence_async_smem();
+        mbar_arrive(bars + B_MID_READY + (i & 1) * F_NB1 + j);
+      }
+    }
+  } else {
+    // =========================== image loader: NCHW fp32 -> [R G B 0 | r g b 0] fp16 hi | lo pixels ===========================
+    const int pw = warp - 10;
+    const long long HW = (long long)H * W;
+    for (int b = 0; b < 2; ++b)      // rows 36..39 are only read against zero weights / by garbage positions: keep them finite
+      reinterpret_cast<uint4*>(smem + b * HD_IN_BYTES)[(36 + pw) * FP + lane] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < ntl; ++i) {
+      const FTile t = f_tile((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      uint4* in = reinterpret_cast<uint4*>(smem + (i & 1) * HD_IN_BYTES);
+      if (i >= 2) mbar_wait(bars + B_IN_FREE + (i & 1), ((i - 2) >> 1) & 1);
+      const int gx = wctb_reflect(t.x0 - 2 + lane, W);
+      float r0[9], r1[9], r2[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {                                  // tile row r <-> gy = ya - 2 + r
+        const int gy = wctb_reflect(t.ya - 2 + pw + 4 * k, H);
+        const float* p = h.img + (long long)gy * W + gx;
+        r0[k] = __ldg(p); r1[k] = __ldg(p + HW); r2[k] = __ldg(p + 2 * HW);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const uint32_t h0 = f2h_sat(r0[k]), h1 = f2h_sat(r1[k]), h2 = f2h_sat(r2[k]);
+        const uint32_t l0 = f2h_sat(r0[k] - h2f(h0)), l1 = f2h_sat(r1[k] - h2f(h1)), l2 = f2h_sat(r2[k] - h2f(h2));
+        in[(pw + 4 * k) * FP + lane] = make_uint4(h0 | (h1 << 16), h2, l0 | (l1 << 16), l2);
+      }
+      fence_async_smem();
+      mbar_arrive(bars + B_IN_READY + (i & 1));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+// ====================================================================================== C ABI
+extern "C" int wctb_conv_head_h2(const float* x_nchw, const void* w11_packed, const float* b11, float inv_s11,
+                                 const void* w12_packed, const float* b12, float inv_s12, void* y_h8, int H, int W,
+                                 void* stream) {
+  if (!x_nchw || !w11_packed || !b11 || !w12_packed || !b12 || !y_h8 || H < 2 || W < 2) return WCTB_E_BADARG;
+  if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
+  static bool done[64] = {};
+  int rc = ensure_smem_attr(conv_head_h2_kernel, HD_SMEM, done);
+  if (rc != WCTB_OK) return rc;
+  HeadH2Args h{x_nchw, (const __half*)w11_packed, (const __half*)w12_packed, b11, b12, inv_s11, inv_s12, (uint4*)y_h8, H, W, 0, 0};
+  h.tiles_x = (W + F_TW - 1) / F_TW;
+  h.ntiles = h.tiles_x * ((H + F_TH - 1) / F_TH);
+  const int grid = h.ntiles < wctb_num_sms() ? h.ntiles : wctb_num_sms();
+  conv_head_h2_kernel<<<grid, 448, HD_SMEM, (cudaStream_t)stream>>>(h);
+  WCTB_RETURN_LAUNCH();
+}

@@ -113,7 +113,7 @@ class _Net(nn.Module):
             b = (b.double() + torch.einsum("ojyx,j->o", wd, b0)).float()
             w = torch.einsum("ojyx,ji->oiyx", wd, w0).float()
         if precision == "h2":
-            return self._pack_layer_h2(L, w, b, first, last)
+            return self._pack_layer_h2(idx, L, w, b, first, last)
         engine = ops.ENGINE_FP32 if (first or last) else self._engine(L, precision)
         out = {"w": ops.pack_weights(w.contiguous(), engine), "b": b.contiguous().float(), "engine": engine}
         if last and precision == "tf32" and LAST_TC and ops.tf32_supported(L["cin"], 16):
@@ -126,11 +126,14 @@ class _Net(nn.Module):
             out["w_tc"] = ops.pack_head_tc_weights(w)       # conv11 on the tensor cores (fused head of the 16x nets)
         return out
 
-    def _pack_layer_h2(self, L, w, b, first, last):
-        """h2 engine: first layer (3 -> C) stays fp32 FFMA; a C -> 3 last layer is zero-padded to 16 outputs"""
+    def _pack_layer_h2(self, idx, L, w, b, first, last):
+        """h2 engine: first layer (3 -> C) stays fp32 FFMA; a C -> 3 last layer is zero-padded to 16 outputs.  The layers
+        that the fused head / tail kernels cover (static weights) also get their dx-stacked tensor-core tiles."""
         if first:
-            return {"w": ops.pack_weights(w.contiguous(), ops.ENGINE_FP32), "b": b.contiguous().float(), "engine": ops.ENGINE_H2,
-                    "w_oihw": w.contiguous().float()}
+            out = {"w": ops.pack_weights(w.contiguous(), ops.ENGINE_FP32), "b": b.contiguous().float(), "engine": ops.ENGINE_H2}
+            if L["cout"] == 16:
+                out["w11_h2"], out["inv_s11"] = ops.pack_head_h2_w11(w.contiguous())
+            return out
         cin, cout = w.shape[1], w.shape[0]
         if last:
             wp = torch.zeros(16, cin, 3, 3, device=w.device, dtype=torch.float32)
@@ -141,7 +144,13 @@ class _Net(nn.Module):
         if not ops.h2_supported(cin, cout):
             raise WctbError("h2 engine: unsupported layer %d -> %d" % (cin, cout))
         wh, ws = ops.pack_weights_h2(w.contiguous())
-        return {"w": wh, "ws": ws, "b": b.contiguous().float(), "engine": ops.ENGINE_H2, "cin": cin, "cout": cout}
+        out = {"w": wh, "ws": ws, "b": b.contiguous().float(), "engine": ops.ENGINE_H2, "cin": cin, "cout": cout}
+        n = len(self.layers)
+        in_head = self.KIND == "enc" and idx == 1 and cin == 16 and cout == 16 and L["pool_after"]
+        in_tail = self.KIND == "dec" and n >= 3 and idx >= n - 2 and cin == 16
+        if in_head or in_tail:
+            out["w_dx"], out["inv_s_dx"] = ops.pack_dx_h2(w.contiguous())
+        return out
 
     def packed(self, precision=None):
         precision = precision or _PRECISION
@@ -219,8 +228,14 @@ class _Encoder(_Net):
             raise WctbError("input %dx%d too small for stage %d (ReflectionPad2d needs >=2 px at the deepest level)" % (H, W, self.STAGE))
         L0 = self.layers[0]
         last = n == 1
-        y8, y4 = ops.conv3x3_first_h2(x, pk[0]["w"], pk[0]["b"], L0["cout"], out_h8=(not last) or want_h8, out_p4=last and want_p4)
-        for i in range(1, n):
+        first = 1
+        if FUSE_HEAD and n >= 3 and "w11_h2" in pk[0] and "w_dx" in pk[1]:
+            # conv11 + conv12 + pool in one kernel (16x nets, stages 2..5)
+            y8, y4 = ops.conv_head_h2(x, pk[0]["w11_h2"], pk[0]["inv_s11"], pk[0]["b"], pk[1]["w_dx"], pk[1]["inv_s_dx"], pk[1]["b"]), None
+            first = 2
+        else:
+            y8, y4 = ops.conv3x3_first_h2(x, pk[0]["w"], pk[0]["b"], L0["cout"], out_h8=(not last) or want_h8, out_p4=last and want_p4)
+        for i in range(first, n):
             L = self.layers[i]
             last = i == n - 1
             epi = ops.EPI_POOL2 if L["pool_after"] else ops.EPI_NONE

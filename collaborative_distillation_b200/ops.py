@@ -453,3 +453,64 @@ def p4_to_h8(x: torch.Tensor) -> torch.Tensor:
     check(_lib.load().wctb_p4_to_h8(_need(x), _need(y, torch.float16), C4 * 4, H, W, _stream()), "p4_to_h8")
     _count("to_h8")
     return y
+
+
+# ---- fused head / tail of the h2 engine: dx-stacked weight tiles, packed on the host (static weights, once at load)
+def h2_host_scale(w: torch.Tensor) -> float:
+    """power of two s with max|w| * s in [512, 1024) (same rule as the device-side packer)"""
+    import math
+    m = float(w.detach().abs().max())
+    if not (m > 0.0) or not math.isfinite(m):
+        return 1.0
+    return 2.0 ** (10 - math.frexp(m)[1])
+
+
+def _hi_lo(w: torch.Tensor, s: float):
+    ws = w.detach().float() * s
+    hi = ws.half()
+    return hi, (ws - hi.float()).half()
+
+
+def pack_head_h2_w11(w_oihw: torch.Tensor):
+    """conv11 [16,3,3,3] (conv0 folded) -> ([2 mma][2 chunks][96][8] fp16, 1/s).  MMA m, K chunk c carries filter row
+    dy = 2m + c (dy = 3 is all zero); a K chunk is one pixel [R G B 0 | r g b 0] (hi | lo); row dx*16+co holds
+    [w_hi(RGB) 0 w_hi(RGB) 0] (hi*w_hi + lo*w_hi), row 48+dx*16+co holds [w_lo(RGB) 0 0 0 0 0] (hi*w_lo)."""
+    s = h2_host_scale(w_oihw)
+    hi, lo = _hi_lo(w_oihw, s)
+    t = torch.zeros(2, 2, 96, 8, device=w_oihw.device, dtype=torch.float16)
+    for dy in range(3):
+        m, c = divmod(dy, 2)
+        for dx in range(3):
+            r = slice(dx * 16, dx * 16 + 16)
+            t[m, c, r, 0:3] = hi[:, :, dy, dx]
+            t[m, c, r, 4:7] = hi[:, :, dy, dx]
+            t[m, c, 48 + dx * 16:48 + dx * 16 + 16, 0:3] = lo[:, :, dy, dx]
+    return t.contiguous(), 1.0 / s
+
+
+def pack_dx_h2(w_oihw: torch.Tensor):
+    """[Cout<=16,16,3,3] -> ([3 dy][2 chunks][96][8] fp16, 1/s): row dx*16+co = w_hi[co, c*8+e, dy, dx], row 48+dx*16+co = w_lo"""
+    cout = w_oihw.shape[0]
+    assert w_oihw.shape[1] == 16 and cout <= 16
+    s = h2_host_scale(w_oihw)
+    hi, lo = _hi_lo(w_oihw, s)
+    t = torch.zeros(3, 2, 96, 8, device=w_oihw.device, dtype=torch.float16)
+    for dy in range(3):
+        for c in range(2):
+            for dx in range(3):
+                t[dy, c, dx * 16:dx * 16 + cout, :] = hi[:, c * 8:c * 8 + 8, dy, dx]
+                t[dy, c, 48 + dx * 16:48 + dx * 16 + cout, :] = lo[:, c * 8:c * 8 + 8, dy, dx]
+    return t.contiguous(), 1.0 / s
+
+
+def conv_head_h2(x_nchw: torch.Tensor, w11p, inv_s11: float, b11, w12p, inv_s12: float, b12) -> torch.Tensor:
+    """fused conv11+ReLU+conv12+ReLU+pool of the 16x encoders: image [1,3,H,W] -> H8 [2,2,H/2,W/2,8]"""
+    if x_nchw.dim() == 4:
+        x_nchw = x_nchw.squeeze(0)
+    _, H, W = x_nchw.shape
+    y = torch.empty(2, 2, H // 2, W // 2, 8, device=x_nchw.device, dtype=torch.float16)
+    check(_lib.load().wctb_conv_head_h2(_need(x_nchw), _need(w11p, torch.float16), _need(b11), float(inv_s11),
+                                        _need(w12p, torch.float16), _need(b12), float(inv_s12), _need(y, torch.float16),
+                                        H, W, _stream()), "conv_head_h2")
+    _count("conv_head_h2")
+    return y

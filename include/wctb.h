@@ -140,6 +140,14 @@ int wctb_conv3x3_h2(const void* x_h8, const void* w_packed, const float* bias, c
  * same arithmetic as wctb_conv3x3_first.  w: [tap][3][Cout] (wctb_pack_weights_fp32), Cout % 8 == 0.                   */
 int wctb_conv3x3_first_h2(const float* x_nchw, const float* w, const float* bias, void* y_h8, float* y_p4,
                           int H, int W, int Cout, void* stream);
+/* fused encoder head of the 16x nets on the h2 engine (csrc/conv_h2_fused.cu): conv11 (3 -> 16, conv0 folded) + ReLU +
+ * conv12 (16 -> 16) + ReLU + MaxPool2d(2,2) in one persistent kernel, both convs on tcgen05 with the three horizontal
+ * filter taps stacked along N; the 16-channel full-resolution activations never touch HBM.
+ * replaces: y = relu(conv11(pad(conv0(y)))); y = relu(conv12(pad(y))); y = pool(y)      (model_cd.py:725-728)
+ * w11_packed: [2][2 k-chunks][96][8] fp16, w12_packed: [3 dy][2 k-chunks][96][8] fp16 (rows dx*16+co: hi, 48+dx*16+co: lo)
+ * of w * s with a host-chosen power-of-two s; inv_s = 1/s.  Built by ops.pack_head_h2_w11 / ops.pack_dx_h2.  y: H8 16 ch. */
+int wctb_conv_head_h2(const float* x_nchw, const void* w11_packed, const float* b11, float inv_s11,
+                      const void* w12_packed, const float* b12, float inv_s12, void* y_h8, int H, int W, void* stream);
 /* layout conversion: NCHW fp32 <-> H8, fp32 P4 -> H8 */
 int wctb_nchw_to_h8(const float* src_nchw, void* dst_h8, int C, int H, int W, void* stream);
 int wctb_h8_to_nchw(const void* src_h8, float* dst_nchw, int C, int H, int W, void* stream);

@@ -148,6 +148,34 @@ def test_conv_h2_large_values_saturate_not_nan():
     assert torch.isfinite(back).all() and back.max().item() >= 65504.0
 
 
+# ------------------------------------------------------------------ fused head (conv11 + conv12 + pool, dx-stacked, block-pipelined)
+@pytest.mark.parametrize("H,W", [(2, 2), (4, 6), (16, 28), (33, 29), (37, 131), (64, 56), (100, 30), (161, 200), (300, 700),
+                                 (31, 57), (32, 58), (65, 85)])
+def test_fused_head_h2_vs_fp64_and_two_layer_path(H, W):
+    g = torch.Generator().manual_seed(H * 7 + W)
+    x = torch.rand(1, 3, H, W, generator=g)
+    w11 = torch.randn(16, 3, 3, 3, generator=g) * 40.0             # conv0-folded magnitudes (x255)
+    b11 = torch.randn(16, generator=g) * 5.0
+    w12 = torch.randn(16, 16, 3, 3, generator=g) * (2.0 / 144) ** 0.5
+    b12 = torch.randn(16, generator=g) * 0.1
+    mid = F.relu(F.conv2d(F.pad(x.double(), (1, 1, 1, 1), mode="reflect"), w11.double(), b11.double()))
+    ref = F.max_pool2d(F.relu(F.conv2d(F.pad(mid, (1, 1, 1, 1), mode="reflect"), w12.double(), b12.double())), 2, 2)
+    w11p, is11 = ops.pack_head_h2_w11(w11.to(DEV))
+    w12p, is12 = ops.pack_dx_h2(w12.to(DEV))
+    y = ops.conv_head_h2(x.to(DEV), w11p, is11, b11.to(DEV), w12p, is12, b12.to(DEV))
+    torch.cuda.synchronize()
+    got = ops.h8_to_nchw(y, 16).cpu().double()
+    assert got.shape == ref.shape
+    scale = max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-5 * scale, "fused head vs fp64: max err %g (scale %g)" % (err, scale)
+    # the unfused h2 path (fp32 FFMA first layer -> generic h2 conv + pool) computes the same thing
+    y1, _ = ops.conv3x3_first_h2(x.to(DEV), ops.pack_weights(w11.to(DEV), ops.ENGINE_FP32), b11.to(DEV), 16)
+    wp, ws = ops.pack_weights_h2(w12.to(DEV))
+    y2, _ = ops.conv3x3_h2(y1, wp, ws, b12.to(DEV), 16, 16, ops.EPI_POOL2)
+    assert (ops.h8_to_nchw(y2, 16).cpu().double() - got).abs().max().item() <= 1e-5 * scale
+
+
 # ------------------------------------------------------------------ modules with the shipped weights
 def _wct16(precision):
     P.set_precision(precision)
