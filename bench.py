@@ -141,65 +141,109 @@ def usable_cpus():
     return n
 
 
-def best_cpu_threads(limit):
+def _cpu_impl():
+    """-> (kind, stylize(content, style)): the reference's own modules staged under oracle/_ref when present ("reference"),
+    else the oracle port of the same algorithm ("port")."""
+    from oracle import ref_runner as R
+    if R.available():
+        w = R.make_wct("16x")
+        return "reference", (lambda c, s: R.stylize(w, c, s))
+    from oracle import wct_oracle as O
+    w = O.load_weights_npz(WEIGHTS)
+    return "port", (lambda c, s: O.stylize(w, "16x", c, s))
+
+
+def best_cpu_threads(limit, fn):
     """oneDNN/MKL on a many-core host can be SLOWER with every thread (measured: 128 threads 23x slower than 8 on a
     cfg2-sized pass); probe a short pass at a few thread counts and keep the fastest -- the baseline gets the best
     setting the host offers, and the count is reported."""
-    from oracle import wct_oracle as O
-    w = O.load_weights_npz(WEIGHTS)
     g = torch.Generator().manual_seed(1)
     c, s = torch.rand(1, 3, 256, 256, generator=g), torch.rand(1, 3, 192, 192, generator=g)
     best, best_t = 1, None
     cand = sorted({t for t in (4, 8, 16, 32, 64, limit) if t <= limit})
     for t in cand:
         torch.set_num_threads(t)
-        O.stylize(w, "16x", c, s)
+        fn(c, s)
         t0 = time.perf_counter()
-        O.stylize(w, "16x", c, s)
+        fn(c, s)
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = t, dt
     return best
 
 
-def cpu_reference_pass(Hc, Wc, Hs, Ws, steps, warmup, threads):
-    """Time the CPU oracle (reference algorithm: torch-cpu fp32 convs, fp64 SVD transform) -> (MP/s, ms/step)."""
-    from oracle import wct_oracle as O
+def cpu_sample_shape(Hc, Wc, Hs, Ws, target_mp=0.52):
+    """bounded sample of a workload: the top-left crop of the SAME synthetic pair, same aspect ratios and same
+    content : style area ratio, about `target_mp` content megapixels (multiples of 16 px)"""
+    f = min(1.0, (target_mp * 1e6 / (Hc * Wc)) ** 0.5)
+    r16 = lambda v: max(32, int(v * f / 16 + 0.5) * 16)
+    return r16(Hc), r16(Wc), r16(Hs), r16(Ws)
+
+
+def cpu_reference_pass(fn, Hc, Wc, Hs, Ws, steps, warmup, threads, crop=None):
+    """Time the CPU path (reference algorithm: torch-cpu fp32 convs, fp64 SVD transform) -> (MP/s, ms/step).
+    crop = (hc, wc, hs, ws): every step stylizes that crop of the (Hc x Wc, Hs x Ws) seed-0 pair."""
     torch.set_num_threads(threads)
-    w = O.load_weights_npz(WEIGHTS)
     g = torch.Generator().manual_seed(0)
     content, style = torch.rand(1, 3, Hc, Wc, generator=g), torch.rand(1, 3, Hs, Ws, generator=g)
+    if crop is not None:
+        content, style = content[..., :crop[0], :crop[1]].contiguous(), style[..., :crop[2], :crop[3]].contiguous()
     for _ in range(warmup):
-        O.stylize(w, "16x", content, style)
+        fn(content, style)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.stylize(w, "16x", content, style)
+        fn(content, style)
         ts.append(time.perf_counter() - t0)
     t = sum(ts) / len(ts)
-    return Hc * Wc / 1e6 / t, t * 1e3
+    return content.shape[-2] * content.shape[-1] / 1e6 / t, t * 1e3
+
+
+def workload(cfg, N):
+    if cfg == "weak":
+        (Hc, Wc), (Hs, Ws) = (2160, 3840 * N), (2000, 2000)
+        return Hc, Wc, Hs, Ws, ("weak-scaling family of configs[2]: %dx%d content (3840 px of width per GPU) / %dx%d style, --mode 16x --UHD"
+                                % (Wc, Hc, Ws, Hs))
+    (Hc, Wc), (Hs, Ws) = CONFIGS[cfg]
+    return Hc, Wc, Hs, Ws, "BASELINE configs %s: %dx%d content / %dx%d style, --mode 16x%s" % (cfg, Wc, Hc, Ws, Hs, "" if cfg == "cfg2" else " --UHD")
+
+
+def default_config(N):
+    return "cfg3" if N == 1 else "weak"
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU path (oracle/_ref when staged, else the port) on the host cores, SAME workload
+    name / metric / unit / steps / warmup as the repo arm; every step is a bounded sample of that workload (a crop of the
+    same seed-0 pair with the same aspect and content:style ratio), because a full cfg3 pass costs ~25 s of host time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = best_cpu_threads(usable_cpus())
-    (Hc, Wc), (Hs, Ws) = CONFIGS["cfg2"]          # bounded sample of the workload: cfg2-sized pair per step
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    mps, ms = cpu_reference_pass(Hc, Wc, Hs, Ws, steps, warmup, threads)
-    sample = "%dx%d content / %dx%d style, 16x, 5 stages, %d timed passes" % (Wc, Hc, Ws, Hs, steps)
-    print(json.dumps({
+    N = args.gpus
+    cfg = args.config or default_config(N)
+    Hc, Wc, Hs, Ws, wl = workload(cfg, N)
+    kind, fn = _cpu_impl()
+    threads = best_cpu_threads(usable_cpus(), fn)
+    crop = cpu_sample_shape(Hc, Wc, Hs, Ws)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    mps, ms = cpu_reference_pass(fn, Hc, Wc, Hs, Ws, steps, warmup, threads, crop)
+    sample = ("top-left %dx%d content / %dx%d style crop of the workload's seed-0 pair per step, 16x, 5 stages, %d warm-up + %d timed steps"
+              % (crop[1], crop[0], crop[3], crop[2], warmup, steps))
+    line = {
         "impl": "reference", "metric": "megapixels/sec end-to-end WCT stylize (16x VGG, UHD)", "value": round(mps, 4),
-        "unit": "MP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 convs + f64 transform",
-        "data": "synthetic torch.rand images (seed 0), shipped 16x weights",
-        "config": {"workload": "CPU oracle (port of the reference torch path) on a bounded sample: " + sample,
-                   "mode": "16x", "alpha": 1.0},
-        "cpu_baseline": {"value": round(mps, 4), "unit": "MP/s", "cores": threads, "host_cpus": usable_cpus(), "kind": "port",
+        "unit": "MP/s", "n_gpus": N, "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 convs + f64 transform (torch-cpu)",
+        "data": "synthetic torch.rand images (seed 0); shipped 16x weights",
+        "config": {"workload": wl, "mode": "16x", "alpha": 1.0, "stages": 5, "parallelism": "host threads",
+                   "sample": sample},
+        "cpu_baseline": {"value": round(mps, 4), "unit": "MP/s", "cores": threads, "host_cpus": usable_cpus(), "kind": kind,
                          "sample": sample + " (thread count = fastest of a probe over 4..all usable cpus)"},
         "e2e": {"value": round(mps, 4), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0}
+    if args.full_pass:
+        fmps, fms = cpu_reference_pass(fn, Hc, Wc, Hs, Ws, 1, 0, threads, None)
+        line["full_workload_pass"] = {"value": round(fmps, 4), "unit": "MP/s", "ms": round(fms, 1), "note": "ONE untimed-warm-up-free pass over the whole workload"}
+    print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -215,6 +259,7 @@ def main():
                          "contract); tf32 = single-pass TF32 (lossy: misses the contract on noise-like inputs); fp32 = CUDA cores")
     ap.add_argument("--fold", type=int, default=1, help="fold the WCT matrix into the decoder's first conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-pass", action="store_true", help="--impl reference: also time ONE pass over the whole workload (cfg3: ~25 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -235,13 +280,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     N = world
 
-    cfg = args.config or ("cfg3" if N == 1 else "weak")
-    if cfg == "weak":
-        (Hc, Wc), (Hs, Ws) = (2160, 3840 * N), (2000, 2000)
-        wl = "weak-scaling family of configs[2]: %dx%d content (3840 px of width per GPU) / %dx%d style, --mode 16x --UHD" % (Wc, Hc, Ws, Hs)
-    else:
-        (Hc, Wc), (Hs, Ws) = CONFIGS[cfg]
-        wl = "BASELINE configs %s: %dx%d content / %dx%d style, --mode 16x%s" % (cfg, Wc, Hc, Ws, Hs, "" if cfg == "cfg2" else " --UHD")
+    cfg = args.config or default_config(N)
+    Hc, Wc, Hs, Ws, wl = workload(cfg, N)
 
     P.set_precision(args.precision)
     wct = P.WCT(SimpleNamespace(mode="16x", numpy=False))
@@ -323,11 +363,13 @@ def main():
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline and N == 1:
-        threads = best_cpu_threads(usable_cpus())
-        (bh, bw), (sh_, sw_) = CONFIGS["cfg2"]
-        mps, _ = cpu_reference_pass(bh, bw, sh_, sw_, 2, 1, threads)
-        cpu_base = {"value": round(mps, 4), "unit": "MP/s", "cores": threads, "host_cpus": usable_cpus(), "kind": "port",
-                    "sample": "%dx%d content / %dx%d style (BASELINE configs[1]), 16x, 5 stages, 1 warm-up + 2 timed passes of the CPU oracle" % (bw, bh, sw_, sh_)}
+        kind, fn = _cpu_impl()
+        threads = best_cpu_threads(usable_cpus(), fn)
+        crop = cpu_sample_shape(Hc, Wc, Hs, Ws)
+        mps, _ = cpu_reference_pass(fn, Hc, Wc, Hs, Ws, 6, 1, threads, crop)
+        cpu_base = {"value": round(mps, 4), "unit": "MP/s", "cores": threads, "host_cpus": usable_cpus(), "kind": kind,
+                    "sample": "top-left %dx%d content / %dx%d style crop of this workload's seed-0 pair, 16x, 5 stages, 1 warm-up + 6 timed passes of %s"
+                              % (crop[1], crop[0], crop[3], crop[2], "the reference's own modules (oracle/_ref)" if kind == "reference" else "the CPU oracle port")}
 
     # ---- extra (not part of the contract keys): the same end-to-end step through the image-I/O row -- 8-bit interleaved
     # RGB pinned host buffers up, ToTensor on the device, stylize, save_image quantisation on the device, 8-bit image down

@@ -34,6 +34,7 @@ SIGNATURES = {
     "wctb_conv3x3_h2": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "wctb_conv3x3_first_h2": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "wctb_conv_head_h2": [_p, _p, _p, ctypes.c_float, _p, _p, ctypes.c_float, _p, _i, _i, _p],
+    "wctb_conv_tail_h2": [_p, _p, _p, ctypes.c_float, _p, _p, ctypes.c_float, _p, _i, _i, _i, _p],
     "wctb_nchw_to_h8": [_p, _p, _i, _i, _i, _p],
     "wctb_h8_to_nchw": [_p, _p, _i, _i, _i, _p],
     "wctb_p4_to_h8": [_p, _p, _i, _i, _i, _p],

@@ -30,27 +30,32 @@ using namespace wctb_umma;
 
 constexpr int FP = 32;                              // tile pitch (pixels) = warp width
 constexpr int F_TW = 28;                            // valid output columns after two chained 3x3 convs (32 -> 30 -> 28)
-constexpr int F_TH = 32;                            // output rows per tile
-constexpr int F_NB2 = F_TH / 4;                     // second-conv blocks per full tile
-constexpr int F_NB1 = F_NB2 + 1;                    // first-conv blocks per full tile (rows -1 .. 34 of the tile)
 constexpr int F_ROW = FP * 16;                      // bytes of one 8-channel row
-constexpr int F_MID_ROWS = 4 * F_NB1;               // 36
-constexpr int F_PLANE = F_MID_ROWS * F_ROW;         // 18432
-constexpr int F_MID_BYTES = 4 * F_PLANE;            // planes hi0, lo0, hi1, lo1
 constexpr int F_WB = 2 * 96 * 16;                   // one B tile: [2 k-chunks][96 rows][16 B]
 constexpr int F_ACC1 = 0, F_ACC2 = 192;             // TMEM column bases of the two rings (2 slots x 96 columns each)
-
-// barrier slots
+// barrier slots (B_MID_READY is followed by 2 x NB1 barriers)
 enum { B_WFULL = 0, B_IN_READY = 1, B_IN_FREE = 3, B_A1_FULL = 5, B_A1_EMPTY = 7, B_A2_FULL = 9, B_A2_EMPTY = 11, B_MID_FREE = 13,
-       B_MID_READY = 15, B_COUNT = 15 + 2 * F_NB1 };
+       B_MID_READY = 15 };
+
+template <int NB2_>
+struct FCfg {
+  static constexpr int NB2 = NB2_;                  // second-conv blocks (4 rows x 32 positions) per full tile
+  static constexpr int NB1 = NB2_ + 1;              // first-conv blocks per full tile (tile rows -1 .. 4*NB2 + 2)
+  static constexpr int TH = 4 * NB2_;               // output rows per tile
+  static constexpr int MID_ROWS = 4 * NB1;
+  static constexpr int PLANE = MID_ROWS * F_ROW;
+  static constexpr int MID_BYTES = 4 * PLANE;       // planes hi0, lo0, hi1, lo1
+  static constexpr int NBAR = B_MID_READY + 2 * NB1;
+};
 
 struct FTile { int x0, ya, nb2, nb1; };
+template <class C>
 __device__ __forceinline__ FTile f_tile(int tile, int tiles_x, int H) {
   FTile t;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   t.x0 = tx * F_TW;
-  t.ya = ty * F_TH;
-  const int rows = min(F_TH, H - t.ya);
+  t.ya = ty * C::TH;
+  const int rows = min(C::TH, H - t.ya);
   t.nb2 = (rows + 3) >> 2;
   t.nb1 = t.nb2 + 1;
   return t;
@@ -81,38 +86,42 @@ __device__ __forceinline__ void f_reduce_dx(uint32_t taddr, float* out) {
 
 // second conv of a chain (16 -> 16 or 16 -> 3 padded), dx-stacked: block k of the operand tile `mid` ([hi0, lo0, hi1, lo1]
 // planes, pitch 32) -> TMEM columns [tacc, tacc + 96).  wsm: [3 dy][2 chunks][96 rows][16 B] (rows 0..47 hi, 48..95 lo).
+template <int PLANE>
 __device__ __forceinline__ void f_issue_conv16(uint32_t mid, uint32_t wsm, uint32_t tacc, int k) {
   constexpr uint32_t id96 = umma_idesc_f16(96), id48 = umma_idesc_f16(48);
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
     const uint32_t a = mid + (uint32_t)(4 * k + dy) * F_ROW;
     const uint64_t bd = umma_desc(wsm + (uint32_t)dy * F_WB, 96u * 16u, 128u);
-    umma_f16(tacc, umma_desc(a, 2u * F_PLANE, 128u), bd, id96, dy > 0 ? 1u : 0u);          // hi x [w_hi | w_lo]
-    umma_f16(tacc, umma_desc(a + F_PLANE, 2u * F_PLANE, 128u), bd, id48, 1u);              // lo x  w_hi
+    umma_f16(tacc, umma_desc(a, 2u * PLANE, 128u), bd, id96, dy > 0 ? 1u : 0u);            // hi x [w_hi | w_lo]
+    umma_f16(tacc, umma_desc(a + PLANE, 2u * PLANE, 128u), bd, id48, 1u);                  // lo x  w_hi
   }
 }
 
 // write 16 channels of one position into the operand tile (planes hi0, lo0, hi1, lo1)
+template <int PLANE>
 __device__ __forceinline__ void f_store_mid(uint8_t* mid, int row, int col, const float* v) {
   uint4 hi, lo;
   uint4* p = reinterpret_cast<uint4*>(mid + (size_t)row * F_ROW) + col;
   split8(v, hi, lo);
   p[0] = hi;
-  p[F_PLANE / 16] = lo;
+  p[PLANE / 16] = lo;
   split8(v + 8, hi, lo);
-  p[2 * (F_PLANE / 16)] = hi;
-  p[3 * (F_PLANE / 16)] = lo;
+  p[2 * (PLANE / 16)] = hi;
+  p[3 * (PLANE / 16)] = lo;
 }
+template <int PLANE>
 __device__ __forceinline__ void f_copy_mid_row(uint8_t* mid, int dst_row, int src_row, int lane) {
 #pragma unroll
   for (int pl = 0; pl < 4; ++pl) {
-    uint4* base = reinterpret_cast<uint4*>(mid + (size_t)pl * F_PLANE);
+    uint4* base = reinterpret_cast<uint4*>(mid + (size_t)pl * PLANE);
     base[dst_row * FP + lane] = base[src_row * FP + lane];
   }
 }
 
 // epilogue of the FIRST conv of a chain: accumulator block j -> rows 4j..4j+3 of the operand tile, with the reflection
 // of the intermediate at true image borders (columns by shuffle before the store, rows by a copy after a group barrier)
+template <class C>
 __device__ __forceinline__ void f_first_epilogue(uint32_t tacc_q, uint8_t* mid, const FTile& t, int j, int q, int lane,
                                                  int H, int W, const float* bias, float inv_s, uint64_t* acc_empty) {
   float v[16];
@@ -134,15 +143,15 @@ __device__ __forceinline__ void f_first_epilogue(uint32_t tacc_q, uint8_t* mid, 
     for (int i = 0; i < 16; ++i) v[i] = __shfl_sync(0xffffffffu, v[i], src);
   }
   const int row = 4 * j + q;
-  f_store_mid(mid, row, lane, v);
+  f_store_mid<C::PLANE>(mid, row, lane, v);
   // tile row r <-> gy = ya - 1 + r.  gy = -1 takes row gy = 1, gy = H takes row gy = H - 2
   const bool top = (t.ya == 0) && (j == 0);
   const int rh = H - t.ya + 1;
-  const bool bottom = (H - t.ya <= F_TH) && (j == (rh >> 2));
+  const bool bottom = (H - t.ya <= C::TH) && (j == (rh >> 2));
   if (top || bottom) {
     asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (top && q == 0) f_copy_mid_row(mid, 0, 2, lane);
-    if (bottom && q == (rh & 3)) f_copy_mid_row(mid, rh, rh - 2, lane);
+    if (top && q == 0) f_copy_mid_row<C::PLANE>(mid, 0, 2, lane);
+    if (bottom && q == (rh & 3)) f_copy_mid_row<C::PLANE>(mid, rh, rh - 2, lane);
   }
 }
 
@@ -157,23 +166,24 @@ struct HeadH2Args {
   uint4* y;             // H8 [2 chunks][2][H/2][W/2] 16-byte units
   int H, W, tiles_x, ntiles;
 };
+using HC = FCfg<8>;                                           // head tile: 32 rows x 28 columns
 constexpr int HD_IN_ROWS = 40;                                // 36 image rows + overrun of the last block's second K chunk
 constexpr int HD_IN_BYTES = HD_IN_ROWS * F_ROW;               // RGB0 hi | RGB0 lo, 16 B per pixel
 constexpr int HD_OFF_MID = 2 * HD_IN_BYTES;
-constexpr int HD_OFF_W11 = HD_OFF_MID + 2 * F_MID_BYTES;
+constexpr int HD_OFF_W11 = HD_OFF_MID + 2 * HC::MID_BYTES;
 constexpr int HD_OFF_W12 = HD_OFF_W11 + 2 * F_WB;
 constexpr int HD_OFF_POOL = HD_OFF_W12 + 3 * F_WB;
 constexpr int HD_POOL_BYTES = 2 * 2 * 32 * 20 * 4;            // [parity][row pair][lane][16 + 4 pad] floats
 constexpr int HD_OFF_BAR = HD_OFF_POOL + HD_POOL_BYTES;
 constexpr int HD_SMEM = HD_OFF_BAR + 512 + 128;
-static_assert(B_COUNT * 8 + 8 <= 512, "barrier area");
+static_assert(HC::NBAR * 8 + 8 <= 512, "barrier area");
 static_assert(HD_SMEM <= 227 * 1024, "shared memory budget");
 
 __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HD_OFF_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + HC::NBAR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = h.H, W = h.W;
   const int ntl = (h.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
@@ -181,11 +191,11 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
   if (threadIdx.x == 0) {
     mbar_init(bars + B_WFULL, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bars + B_IN_READY + s, 128); mbar_init(bars + B_IN_FREE + s, 1);
+      mbar_init(bars + B_IN_READY + s, 4);   mbar_init(bars + B_IN_FREE + s, 1);
       mbar_init(bars + B_A1_FULL + s, 1);    mbar_init(bars + B_A1_EMPTY + s, 4);
       mbar_init(bars + B_A2_FULL + s, 1);    mbar_init(bars + B_A2_EMPTY + s, 4);
       mbar_init(bars + B_MID_FREE + s, 1);
-      for (int j = 0; j < F_NB1; ++j) mbar_init(bars + B_MID_READY + s * F_NB1 + j, 128);
+      for (int j = 0; j < HC::NB1; ++j) mbar_init(bars + B_MID_READY + s * HC::NB1 + j, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
       mbar_wait(bars + B_WFULL, 0);
       int i1 = 0, j1 = 0, i2 = 0, k2 = 0;          // cursors: (local tile, block) of the next first- / second-conv block
       uint32_t g1 = 0, g2 = 0, base1 = 0;          // global block counters; first-conv blocks issued before tile i2
-      FTile t1 = f_tile((int)blockIdx.x, h.tiles_x, H), t2 = t1;
+      FTile t1 = f_tile<HC>((int)blockIdx.x, h.tiles_x, H), t2 = t1;
       while (i2 < ntl) {
         // second-conv block (i2, k2) reads first-conv blocks 0..k2+1 of its tile; stay one more block ahead
         const uint32_t need = base1 + (uint32_t)k2 + 2u;
@@ -231,17 +241,17 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
             tc_commit(bars + B_IN_FREE + (i1 & 1));
             j1 = 0;
             ++i1;
-            if (i1 < ntl) t1 = f_tile((int)blockIdx.x + i1 * (int)gridDim.x, h.tiles_x, H);
+            if (i1 < ntl) t1 = f_tile<HC>((int)blockIdx.x + i1 * (int)gridDim.x, h.tiles_x, H);
           }
         }
         {
-          uint64_t* ready = bars + B_MID_READY + (i2 & 1) * F_NB1;
+          uint64_t* ready = bars + B_MID_READY + (i2 & 1) * HC::NB1;
           mbar_wait(ready + k2, (i2 >> 1) & 1);
           mbar_wait(ready + k2 + 1, (i2 >> 1) & 1);
           const uint32_t slot = g2 & 1u;
           mbar_wait(bars + B_A2_EMPTY + slot, ((g2 >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          f_issue_conv16(smem_u32(smem + HD_OFF_MID + (i2 & 1) * F_MID_BYTES), w12s, tmem_base + F_ACC2 + slot * 96u, k2);
+          f_issue_conv16<HC::PLANE>(smem_u32(smem + HD_OFF_MID + (i2 & 1) * HC::MID_BYTES), w12s, tmem_base + F_ACC2 + slot * 96u, k2);
           tc_commit(bars + B_A2_FULL + slot);
           ++g2;
           if (++k2 == t2.nb2) {
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
             base1 += (uint32_t)t2.nb1;
             k2 = 0;
             ++i2;
-            if (i2 < ntl) t2 = f_tile((int)blockIdx.x + i2 * (int)gridDim.x, h.tiles_x, H);
+            if (i2 < ntl) t2 = f_tile<HC>((int)blockIdx.x + i2 * (int)gridDim.x, h.tiles_x, H);
           }
         }
       }
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
     const long long HWo = (long long)Ho * Wo;
     uint32_t g2 = 0;
     for (int i = 0; i < ntl; ++i) {
-      const FTile t = f_tile((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      const FTile t = f_tile<HC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       for (int k = 0; k < t.nb2; ++k, ++g2) {
         const uint32_t slot = g2 & 1u;
         mbar_wait(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
@@ -319,16 +329,17 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
     for (int i = 0; i < 16; ++i) bv[i] = __ldg(h.b11 + i);
     uint32_t g1 = 0;
     for (int i = 0; i < ntl; ++i) {
-      const FTile t = f_tile((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
-      uint8_t* mid = smem + HD_OFF_MID + (i & 1) * F_MID_BYTES;
+      const FTile t = f_tile<HC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      uint8_t* mid = smem + HD_OFF_MID + (i & 1) * HC::MID_BYTES;
       if (i >= 2) mbar_wait(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);      // conv12 of tile i-2 has read this buffer
       for (int j = 0; j < t.nb1; ++j, ++g1) {
         const uint32_t slot = g1 & 1u;
         mbar_wait(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
         tc_fence_after();
-        f_first_epilogue(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s11, bars + B_A1_EMPTY + slot);
-        fence_async_smem();
-        mbar_arrive(bars + B_MID_READY + (i & 1) * F_NB1 + j);
+        f_first_epilogue<HC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s11, bars + B_A1_EMPTY + slot);
+        fence_async_smem();                         // every writer: generic-proxy stores -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + B_MID_READY + (i & 1) * HC::NB1 + j);
       }
     }
   } else {
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
     for (int b = 0; b < 2; ++b)      // rows 36..39 are only read against zero weights / by garbage positions: keep them finite
       reinterpret_cast<uint4*>(smem + b * HD_IN_BYTES)[(36 + pw) * FP + lane] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = 0; i < ntl; ++i) {
-      const FTile t = f_tile((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      const FTile t = f_tile<HC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       uint4* in = reinterpret_cast<uint4*>(smem + (i & 1) * HD_IN_BYTES);
       if (i >= 2) mbar_wait(bars + B_IN_FREE + (i & 1), ((i - 2) >> 1) & 1);
       const int gx = wctb_reflect(t.x0 - 2 + lane, W);
@@ -356,7 +367,199 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
         in[(pw + 4 * k) * FP + lane] = make_uint4(h0 | (h1 << 16), h2, l0 | (l1 << 16), l2);
       }
       fence_async_smem();
-      mbar_arrive(bars + B_IN_READY + (i & 1));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + B_IN_READY + (i & 1));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ====================================================================================== fused decoder tail
+struct TailH2Args {
+  const uint4* x;       // H8 16 ch: [4 planes hi0, lo0, hi1, lo1][Hs][Ws] 16-byte units; (Hs, Ws) = (H, W) >> ups
+  const __half* w12;    // [3 dy][2 chunks][96][8]
+  const __half* w11;    // [3 dy][2 chunks][96][8], output channels 3..15 zero
+  const float* b12;     // [16]
+  const float* b11;     // [3]
+  float inv_s12, inv_s11;
+  float* img;           // [3][H][W]
+  int H, W, ups, tiles_x, ntiles;
+};
+using TC = FCfg<4>;                                           // tail tile: 16 rows x 28 columns
+constexpr int TL_IN_ROWS = 4 * TC::NB1 + 2;                   // 22 input rows (tile rows -2 .. 19)
+constexpr int TL_IN_PLANE = TL_IN_ROWS * F_ROW;
+constexpr int TL_IN_BYTES = 4 * TL_IN_PLANE;
+constexpr int TL_OFF_MID = 2 * TL_IN_BYTES;
+constexpr int TL_OFF_W12 = TL_OFF_MID + 2 * TC::MID_BYTES;
+constexpr int TL_OFF_W11 = TL_OFF_W12 + 3 * F_WB;
+constexpr int TL_OFF_BAR = TL_OFF_W11 + 3 * F_WB;
+constexpr int TL_SMEM = TL_OFF_BAR + 512 + 128;
+static_assert(TC::NBAR * 8 + 8 <= 512, "barrier area");
+static_assert(TL_SMEM <= 227 * 1024, "shared memory budget");
+
+__global__ void __launch_bounds__(448, 1) conv_tail_h2_kernel(const TailH2Args h) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TL_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC::NBAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = h.H, W = h.W;
+  const int ntl = (h.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bars + B_WFULL, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bars + B_IN_READY + s, 4);   mbar_init(bars + B_IN_FREE + s, 1);
+      mbar_init(bars + B_A1_FULL + s, 1);    mbar_init(bars + B_A1_EMPTY + s, 4);
+      mbar_init(bars + B_A2_FULL + s, 1);    mbar_init(bars + B_A2_EMPTY + s, 4);
+      mbar_init(bars + B_MID_FREE + s, 1);
+      for (int j = 0; j < TC::NB1; ++j) mbar_init(bars + B_MID_READY + s * TC::NB1 + j, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bars + B_WFULL, 6u * F_WB);
+      bulk_g2s(smem_u32(smem + TL_OFF_W12), h.w12, 3u * F_WB, bars + B_WFULL);
+      bulk_g2s(smem_u32(smem + TL_OFF_W11), h.w11, 3u * F_WB, bars + B_WFULL);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer (same schedule as the head) ===========================
+    if (elect_one()) {
+      const uint32_t w12s = smem_u32(smem + TL_OFF_W12), w11s = smem_u32(smem + TL_OFF_W11);
+      mbar_wait(bars + B_WFULL, 0);
+      int i1 = 0, j1 = 0, i2 = 0, k2 = 0;
+      uint32_t g1 = 0, g2 = 0, base1 = 0;
+      FTile t1 = f_tile<TC>((int)blockIdx.x, h.tiles_x, H), t2 = t1;
+      while (i2 < ntl) {
+        const uint32_t need = base1 + (uint32_t)k2 + 2u;
+        while (i1 < ntl && g1 < need + 1u) {
+          if (j1 == 0) mbar_wait(bars + B_IN_READY + (i1 & 1), (i1 >> 1) & 1);
+          const uint32_t slot = g1 & 1u;
+          mbar_wait(bars + B_A1_EMPTY + slot, ((g1 >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          f_issue_conv16<TL_IN_PLANE>(smem_u32(smem + (i1 & 1) * TL_IN_BYTES), w12s, tmem_base + F_ACC1 + slot * 96u, j1);
+          tc_commit(bars + B_A1_FULL + slot);
+          ++g1;
+          if (++j1 == t1.nb1) {
+            tc_commit(bars + B_IN_FREE + (i1 & 1));
+            j1 = 0;
+            ++i1;
+            if (i1 < ntl) t1 = f_tile<TC>((int)blockIdx.x + i1 * (int)gridDim.x, h.tiles_x, H);
+          }
+        }
+        {
+          uint64_t* ready = bars + B_MID_READY + (i2 & 1) * TC::NB1;
+          mbar_wait(ready + k2, (i2 >> 1) & 1);
+          mbar_wait(ready + k2 + 1, (i2 >> 1) & 1);
+          const uint32_t slot = g2 & 1u;
+          mbar_wait(bars + B_A2_EMPTY + slot, ((g2 >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          f_issue_conv16<TC::PLANE>(smem_u32(smem + TL_OFF_MID + (i2 & 1) * TC::MID_BYTES), w11s, tmem_base + F_ACC2 + slot * 96u, k2);
+          tc_commit(bars + B_A2_FULL + slot);
+          ++g2;
+          if (++k2 == t2.nb2) {
+            tc_commit(bars + B_MID_FREE + (i2 & 1));
+            base1 += (uint32_t)t2.nb1;
+            k2 = 0;
+            ++i2;
+            if (i2 < ntl) t2 = f_tile<TC>((int)blockIdx.x + i2 * (int)gridDim.x, h.tiles_x, H);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // =========================== epilogue of conv11: 3 channels -> NCHW fp32 ===========================
+    const int q = warp & 3;
+    const uint32_t tq = tmem_base + F_ACC2 + ((uint32_t)(32 * q) << 16);
+    const float b0 = __ldg(h.b11), b1 = __ldg(h.b11 + 1), b2 = __ldg(h.b11 + 2);
+    const long long HW = (long long)H * W;
+    uint32_t g2 = 0;
+    for (int i = 0; i < ntl; ++i) {
+      const FTile t = f_tile<TC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      for (int k = 0; k < t.nb2; ++k, ++g2) {
+        const uint32_t slot = g2 & 1u;
+        mbar_wait(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
+        tc_fence_after();
+        // channels 0..2 of each dx group: main at dx*16, minor at 48 + dx*16
+        float m[6][4];
+        const uint32_t ta = tq + slot * 96u;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { tmem_ld4(ta + 16u * d, m[d]); tmem_ld4(ta + 48u + 16u * d, m[3 + d]); }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + B_A2_EMPTY + slot);
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[c] = (m[0][c] + m[3][c]) + __shfl_down_sync(0xffffffffu, m[1][c] + m[4][c], 1) + __shfl_down_sync(0xffffffffu, m[2][c] + m[5][c], 2);
+        const int gy = t.ya + 4 * k + q, gx = t.x0 + lane;
+        if (lane < F_TW && gy < H && gx < W) {
+          const long long o = (long long)gy * W + gx;
+          h.img[o] = wctb_relu(fmaf(v[0], h.inv_s11, b0));
+          h.img[HW + o] = wctb_relu(fmaf(v[1], h.inv_s11, b1));
+          h.img[2 * HW + o] = wctb_relu(fmaf(v[2], h.inv_s11, b2));
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // =========================== epilogue of conv12 -> conv11 operand tile ===========================
+    const int q = warp & 3;
+    const uint32_t tq = tmem_base + F_ACC1 + ((uint32_t)(32 * q) << 16);
+    float bv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bv[i] = __ldg(h.b12 + i);
+    uint32_t g1 = 0;
+    for (int i = 0; i < ntl; ++i) {
+      const FTile t = f_tile<TC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      uint8_t* mid = smem + TL_OFF_MID + (i & 1) * TC::MID_BYTES;
+      if (i >= 2) mbar_wait(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);
+      for (int j = 0; j < t.nb1; ++j, ++g1) {
+        const uint32_t slot = g1 & 1u;
+        mbar_wait(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
+        tc_fence_after();
+        f_first_epilogue<TC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s12, bars + B_A1_EMPTY + slot);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + B_MID_READY + (i & 1) * TC::NB1 + j);
+      }
+    }
+  } else {
+    // =========================== input loader: (up-sampled) H8 tile, reflection resolved in the source address ===========================
+    const int pw = warp - 10;
+    const int Hs = H >> h.ups, Ws = W >> h.ups;
+    const long long HWs = (long long)Hs * Ws;
+    for (int i = 0; i < ntl; ++i) {
+      const FTile t = f_tile<TC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
+      uint4* in = reinterpret_cast<uint4*>(smem + (i & 1) * TL_IN_BYTES);
+      if (i >= 2) mbar_wait(bars + B_IN_FREE + (i & 1), ((i - 2) >> 1) & 1);
+      const int sx = wctb_reflect(t.x0 - 2 + lane, W) >> h.ups;               // tile col c <-> gx = x0 - 2 + c
+      // warp pw loads plane pw: 22 rows, two batches of 11 loads in flight
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint4 v[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          const int r = half * 11 + k;                                        // tile row r <-> gy = ya - 2 + r
+          const int sy = wctb_reflect(t.ya - 2 + r, H) >> h.ups;
+          v[k] = __ldg(h.x + (long long)pw * HWs + (long long)sy * Ws + sx);
+        }
+#pragma unroll
+        for (int k = 0; k < 11; ++k) in[(pw * TL_IN_ROWS + half * 11 + k) * FP + lane] = v[k];
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + B_IN_READY + (i & 1));
     }
   }
   tc_fence_before();
@@ -377,8 +580,26 @@ extern "C" int wctb_conv_head_h2(const float* x_nchw, const void* w11_packed, co
   if (rc != WCTB_OK) return rc;
   HeadH2Args h{x_nchw, (const __half*)w11_packed, (const __half*)w12_packed, b11, b12, inv_s11, inv_s12, (uint4*)y_h8, H, W, 0, 0};
   h.tiles_x = (W + F_TW - 1) / F_TW;
-  h.ntiles = h.tiles_x * ((H + F_TH - 1) / F_TH);
+  h.ntiles = h.tiles_x * ((H + HC::TH - 1) / HC::TH);
   const int grid = h.ntiles < wctb_num_sms() ? h.ntiles : wctb_num_sms();
   conv_head_h2_kernel<<<grid, 448, HD_SMEM, (cudaStream_t)stream>>>(h);
+  WCTB_RETURN_LAUNCH();
+}
+
+extern "C" int wctb_conv_tail_h2(const void* x_h8, const void* w12_packed, const float* b12, float inv_s12,
+                                 const void* w11_packed, const float* b11, float inv_s11, float* y_nchw, int H, int W,
+                                 int upsample_input, void* stream) {
+  if (!x_h8 || !w12_packed || !b12 || !w11_packed || !b11 || !y_nchw || H < 2 || W < 2) return WCTB_E_BADARG;
+  if (upsample_input && ((H & 1) || (W & 1))) return WCTB_E_BADARG;
+  if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
+  static bool done[64] = {};
+  int rc = ensure_smem_attr(conv_tail_h2_kernel, TL_SMEM, done);
+  if (rc != WCTB_OK) return rc;
+  TailH2Args h{(const uint4*)x_h8, (const __half*)w12_packed, (const __half*)w11_packed, b12, b11, inv_s12, inv_s11, y_nchw,
+               H, W, upsample_input ? 1 : 0, 0, 0};
+  h.tiles_x = (W + F_TW - 1) / F_TW;
+  h.ntiles = h.tiles_x * ((H + TC::TH - 1) / TC::TH);
+  const int grid = h.ntiles < wctb_num_sms() ? h.ntiles : wctb_num_sms();
+  conv_tail_h2_kernel<<<grid, 448, TL_SMEM, (cudaStream_t)stream>>>(h);
   WCTB_RETURN_LAUNCH();
 }

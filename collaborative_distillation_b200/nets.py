@@ -289,10 +289,16 @@ class _Decoder(_Net):
         if y.shape[2] < 2 or y.shape[3] < 2:
             raise WctbError("feature map too small for ReflectionPad2d(1)")
         n = len(self.layers)
-        for i in range(n - 1):
+        fuse_tail = FUSE_TAIL and n >= 3 and "w_dx" in pk[n - 2] and "w_dx" in pk[n - 1]
+        for i in range(n - 2 if fuse_tail else n - 1):
             L = self.layers[i]
             epi = ops.EPI_UP2 if L["up_after"] else ops.EPI_NONE
+            if fuse_tail and i == n - 3:
+                epi = ops.EPI_NONE                       # the tail kernel upsamples while it loads
             y, _ = ops.conv3x3_h2(y, pk[i]["w"], pk[i]["ws"], pk[i]["b"], L["cin"], L["cout"], epi)
+        if fuse_tail:
+            return ops.conv_tail_h2(y, pk[n - 2]["w_dx"], pk[n - 2]["inv_s_dx"], pk[n - 2]["b"], pk[n - 1]["w_dx"], pk[n - 1]["inv_s_dx"],
+                                    pk[n - 1]["b"], bool(self.layers[n - 3]["up_after"]))
         L = self.layers[n - 1]
         return ops.conv3x3_h2(y, pk[n - 1]["w"], pk[n - 1]["ws"], pk[n - 1]["b"], L["cin"], 16, ops.EPI_NCHW3)[1]
 

@@ -514,3 +514,16 @@ def conv_head_h2(x_nchw: torch.Tensor, w11p, inv_s11: float, b11, w12p, inv_s12:
                                         H, W, _stream()), "conv_head_h2")
     _count("conv_head_h2")
     return y
+
+
+def conv_tail_h2(x_h8: torch.Tensor, w12p, inv_s12: float, b12, w11p, inv_s11: float, b11, upsample_input: bool) -> torch.Tensor:
+    """fused [nearest x2 +] conv12(16->16)+ReLU+conv11(16->3)+ReLU of the 16x decoders: H8 [2,2,h,w,8] -> image [1,3,H,W]"""
+    _need_h8(x_h8)
+    _, _, h, w, _ = x_h8.shape
+    H, W = (2 * h, 2 * w) if upsample_input else (h, w)
+    y = torch.empty(1, 3, H, W, device=x_h8.device, dtype=torch.float32)
+    check(_lib.load().wctb_conv_tail_h2(_need(x_h8, torch.float16), _need(w12p, torch.float16), _need(b12), float(inv_s12),
+                                        _need(w11p, torch.float16), _need(b11), float(inv_s11), _need(y), H, W,
+                                        int(upsample_input), _stream()), "conv_tail_h2")
+    _count("conv_tail_h2")
+    return y

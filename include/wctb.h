@@ -148,6 +148,13 @@ int wctb_conv3x3_first_h2(const float* x_nchw, const float* w, const float* bias
  * of w * s with a host-chosen power-of-two s; inv_s = 1/s.  Built by ops.pack_head_h2_w11 / ops.pack_dx_h2.  y: H8 16 ch. */
 int wctb_conv_head_h2(const float* x_nchw, const void* w11_packed, const float* b11, float inv_s11,
                       const void* w12_packed, const float* b12, float inv_s12, void* y_h8, int H, int W, void* stream);
+/* fused decoder tail of the 16x nets on the h2 engine: [UpsamplingNearest2d(2) +] conv12 (16 -> 16) + ReLU + conv11 (16 -> 3)
+ * + ReLU -> NCHW fp32 image, same kernel structure as the head (dx-stacked taps, block-pipelined TMEM rings); with
+ * upsample_input != 0 x_h8 is the HALF-resolution tensor and the nearest x2 is applied while the operand tile is loaded.
+ * replaces: [y = unpool(y);] y = relu(conv12(pad(y))); y = relu(conv11(pad(y)))       (model_cd.py:291-293)
+ * w12_packed / w11_packed: ops.pack_dx_h2 layout (conv11's 3 output channels in rows dx*16 + {0,1,2}); b11: [3].        */
+int wctb_conv_tail_h2(const void* x_h8, const void* w12_packed, const float* b12, float inv_s12, const void* w11_packed,
+                      const float* b11, float inv_s11, float* y_nchw, int H, int W, int upsample_input, void* stream);
 /* layout conversion: NCHW fp32 <-> H8, fp32 P4 -> H8 */
 int wctb_nchw_to_h8(const float* src_nchw, void* dst_h8, int C, int H, int W, void* stream);
 int wctb_h8_to_nchw(const void* src_h8, float* dst_nchw, int C, int H, int W, void* stream);
