@@ -33,6 +33,10 @@ constexpr int F_TW = 28;                            // valid output columns afte
 constexpr int F_ROW = FP * 16;                      // bytes of one 8-channel row
 constexpr int F_WB = 2 * 96 * 16;                   // one B tile: [2 k-chunks][96 rows][16 B]
 constexpr int F_ACC1 = 0, F_ACC2 = 192;             // TMEM column bases of the two rings (2 slots x 96 columns each)
+// warps: 0 weights, 1 MMA issuer, 2-9 second-conv epilogue (two groups of 4), 10-17 first-conv epilogue (two groups of 4),
+// 18-21 loader.  The two groups of an epilogue alternate accumulator blocks (group = TMEM ring slot = block parity), so a
+// group has two block periods for its ~300-instruction body and the SM sub-partitions always have a second warp to issue from.
+constexpr int F_THREADS = 22 * 32;
 // barrier slots (B_MID_READY is followed by 2 x NB1 barriers)
 enum { B_WFULL = 0, B_IN_READY = 1, B_IN_FREE = 3, B_A1_FULL = 5, B_A1_EMPTY = 7, B_A2_FULL = 9, B_A2_EMPTY = 11, B_MID_FREE = 13,
        B_MID_READY = 15 };
@@ -66,18 +70,22 @@ __device__ __forceinline__ void f_reduce_dx(uint32_t taddr, float* out) {
   uint32_t m0[16], n0[16], m1[16], n1[16];
   tmem_ld16_issue(taddr, m0);
   tmem_ld16_issue(taddr + 48u, n0);
-  tmem_ld16_wait(m0);
-  tmem_ld16_wait(n0);
   tmem_ld16_issue(taddr + 16u, m1);
   tmem_ld16_issue(taddr + 64u, n1);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) out[i] = __uint_as_float(m0[i]) + __uint_as_float(n0[i]);
+  tmem_ld16_wait(m0);
+  tmem_ld16_wait(n0);
   tmem_ld16_wait(m1);
   tmem_ld16_wait(n1);
-  tmem_ld16_issue(taddr + 32u, m0);
+  float s1[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    out[i] = __uint_as_float(m0[i]) + __uint_as_float(n0[i]);
+    s1[i] = __uint_as_float(m1[i]) + __uint_as_float(n1[i]);
+  }
+  tmem_ld16_issue(taddr + 32u, m0);              // dx = 2 flies while the dx = 1 shuffles run
   tmem_ld16_issue(taddr + 80u, n0);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) out[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(m1[i]) + __uint_as_float(n1[i]), 1);
+  for (int i = 0; i < 16; ++i) out[i] += __shfl_down_sync(0xffffffffu, s1[i], 1);
   tmem_ld16_wait(m0);
   tmem_ld16_wait(n0);
 #pragma unroll
@@ -123,7 +131,8 @@ __device__ __forceinline__ void f_copy_mid_row(uint8_t* mid, int dst_row, int sr
 // of the intermediate at true image borders (columns by shuffle before the store, rows by a copy after a group barrier)
 template <class C>
 __device__ __forceinline__ void f_first_epilogue(uint32_t tacc_q, uint8_t* mid, const FTile& t, int j, int q, int lane,
-                                                 int H, int W, const float* bias, float inv_s, uint64_t* acc_empty) {
+                                                 int H, int W, const float* bias, float inv_s, uint64_t* acc_empty, int grp,
+                                                 uint64_t* prev_ready, uint32_t ready_parity) {
   float v[16];
   f_reduce_dx(tacc_q, v);
   tc_fence_before();
@@ -149,9 +158,15 @@ __device__ __forceinline__ void f_first_epilogue(uint32_t tacc_q, uint8_t* mid, 
   const int rh = H - t.ya + 1;
   const bool bottom = (H - t.ya <= C::TH) && (j == (rh >> 2));
   if (top || bottom) {
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    // the two epilogue groups alternate blocks: rows of this block were written by this group (named barrier), the source
+    // row of the bottom patch may sit in the previous block, written by the other group (its mid_ready barrier)
+    if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+    else asm volatile("bar.sync 4, 128;" ::: "memory");
     if (top && q == 0) f_copy_mid_row<C::PLANE>(mid, 0, 2, lane);
-    if (bottom && q == (rh & 3)) f_copy_mid_row<C::PLANE>(mid, rh, rh - 2, lane);
+    if (bottom && q == (rh & 3)) {
+      if (j > 0) mbar_wait(prev_ready, ready_parity);
+      f_copy_mid_row<C::PLANE>(mid, rh, rh - 2, lane);
+    }
   }
 }
 
@@ -173,13 +188,13 @@ constexpr int HD_OFF_MID = 2 * HD_IN_BYTES;
 constexpr int HD_OFF_W11 = HD_OFF_MID + 2 * HC::MID_BYTES;
 constexpr int HD_OFF_W12 = HD_OFF_W11 + 2 * F_WB;
 constexpr int HD_OFF_POOL = HD_OFF_W12 + 3 * F_WB;
-constexpr int HD_POOL_BYTES = 2 * 2 * 32 * 20 * 4;            // [parity][row pair][lane][16 + 4 pad] floats
+constexpr int HD_POOL_BYTES = 2 * 2 * 2 * 32 * 20 * 4;        // [parity][group][row pair][lane][16 + 4 pad] floats
 constexpr int HD_OFF_BAR = HD_OFF_POOL + HD_POOL_BYTES;
 constexpr int HD_SMEM = HD_OFF_BAR + 512 + 128;
 static_assert(HC::NBAR * 8 + 8 <= 512, "barrier area");
 static_assert(HD_SMEM <= 227 * 1024, "shared memory budget");
 
-__global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h) {
+__global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2Args h) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HD_OFF_BAR);
@@ -265,9 +280,9 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // =========================== epilogue of conv12: pool, split, store ===========================
-    const int q = warp & 3;
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const uint32_t tq = tmem_base + F_ACC2 + ((uint32_t)(32 * q) << 16);
     float bv[16];
 #pragma unroll
@@ -280,6 +295,7 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
       const FTile t = f_tile<HC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       for (int k = 0; k < t.nb2; ++k, ++g2) {
         const uint32_t slot = g2 & 1u;
+        if (slot != (uint32_t)grp) continue;        // the other group's block
         mbar_wait(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
         tc_fence_after();
         float v[16];
@@ -290,13 +306,14 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] = wctb_relu(fmaf(v[c], h.inv_s12, bv[c]));
         // rows 4k+q: (q, q+1) pool together; odd rows hand their values to the even row's warp
-        float* pb = poolbuf + ((g2 & 1u) * 2u + (uint32_t)(q >> 1)) * (32 * 20) + lane * 20;
+        float* pb = poolbuf + ((((g2 >> 1) & 1u) * 2u + (uint32_t)grp) * 2u + (uint32_t)(q >> 1)) * (32 * 20) + lane * 20;
         if (q & 1) {
           float4* d = reinterpret_cast<float4*>(pb);
           d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
           d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         if (!(q & 1)) {
           const float4* s = reinterpret_cast<const float4*>(pb);
           const float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
@@ -320,9 +337,9 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
         }
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 18) {
     // =========================== epilogue of conv11 -> conv12 operand tile ===========================
-    const int q = warp & 3;
+    const int q = warp & 3, grp = (warp - 10) >> 2;
     const uint32_t tq = tmem_base + F_ACC1 + ((uint32_t)(32 * q) << 16);
     float bv[16];
 #pragma unroll
@@ -334,9 +351,11 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
       if (i >= 2) mbar_wait(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);      // conv12 of tile i-2 has read this buffer
       for (int j = 0; j < t.nb1; ++j, ++g1) {
         const uint32_t slot = g1 & 1u;
+        if (slot != (uint32_t)grp) continue;        // the other group's block
         mbar_wait(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
         tc_fence_after();
-        f_first_epilogue<HC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s11, bars + B_A1_EMPTY + slot);
+        f_first_epilogue<HC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s11, bars + B_A1_EMPTY + slot, grp,
+                             bars + B_MID_READY + (i & 1) * HC::NB1 + (j > 0 ? j - 1 : 0), (uint32_t)((i >> 1) & 1));
         fence_async_smem();                         // every writer: generic-proxy stores -> visible to tcgen05.mma
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + B_MID_READY + (i & 1) * HC::NB1 + j);
@@ -344,7 +363,7 @@ __global__ void __launch_bounds__(448, 1) conv_head_h2_kernel(const HeadH2Args h
     }
   } else {
     // =========================== image loader: NCHW fp32 -> [R G B 0 | r g b 0] fp16 hi | lo pixels ===========================
-    const int pw = warp - 10;
+    const int pw = warp - 18;
     const long long HW = (long long)H * W;
     for (int b = 0; b < 2; ++b)      // rows 36..39 are only read against zero weights / by garbage positions: keep them finite
       reinterpret_cast<uint4*>(smem + b * HD_IN_BYTES)[(36 + pw) * FP + lane] = make_uint4(0u, 0u, 0u, 0u);
@@ -399,7 +418,7 @@ constexpr int TL_SMEM = TL_OFF_BAR + 512 + 128;
 static_assert(TC::NBAR * 8 + 8 <= 512, "barrier area");
 static_assert(TL_SMEM <= 227 * 1024, "shared memory budget");
 
-__global__ void __launch_bounds__(448, 1) conv_tail_h2_kernel(const TailH2Args h) {
+__global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2Args h) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TL_OFF_BAR);
@@ -478,9 +497,9 @@ __global__ void __launch_bounds__(448, 1) conv_tail_h2_kernel(const TailH2Args h
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // =========================== epilogue of conv11: 3 channels -> NCHW fp32 ===========================
-    const int q = warp & 3;
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const uint32_t tq = tmem_base + F_ACC2 + ((uint32_t)(32 * q) << 16);
     const float b0 = __ldg(h.b11), b1 = __ldg(h.b11 + 1), b2 = __ldg(h.b11 + 2);
     const long long HW = (long long)H * W;
@@ -489,6 +508,7 @@ __global__ void __launch_bounds__(448, 1) conv_tail_h2_kernel(const TailH2Args h
       const FTile t = f_tile<TC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       for (int k = 0; k < t.nb2; ++k, ++g2) {
         const uint32_t slot = g2 & 1u;
+        if (slot != (uint32_t)grp) continue;        // the other group's block
         mbar_wait(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
         tc_fence_after();
         // channels 0..2 of each dx group: main at dx*16, minor at 48 + dx*16
@@ -512,9 +532,9 @@ __global__ void __launch_bounds__(448, 1) conv_tail_h2_kernel(const TailH2Args h
         }
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 18) {
     // =========================== epilogue of conv12 -> conv11 operand tile ===========================
-    const int q = warp & 3;
+    const int q = warp & 3, grp = (warp - 10) >> 2;
     const uint32_t tq = tmem_base + F_ACC1 + ((uint32_t)(32 * q) << 16);
     float bv[16];
 #pragma unroll
@@ -526,9 +546,11 @@ __global__ void __launch_bounds__(448, 1) conv_tail_h2_kernel(const TailH2Args h
       if (i >= 2) mbar_wait(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);
       for (int j = 0; j < t.nb1; ++j, ++g1) {
         const uint32_t slot = g1 & 1u;
+        if (slot != (uint32_t)grp) continue;        // the other group's block
         mbar_wait(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
         tc_fence_after();
-        f_first_epilogue<TC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s12, bars + B_A1_EMPTY + slot);
+        f_first_epilogue<TC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s12, bars + B_A1_EMPTY + slot, grp,
+                             bars + B_MID_READY + (i & 1) * TC::NB1 + (j > 0 ? j - 1 : 0), (uint32_t)((i >> 1) & 1));
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + B_MID_READY + (i & 1) * TC::NB1 + j);
@@ -536,7 +558,7 @@ __global__ void __launch_bounds__(448, 1) conv_tail_h2_kernel(const TailH2Args h
     }
   } else {
     // =========================== input loader: (up-sampled) H8 tile, reflection resolved in the source address ===========================
-    const int pw = warp - 10;
+    const int pw = warp - 18;
     const int Hs = H >> h.ups, Ws = W >> h.ups;
     const long long HWs = (long long)Hs * Ws;
     for (int i = 0; i < ntl; ++i) {
@@ -582,7 +604,7 @@ extern "C" int wctb_conv_head_h2(const float* x_nchw, const void* w11_packed, co
   h.tiles_x = (W + F_TW - 1) / F_TW;
   h.ntiles = h.tiles_x * ((H + HC::TH - 1) / HC::TH);
   const int grid = h.ntiles < wctb_num_sms() ? h.ntiles : wctb_num_sms();
-  conv_head_h2_kernel<<<grid, 448, HD_SMEM, (cudaStream_t)stream>>>(h);
+  conv_head_h2_kernel<<<grid, F_THREADS, HD_SMEM, (cudaStream_t)stream>>>(h);
   WCTB_RETURN_LAUNCH();
 }
 
@@ -600,6 +622,6 @@ extern "C" int wctb_conv_tail_h2(const void* x_h8, const void* w12_packed, const
   h.tiles_x = (W + F_TW - 1) / F_TW;
   h.ntiles = h.tiles_x * ((H + TC::TH - 1) / TC::TH);
   const int grid = h.ntiles < wctb_num_sms() ? h.ntiles : wctb_num_sms();
-  conv_tail_h2_kernel<<<grid, 448, TL_SMEM, (cudaStream_t)stream>>>(h);
+  conv_tail_h2_kernel<<<grid, F_THREADS, TL_SMEM, (cudaStream_t)stream>>>(h);
   WCTB_RETURN_LAUNCH();
 }

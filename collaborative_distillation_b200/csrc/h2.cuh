@@ -16,18 +16,31 @@ __device__ __forceinline__ float h2f(uint32_t h) {
   asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((uint16_t)h));
   return f;
 }
+// two floats -> packed fp16x2 (a in the low half, b in the high half), round-to-nearest-even, saturating: one F2FP
+__device__ __forceinline__ uint32_t f2h2_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ void h22f(uint32_t h2, float& a, float& b) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&h2);
+  const float2 f = __half22float2(h);
+  a = f.x;
+  b = f.y;
+}
 // x -> (hi, lo) fp16 pair; 8 values -> two 16-byte units
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  uint32_t h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = f2h_sat(v[i]);
-    l[i] = f2h_sat(v[i] - h2f(h[i]));
+  for (int i = 0; i < 4; ++i) {
+    h[i] = f2h2_sat(v[2 * i], v[2 * i + 1]);
+    float a, b;
+    h22f(h[i], a, b);
+    l[i] = f2h2_sat(v[2 * i] - a, v[2 * i + 1] - b);
   }
-  hi = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-  lo = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-
 
 // (hi, lo) 16-byte units -> 8 floats
 __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float* v) {

@@ -109,6 +109,22 @@ class StripGroup:
         parts = [p for p in (left, own, right) if p is not None]
         return torch.cat(parts, dim=-1).contiguous(), lh, rh
 
+    def gather_strips(self, own: torch.Tensor, dst: int = 0):
+        """concatenate every rank's strip [1,3,H,w_r] along W on rank `dst` (widths may differ); other ranks get None.
+        Only used at the very end of a stylization (saving the image): features are never gathered."""
+        w = torch.tensor([own.shape[-1]], dtype=torch.int64, device=own.device)
+        ws = [torch.zeros_like(w) for _ in range(self.world)]
+        dist.all_gather(ws, w, group=self.group)
+        ws = [int(v.item()) for v in ws]
+        wmax = max(ws)
+        pad = own.new_zeros(own.shape[:-1] + (wmax,))
+        pad[..., :own.shape[-1]] = own
+        bufs = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == dst else None
+        dist.gather(pad, bufs, dst=dst, group=self.group)
+        if self.rank != dst:
+            return None
+        return torch.cat([b[..., :n] for b, n in zip(bufs, ws)], dim=-1)
+
     @staticmethod
     def own_slice(full: torch.Tensor, cuts, rank: int):
         return full[..., cuts[rank]:cuts[rank + 1]].contiguous()

@@ -55,6 +55,7 @@ class WCT(nn.Module):
         self.overlap_style = True  # single-GPU stylize(): run the (content-independent) style branch on a side stream
         self._side = None
         self._main = None
+        self._stream_dev = None
         self.fast_stats = True     # TF32 mode, single GPU: fp32-product Gram (see _moments)
         self.fast_stats_h2 = os.environ.get("WCTB_FAST_STATS_H2", "0") == "1"   # h2 engine: fp64 Gram unless told otherwise
         self.use_graph = True      # single-GPU stylize(): capture the two-stream schedule in a CUDA graph per input shape
@@ -102,6 +103,8 @@ class WCT(nn.Module):
         s_region = s_region or full(s_p4)
         nc = float(c_count if c_count is not None else (c_region[1] - c_region[0]) * (c_region[3] - c_region[2]))
         ns = float(s_count if s_count is not None else (s_region[1] - s_region[0]) * (s_region[3] - s_region[2]))
+        if nc < 2 or ns < 2:
+            raise WctbError("the covariance divides by HW - 1 (util_wct.py:70,96): feature maps need at least 2 pixels")
         grams = torch.zeros(2, C, C, device=c_p4.device, dtype=torch.float64)
         c_mean = self._moments(c_p4, c_region, nc, grams[0])
         s_mean = self._moments(s_p4, s_region, ns, grams[1])
@@ -209,9 +212,11 @@ class WCT(nn.Module):
         statistics and eigensolve of every stage -- on a low-priority stream: style work fills the SMs whenever the
         critical path leaves them idle (notably during the single-CTA content eigensolves) without delaying it."""
         cur = torch.cuda.current_stream()
-        if self._side is None:
+        dev = torch.cuda.current_device()
+        if self._side is None or self._stream_dev != dev:        # streams belong to a device
             self._main = torch.cuda.Stream(priority=-1)
             self._side = torch.cuda.Stream(priority=0)
+            self._stream_dev = dev
         main, side = self._main, self._side
         main.wait_stream(cur)
         side.wait_stream(cur)
@@ -288,6 +293,15 @@ class WCT(nn.Module):
         cur.wait_stream(side)
         return img
 
+    def _weights_fingerprint(self, stages):
+        """changes whenever a weight tensor of the nets on the path is replaced or updated in place (load_state_dict,
+        load_npz_into, optimizer steps): a captured graph replays the PACKED weights of capture time, so it must not outlive them"""
+        fp = []
+        for s in stages:
+            for net in (getattr(self, "e%d" % s), getattr(self, "d%d" % s)):
+                fp.append(tuple((p.data_ptr(), p._version) for p in net.parameters()))
+        return hash(tuple(fp))
+
     @torch.no_grad()
     def _stylize_graph(self, content, style, alpha, num_run, stages, style_cache=None):
         """Replay (capture on first use) a CUDA graph of the two-stream schedule for this input shape: ~500 kernel launches
@@ -300,7 +314,8 @@ class WCT(nn.Module):
         host = (not content.is_cuda) and (not style.is_cuda) and content.is_pinned() and style.is_pinned()
         key = (tuple(content.shape), tuple(style.shape), float(alpha), int(num_run), tuple(stages), nets.get_precision(),
                bool(self.fold_into_decoder), bool(getattr(self.args, "numpy", False)), self.num_eig, self.rat_eig, float(self.tau), self._early(), self.whiten_solver,
-               (content.data_ptr(), style.data_ptr()) if host else None, id(style_cache) if style_cache is not None else None)
+               (content.data_ptr(), style.data_ptr()) if host else None, id(style_cache) if style_cache is not None else None,
+               torch.cuda.current_device(), bool(self.fast_stats), bool(self.fast_stats_h2), self._weights_fingerprint(stages))
         ent = self._graphs.get(key)
         if ent is None:
             dev = torch.device("cuda", torch.cuda.current_device())
@@ -349,6 +364,9 @@ class WCT(nn.Module):
             if self.use_graph and getattr(self, "timeline", None) is None:
                 return self._stylize_graph(c, st, alpha, num_run, tuple(stages), style_cache)
             return self._stylize_two_streams(c, st, alpha, num_run, tuple(stages), style_cache)
+        if style is None:
+            raise WctbError("stylize(style_cache=...) needs the single-GPU overlapped path (dist is None and overlap_style=True); "
+                            "pass the style image here")
         img = content.to("cuda", torch.float32)
         style = style.to("cuda", torch.float32)
         for _ in range(num_run):
