@@ -76,20 +76,39 @@ __device__ __forceinline__ void f_reduce_dx(uint32_t taddr, float* out) {
   tmem_ld16_wait(n0);
   tmem_ld16_wait(m1);
   tmem_ld16_wait(n1);
+  f32x2 acc[8];
   float s1[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    out[i] = __uint_as_float(m0[i]) + __uint_as_float(n0[i]);
-    s1[i] = __uint_as_float(m1[i]) + __uint_as_float(n1[i]);
+  for (int i = 0; i < 8; ++i) {
+    acc[i] = add2(pk2(__uint_as_float(m0[2 * i]), __uint_as_float(m0[2 * i + 1])), pk2(__uint_as_float(n0[2 * i]), __uint_as_float(n0[2 * i + 1])));
+    upk2(add2(pk2(__uint_as_float(m1[2 * i]), __uint_as_float(m1[2 * i + 1])), pk2(__uint_as_float(n1[2 * i]), __uint_as_float(n1[2 * i + 1]))),
+         s1[2 * i], s1[2 * i + 1]);
   }
   tmem_ld16_issue(taddr + 32u, m0);              // dx = 2 flies while the dx = 1 shuffles run
   tmem_ld16_issue(taddr + 80u, n0);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) out[i] += __shfl_down_sync(0xffffffffu, s1[i], 1);
+  for (int i = 0; i < 8; ++i)
+    acc[i] = add2(acc[i], pk2(__shfl_down_sync(0xffffffffu, s1[2 * i], 1), __shfl_down_sync(0xffffffffu, s1[2 * i + 1], 1)));
   tmem_ld16_wait(m0);
   tmem_ld16_wait(n0);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) out[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(m0[i]) + __uint_as_float(n0[i]), 2);
+  for (int i = 0; i < 8; ++i) {
+    float a, b;
+    upk2(add2(pk2(__uint_as_float(m0[2 * i]), __uint_as_float(m0[2 * i + 1])), pk2(__uint_as_float(n0[2 * i]), __uint_as_float(n0[2 * i + 1]))), a, b);
+    acc[i] = add2(acc[i], pk2(__shfl_down_sync(0xffffffffu, a, 2), __shfl_down_sync(0xffffffffu, b, 2)));
+    upk2(acc[i], out[2 * i], out[2 * i + 1]);
+  }
+}
+// v[i] = relu(v[i] * s + b[i]) for 16 values, packed FFMA2
+__device__ __forceinline__ void f_scale_bias_relu16(float* v, float s, const float* b) {
+  const f32x2 s2 = pk2(s, s);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a, c;
+    upk2(fma2(pk2(v[2 * i], v[2 * i + 1]), s2, pk2(b[2 * i], b[2 * i + 1])), a, c);
+    v[2 * i] = wctb_relu(a);
+    v[2 * i + 1] = wctb_relu(c);
+  }
 }
 
 // second conv of a chain (16 -> 16 or 16 -> 3 padded), dx-stacked: block k of the operand tile `mid` ([hi0, lo0, hi1, lo1]
@@ -110,20 +129,20 @@ __device__ __forceinline__ void f_issue_conv16(uint32_t mid, uint32_t wsm, uint3
 template <int PLANE>
 __device__ __forceinline__ void f_store_mid(uint8_t* mid, int row, int col, const float* v) {
   uint4 hi, lo;
-  uint4* p = reinterpret_cast<uint4*>(mid + (size_t)row * F_ROW) + col;
+  const uint32_t p = smem_u32(mid) + (uint32_t)(row * F_ROW + col * 16);
   split8(v, hi, lo);
-  p[0] = hi;
-  p[PLANE / 16] = lo;
+  sts128(p, hi);
+  sts128(p + PLANE, lo);
   split8(v + 8, hi, lo);
-  p[2 * (PLANE / 16)] = hi;
-  p[3 * (PLANE / 16)] = lo;
+  sts128(p + 2 * PLANE, hi);
+  sts128(p + 3 * PLANE, lo);
 }
 template <int PLANE>
 __device__ __forceinline__ void f_copy_mid_row(uint8_t* mid, int dst_row, int src_row, int lane) {
 #pragma unroll
   for (int pl = 0; pl < 4; ++pl) {
-    uint4* base = reinterpret_cast<uint4*>(mid + (size_t)pl * PLANE);
-    base[dst_row * FP + lane] = base[src_row * FP + lane];
+    const uint32_t base = smem_u32(mid) + (uint32_t)(pl * PLANE + lane * 16);
+    sts128(base + dst_row * F_ROW, lds128(base + src_row * F_ROW));
   }
 }
 
@@ -138,8 +157,7 @@ __device__ __forceinline__ void f_first_epilogue(uint32_t tacc_q, uint8_t* mid, 
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(acc_empty);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = wctb_relu(fmaf(v[i], inv_s, bias[i]));
+  f_scale_bias_relu16(v, inv_s, bias);
   // tile col c <-> gx = x0 - 1 + c.  gx = -1 takes the value of gx = 1, gx = W the value of gx = W - 2
   const bool left = (t.x0 == 0);
   const int cr = W - t.x0 + 1;
@@ -164,7 +182,7 @@ __device__ __forceinline__ void f_first_epilogue(uint32_t tacc_q, uint8_t* mid, 
     else asm volatile("bar.sync 4, 128;" ::: "memory");
     if (top && q == 0) f_copy_mid_row<C::PLANE>(mid, 0, 2, lane);
     if (bottom && q == (rh & 3)) {
-      if (j > 0) mbar_wait(prev_ready, ready_parity);
+      if (j > 0) mbar_wait_sleep(prev_ready, ready_parity);
       f_copy_mid_row<C::PLANE>(mid, rh, rh - 2, lane);
     }
   }
@@ -233,7 +251,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
     if (elect_one()) {
       constexpr uint32_t id96 = umma_idesc_f16(96);
       const uint32_t w11s = smem_u32(smem + HD_OFF_W11), w12s = smem_u32(smem + HD_OFF_W12);
-      mbar_wait(bars + B_WFULL, 0);
+      mbar_wait_sleep(bars + B_WFULL, 0);
       int i1 = 0, j1 = 0, i2 = 0, k2 = 0;          // cursors: (local tile, block) of the next first- / second-conv block
       uint32_t g1 = 0, g2 = 0, base1 = 0;          // global block counters; first-conv blocks issued before tile i2
       FTile t1 = f_tile<HC>((int)blockIdx.x, h.tiles_x, H), t2 = t1;
@@ -241,9 +259,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
         // second-conv block (i2, k2) reads first-conv blocks 0..k2+1 of its tile; stay one more block ahead
         const uint32_t need = base1 + (uint32_t)k2 + 2u;
         while (i1 < ntl && g1 < need + 1u) {
-          if (j1 == 0) mbar_wait(bars + B_IN_READY + (i1 & 1), (i1 >> 1) & 1);
+          if (j1 == 0) mbar_wait_sleep(bars + B_IN_READY + (i1 & 1), (i1 >> 1) & 1);
           const uint32_t slot = g1 & 1u;
-          mbar_wait(bars + B_A1_EMPTY + slot, ((g1 >> 1) & 1u) ^ 1u);
+          mbar_wait_sleep(bars + B_A1_EMPTY + slot, ((g1 >> 1) & 1u) ^ 1u);
           tc_fence_after();
           // conv11: K chunk 0 = image row r (RGB hi | RGB lo of one pixel), chunk 1 = row r + 1 (LBO = one row)
           const uint32_t a = smem_u32(smem + (i1 & 1) * HD_IN_BYTES) + (uint32_t)(4 * j1) * F_ROW;
@@ -261,10 +279,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
         }
         {
           uint64_t* ready = bars + B_MID_READY + (i2 & 1) * HC::NB1;
-          mbar_wait(ready + k2, (i2 >> 1) & 1);
-          mbar_wait(ready + k2 + 1, (i2 >> 1) & 1);
+          mbar_wait_sleep(ready + k2, (i2 >> 1) & 1);
+          mbar_wait_sleep(ready + k2 + 1, (i2 >> 1) & 1);
           const uint32_t slot = g2 & 1u;
-          mbar_wait(bars + B_A2_EMPTY + slot, ((g2 >> 1) & 1u) ^ 1u);
+          mbar_wait_sleep(bars + B_A2_EMPTY + slot, ((g2 >> 1) & 1u) ^ 1u);
           tc_fence_after();
           f_issue_conv16<HC::PLANE>(smem_u32(smem + HD_OFF_MID + (i2 & 1) * HC::MID_BYTES), w12s, tmem_base + F_ACC2 + slot * 96u, k2);
           tc_commit(bars + B_A2_FULL + slot);
@@ -296,15 +314,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
       for (int k = 0; k < t.nb2; ++k, ++g2) {
         const uint32_t slot = g2 & 1u;
         if (slot != (uint32_t)grp) continue;        // the other group's block
-        mbar_wait(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
+        mbar_wait_sleep(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
         tc_fence_after();
         float v[16];
         f_reduce_dx(tq + slot * 96u, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + B_A2_EMPTY + slot);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = wctb_relu(fmaf(v[c], h.inv_s12, bv[c]));
+        f_scale_bias_relu16(v, h.inv_s12, bv);
         // rows 4k+q: (q, q+1) pool together; odd rows hand their values to the even row's warp
         float* pb = poolbuf + ((((g2 >> 1) & 1u) * 2u + (uint32_t)grp) * 2u + (uint32_t)(q >> 1)) * (32 * 20) + lane * 20;
         if (q & 1) {
@@ -348,11 +365,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
     for (int i = 0; i < ntl; ++i) {
       const FTile t = f_tile<HC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       uint8_t* mid = smem + HD_OFF_MID + (i & 1) * HC::MID_BYTES;
-      if (i >= 2) mbar_wait(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);      // conv12 of tile i-2 has read this buffer
+      if (i >= 2) mbar_wait_sleep(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);      // conv12 of tile i-2 has read this buffer
       for (int j = 0; j < t.nb1; ++j, ++g1) {
         const uint32_t slot = g1 & 1u;
         if (slot != (uint32_t)grp) continue;        // the other group's block
-        mbar_wait(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
+        mbar_wait_sleep(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
         tc_fence_after();
         f_first_epilogue<HC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s11, bars + B_A1_EMPTY + slot, grp,
                              bars + B_MID_READY + (i & 1) * HC::NB1 + (j > 0 ? j - 1 : 0), (uint32_t)((i >> 1) & 1));
@@ -370,7 +387,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
     for (int i = 0; i < ntl; ++i) {
       const FTile t = f_tile<HC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       uint4* in = reinterpret_cast<uint4*>(smem + (i & 1) * HD_IN_BYTES);
-      if (i >= 2) mbar_wait(bars + B_IN_FREE + (i & 1), ((i - 2) >> 1) & 1);
+      if (i >= 2) mbar_wait_sleep(bars + B_IN_FREE + (i & 1), ((i - 2) >> 1) & 1);
       const int gx = wctb_reflect(t.x0 - 2 + lane, W);
       float r0[9], r1[9], r2[9];
 #pragma unroll
@@ -383,7 +400,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
       for (int k = 0; k < 9; ++k) {
         const uint32_t h0 = f2h_sat(r0[k]), h1 = f2h_sat(r1[k]), h2 = f2h_sat(r2[k]);
         const uint32_t l0 = f2h_sat(r0[k] - h2f(h0)), l1 = f2h_sat(r1[k] - h2f(h1)), l2 = f2h_sat(r2[k] - h2f(h2));
-        in[(pw + 4 * k) * FP + lane] = make_uint4(h0 | (h1 << 16), h2, l0 | (l1 << 16), l2);
+        sts128(smem_u32(in + (pw + 4 * k) * FP + lane), make_uint4(h0 | (h1 << 16), h2, l0 | (l1 << 16), l2));
       }
       fence_async_smem();
       __syncwarp();
@@ -455,16 +472,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
     // =========================== MMA issuer (same schedule as the head) ===========================
     if (elect_one()) {
       const uint32_t w12s = smem_u32(smem + TL_OFF_W12), w11s = smem_u32(smem + TL_OFF_W11);
-      mbar_wait(bars + B_WFULL, 0);
+      mbar_wait_sleep(bars + B_WFULL, 0);
       int i1 = 0, j1 = 0, i2 = 0, k2 = 0;
       uint32_t g1 = 0, g2 = 0, base1 = 0;
       FTile t1 = f_tile<TC>((int)blockIdx.x, h.tiles_x, H), t2 = t1;
       while (i2 < ntl) {
         const uint32_t need = base1 + (uint32_t)k2 + 2u;
         while (i1 < ntl && g1 < need + 1u) {
-          if (j1 == 0) mbar_wait(bars + B_IN_READY + (i1 & 1), (i1 >> 1) & 1);
+          if (j1 == 0) mbar_wait_sleep(bars + B_IN_READY + (i1 & 1), (i1 >> 1) & 1);
           const uint32_t slot = g1 & 1u;
-          mbar_wait(bars + B_A1_EMPTY + slot, ((g1 >> 1) & 1u) ^ 1u);
+          mbar_wait_sleep(bars + B_A1_EMPTY + slot, ((g1 >> 1) & 1u) ^ 1u);
           tc_fence_after();
           f_issue_conv16<TL_IN_PLANE>(smem_u32(smem + (i1 & 1) * TL_IN_BYTES), w12s, tmem_base + F_ACC1 + slot * 96u, j1);
           tc_commit(bars + B_A1_FULL + slot);
@@ -478,10 +495,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
         }
         {
           uint64_t* ready = bars + B_MID_READY + (i2 & 1) * TC::NB1;
-          mbar_wait(ready + k2, (i2 >> 1) & 1);
-          mbar_wait(ready + k2 + 1, (i2 >> 1) & 1);
+          mbar_wait_sleep(ready + k2, (i2 >> 1) & 1);
+          mbar_wait_sleep(ready + k2 + 1, (i2 >> 1) & 1);
           const uint32_t slot = g2 & 1u;
-          mbar_wait(bars + B_A2_EMPTY + slot, ((g2 >> 1) & 1u) ^ 1u);
+          mbar_wait_sleep(bars + B_A2_EMPTY + slot, ((g2 >> 1) & 1u) ^ 1u);
           tc_fence_after();
           f_issue_conv16<TC::PLANE>(smem_u32(smem + TL_OFF_MID + (i2 & 1) * TC::MID_BYTES), w11s, tmem_base + F_ACC2 + slot * 96u, k2);
           tc_commit(bars + B_A2_FULL + slot);
@@ -509,7 +526,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
       for (int k = 0; k < t.nb2; ++k, ++g2) {
         const uint32_t slot = g2 & 1u;
         if (slot != (uint32_t)grp) continue;        // the other group's block
-        mbar_wait(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
+        mbar_wait_sleep(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
         tc_fence_after();
         // channels 0..2 of each dx group: main at dx*16, minor at 48 + dx*16
         float m[6][4];
@@ -543,11 +560,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
     for (int i = 0; i < ntl; ++i) {
       const FTile t = f_tile<TC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       uint8_t* mid = smem + TL_OFF_MID + (i & 1) * TC::MID_BYTES;
-      if (i >= 2) mbar_wait(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);
+      if (i >= 2) mbar_wait_sleep(bars + B_MID_FREE + (i & 1), ((i - 2) >> 1) & 1);
       for (int j = 0; j < t.nb1; ++j, ++g1) {
         const uint32_t slot = g1 & 1u;
         if (slot != (uint32_t)grp) continue;        // the other group's block
-        mbar_wait(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
+        mbar_wait_sleep(bars + B_A1_FULL + slot, (g1 >> 1) & 1u);
         tc_fence_after();
         f_first_epilogue<TC>(tq + slot * 96u, mid, t, j, q, lane, H, W, bv, h.inv_s12, bars + B_A1_EMPTY + slot, grp,
                              bars + B_MID_READY + (i & 1) * TC::NB1 + (j > 0 ? j - 1 : 0), (uint32_t)((i >> 1) & 1));
@@ -564,7 +581,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
     for (int i = 0; i < ntl; ++i) {
       const FTile t = f_tile<TC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
       uint4* in = reinterpret_cast<uint4*>(smem + (i & 1) * TL_IN_BYTES);
-      if (i >= 2) mbar_wait(bars + B_IN_FREE + (i & 1), ((i - 2) >> 1) & 1);
+      if (i >= 2) mbar_wait_sleep(bars + B_IN_FREE + (i & 1), ((i - 2) >> 1) & 1);
       const int sx = wctb_reflect(t.x0 - 2 + lane, W) >> h.ups;               // tile col c <-> gx = x0 - 2 + c
       // warp pw loads plane pw: 22 rows, two batches of 11 loads in flight
 #pragma unroll
@@ -577,7 +594,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
           v[k] = __ldg(h.x + (long long)pw * HWs + (long long)sy * Ws + sx);
         }
 #pragma unroll
-        for (int k = 0; k < 11; ++k) in[(pw * TL_IN_ROWS + half * 11 + k) * FP + lane] = v[k];
+        for (int k = 0; k < 11; ++k) sts128(smem_u32(in + (pw * TL_IN_ROWS + half * 11 + k) * FP + lane), v[k]);
       }
       fence_async_smem();
       __syncwarp();

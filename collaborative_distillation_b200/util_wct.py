@@ -53,11 +53,15 @@ class WCT(nn.Module):
         self.dist = None          # set by parallel.StripGroup for multi-GPU runs
         self.fold_into_decoder = True   # csF = M(cF - mu) + b folded exactly into the decoder's first conv (no apply pass)
         self.overlap_style = True  # single-GPU stylize(): run the (content-independent) style branch on a side stream
+        self.stagger_style = os.environ.get("WCTB_STAGGER", "1") == "1"   # release style stages into the content eigensolve gaps
         self._side = None
         self._main = None
         self._stream_dev = None
         self.fast_stats = True     # TF32 mode, single GPU: fp32-product Gram (see _moments)
-        self.fast_stats_h2 = os.environ.get("WCTB_FAST_STATS_H2", "0") == "1"   # h2 engine: fp64 Gram unless told otherwise
+        # h2 engine: fp32-product Gram (1e-8 relative, far below the 1e-6 noise of the features themselves) on large maps only;
+        # small or nearly rank-deficient maps (HW < 64 C, HW < 65536) keep the fp64 Gram: there its cost is nil and the
+        # noise eigenvalues of the fp32 products (1e-8 lambda_max) would sit next to the rank threshold tau
+        self.fast_stats_h2 = os.environ.get("WCTB_FAST_STATS_H2", "1") == "1"
         self.use_graph = True      # single-GPU stylize(): capture the two-stream schedule in a CUDA graph per input shape
         self.max_graphs = 4        # captured graphs kept (LRU): each one pins the activations of its input shape in HBM
         self._graphs = collections.OrderedDict()
@@ -92,7 +96,9 @@ class WCT(nn.Module):
         # TF32 pipeline amplifies through the whitening; the sharded path keeps the fp64 Gram so that strips stay
         # tile-invariant (sharded == single GPU to fp64 summation order).
         prec = nets.get_precision()
-        fast = self.dist is None and ((prec == "tf32" and self.fast_stats) or (prec == "h2" and self.fast_stats_h2))
+        C = x_p4.shape[0] * 4
+        fast = self.dist is None and ((prec == "tf32" and self.fast_stats) or
+                                      (prec == "h2" and self.fast_stats_h2 and count >= 65536 and count >= 64 * C))
         ops.centered_gram(x_p4, mean, region, out=gram_out, fast=fast)
         return mean
 
@@ -237,7 +243,11 @@ class WCT(nn.Module):
                 pass
             elif not style.is_cuda:
                 style = style.to("cuda", torch.float32, non_blocking=True)
-            for s in (stages if style_cache is None else ()):
+        def launch_style(s, after=None):
+            """style branch of stage s on the side stream (optionally not before event `after` of the main stream)"""
+            with torch.cuda.stream(side):
+                if after is not None:
+                    side.wait_event(after)
                 s4 = getattr(self, "e%d" % s).forward_p4(style)
                 res = self._eig_one(s4)
                 del s4
@@ -247,6 +257,23 @@ class WCT(nn.Module):
                     for t in res:
                         t.record_stream(main)
                 style_res[s] = (res, ev)
+
+        # Staggered schedule: the content eigensolves are single-CTA kernels on the critical path (2.3 ms of a cfg3 step) during
+        # which 147 SMs idle, and the persistent conv kernels of the two branches cannot share SMs anyway.  So only the first
+        # stage's style work starts at once; the style work of stage S[i+2] (and S[1], S[2] for i = 0) is released when the
+        # content branch reaches the eigensolve of stage S[i], i.e. exactly when the GPU would otherwise go idle.
+        todo = [s for s in stages if s not in style_res]
+        slots = {}
+        if style_cache is None and todo:
+            launch_style(todo[0])
+            if self.stagger_style:
+                slots[todo[0]] = todo[1:3]
+                for i in range(1, len(todo)):
+                    if i + 2 < len(todo):
+                        slots[todo[i]] = [todo[i + 2]]
+            else:
+                for s in todo[1:]:
+                    launch_style(s)
         numpy_variant = bool(getattr(self.args, "numpy", False))
         with torch.cuda.stream(main):
             img = content if img0 is None else img0
@@ -262,6 +289,11 @@ class WCT(nn.Module):
                     gram = torch.zeros(1, C, C, device=c4.device, dtype=torch.float64)
                     c_mean = self._moments(c4, (0, c4.shape[1], 0, c4.shape[2]), n, gram[0])
                     mark(s, "stats")
+                    if slots.get(s):
+                        ev_slot = torch.cuda.Event()
+                        ev_slot.record(main)
+                        for ss in slots.pop(s):
+                            launch_style(ss, ev_slot)
                     use_ns = self._use_ns(C)
                     if use_ns:
                         w_c = ops.whiten_ns(gram[0], 1.0 / (n - 1.0), add_identity=numpy_variant)
