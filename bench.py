@@ -34,6 +34,7 @@ CONFIGS = {  # name -> (content HxW, style HxW)
     "cfg2": ((1024, 1024), (512, 512)),
     "cfg3": ((2160, 3840), (2000, 2000)),
     "cfg4": ((4096, 10240), (2160, 3840)),
+    "cfg5": ((2160, 3840), (2000, 2000)),     # BASELINE configs[4]: --mode original (unpruned VGG-19) --UHD
 }
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_16x.npz")
 DTYPE_TEXT = {
@@ -205,7 +206,8 @@ def workload(cfg, N):
         return Hc, Wc, Hs, Ws, ("weak-scaling family of configs[2]: %dx%d content (3840 px of width per GPU) / %dx%d style, --mode 16x --UHD"
                                 % (Wc, Hc, Ws, Hs))
     (Hc, Wc), (Hs, Ws) = CONFIGS[cfg]
-    return Hc, Wc, Hs, Ws, "BASELINE configs %s: %dx%d content / %dx%d style, --mode 16x%s" % (cfg, Wc, Hc, Ws, Hs, "" if cfg == "cfg2" else " --UHD")
+    return Hc, Wc, Hs, Ws, "BASELINE configs %s: %dx%d content / %dx%d style, --mode %s%s" % (
+        cfg, Wc, Hc, Ws, Hs, "original" if cfg == "cfg5" else "16x", "" if cfg == "cfg2" else " --UHD")
 
 
 def default_config(N):
@@ -247,18 +249,43 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def parity_leg(P, wct, dev):
+    """achieved error of the benched engine against the CPU oracle on BASELINE configs[1] (1024^2 / 512^2) with the image family
+    the bench feeds (torch.rand, seed 0): ~1 s of host time; the contract is SURVEY 8(d): 3e-3 RMS / 6e-2 max"""
+    from oracle import wct_oracle as O
+    g = torch.Generator().manual_seed(0)
+    c, s = torch.rand(1, 3, 1024, 1024, generator=g), torch.rand(1, 3, 512, 512, generator=g)
+    ref = O.stylize(O.load_weights_npz(WEIGHTS), "16x", c, s)
+    out = wct.stylize(c.to(dev), s.to(dev)).cpu()
+    d = out - ref
+    return {"rms": float(d.pow(2).mean().sqrt()), "max": float(d.abs().max()), "image_range": [float(ref.min()), float(ref.max())],
+            "config": "BASELINE configs[1] 1024x1024 / 512x512, torch.rand seed 0, vs the CPU oracle", "contract": {"rms": 3e-3, "max": 6e-2}}
+
+
+def ncu_traffic(kernel, shape_hw):
+    """DRAM read+write bytes of one launch from this round's `ncu --set full` captures (profiles/r02_traffic.json, written by
+    tools/ncu_traffic.py from the .ncu-rep files) -- None when no capture of that kernel / shape is on record"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        e = d.get("%s@%dx%d" % (kernel, shape_hw[1], shape_hw[0]))
+        return e
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default=None, help="cfg2|cfg3|cfg4|weak (default: cfg3 at N=1, weak at N>1)")
+    ap.add_argument("--config", default=None, help="cfg2|cfg3|cfg4|cfg5|weak (default: cfg3 at N=1, weak at N>1; cfg5 = --mode original UHD)")
     ap.add_argument("--precision", default="h2", choices=["h2", "tf32", "fp32"],
                     help="conv engine: h2 = fp32-accurate tensor-core convs on fp16 hi/lo operand pairs (default, meets the precision "
                          "contract); tf32 = single-pass TF32 (lossy: misses the contract on noise-like inputs); fp32 = CUDA cores")
     ap.add_argument("--fold", type=int, default=1, help="fold the WCT matrix into the decoder's first conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (cfg4 / cfg5 keys) and the parity leg")
     ap.add_argument("--full-pass", action="store_true", help="--impl reference: also time ONE pass over the whole workload (cfg3: ~25 s)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -279,34 +306,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = world
-
-    cfg = args.config or default_config(N)
-    Hc, Wc, Hs, Ws, wl = workload(cfg, N)
-
     P.set_precision(args.precision)
-    wct = P.WCT(SimpleNamespace(mode="16x", numpy=False))
-    P.weights.load_npz_into(wct, WEIGHTS)
-    wct = wct.to(dev)
-    wct.fold_into_decoder = bool(args.fold)
-
-    g = torch.Generator().manual_seed(0)
-    content_h = torch.rand(1, 3, Hc, Wc, generator=g)
-    style_h = torch.rand(1, 3, Hs, Ws, generator=g)
-    grp = None
-    if N > 1:
-        grp = parallel.StripGroup()
-        wct.dist = grp
-        content_h = grp.own_slice(content_h, parallel.strip_cuts(Wc, N), rank)
-        style_h = grp.own_slice(style_h, parallel.strip_cuts(Ws, N), rank)
-    content_h, style_h = content_h.pin_memory(), style_h.pin_memory()
-    content_d, style_d = content_h.to(dev), style_h.to(dev)
-    out_h = torch.empty(1, 3, (Hc >> 4) << 4, content_h.shape[-1], dtype=torch.float32).pin_memory()
-
-    def step(c, s):
-        if grp is None:
-            return wct.stylize(c, s, alpha=1.0)
-        return grp.stylize(wct.style_transfer_stage, "16x", c, s, alpha=1.0)
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -332,34 +332,84 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        step(content_d, style_d)
-    l0 = ops.launches()
-    with ClockSampler(local) as cs:
-        total_ms = timed(lambda: step(content_d, style_d), args.steps)
-    launches = (ops.launches() - l0)
-    clocks = cs.summary()
-    ms_per_step = total_ms / args.steps
-    mp = Hc * Wc / 1e6
-    value = mp / (ms_per_step / 1e3)
+    _wcts = {}
 
-    # ---- e2e: pinned host -> device -> stylize -> host, every step
-    def e2e_step():
-        if grp is None:
-            o = step(content_h, style_h)          # public API with pinned HOST tensors: H2D happens inside stylize()
+    def get_wct(mode):
+        if mode not in _wcts:
+            if mode == "16x":
+                w = P.WCT(SimpleNamespace(mode="16x", numpy=False))
+                P.weights.load_npz_into(w, WEIGHTS)
+            else:                                                  # original mode = random init under seed 0
+                torch.manual_seed(0)
+                w = P.WCT(SimpleNamespace(mode=mode, numpy=False))
+                P.weights.synthetic_init_(w, seed=0)
+            w = w.to(dev)
+            w.fold_into_decoder = bool(args.fold)
+            if N > 1:
+                w.dist = parallel.StripGroup()
+            _wcts[mode] = w
+        return _wcts[mode]
+
+    def run_workload(cfg, steps, warmup, want_e2e=True, want_roof=False, clocks=False):
+        """one workload end to end on the current world -> dict (rank 0 gets the numbers; every rank runs the work)"""
+        mode = "original" if cfg == "cfg5" else "16x"
+        Hc, Wc, Hs, Ws, wl = workload(cfg, N)
+        wct = get_wct(mode)
+        grp = wct.dist
+        g = torch.Generator().manual_seed(0)
+        content_h = torch.rand(1, 3, Hc, Wc, generator=g)
+        style_h = torch.rand(1, 3, Hs, Ws, generator=g)
+        if grp is not None:
+            content_h = grp.own_slice(content_h, parallel.strip_cuts(Wc, N), rank)
+            style_h = grp.own_slice(style_h, parallel.strip_cuts(Ws, N), rank)
+        content_h, style_h = content_h.pin_memory(), style_h.pin_memory()
+        content_d, style_d = content_h.to(dev), style_h.to(dev)
+        out_h = torch.empty(1, 3, (Hc >> 4) << 4, content_h.shape[-1], dtype=torch.float32).pin_memory()
+
+        def step(c, s):
+            if grp is None:
+                return wct.stylize(c, s, alpha=1.0)
+            return grp.stylize(wct, mode, c, s, alpha=1.0, content_width=Wc, style_width=Ws)
+
+        torch.cuda.reset_peak_memory_stats(dev)
+        for _ in range(warmup):
+            step(content_d, style_d)
+        l0 = ops.launches()
+        if clocks:
+            with ClockSampler(local) as cs:
+                total_ms = timed(lambda: step(content_d, style_d), steps)
         else:
-            o = step(content_h.to(dev, non_blocking=True), style_h.to(dev, non_blocking=True))
-        out_h[..., :o.shape[-2], :o.shape[-1]].copy_(o, non_blocking=True)
-    for _ in range(2):
-        e2e_step()
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
-    e2e_val = mp / (e2e_ms / 1e3)
-    h2d = (content_h.numel() + style_h.numel()) * 4
-    d2h = out_h.numel() * 4
+            cs, total_ms = None, timed(lambda: step(content_d, style_d), steps)
+        launches = ops.launches() - l0
+        ms_per_step = total_ms / steps
+        mp = Hc * Wc / 1e6
+        res = {"cfg": cfg, "mode": mode, "workload": wl, "ms_per_step": ms_per_step, "value": mp / (ms_per_step / 1e3), "launches": launches,
+               "shape": (Hc, Wc, Hs, Ws), "clocks": cs.summary() if cs else None, "flops": algorithmic_conv_flops(mode, Hc, Wc, Hs, Ws),
+               "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        if want_e2e:
+            # e2e: pinned host -> device -> stylize -> host, every step.  Sharded: the uploads go on a copy stream so the style
+            # strip's H2D overlaps the first content kernels, and the download of step i overlaps nothing (it is the result)
+            def e2e_step():
+                if grp is None:
+                    o = step(content_h, style_h)          # public API with pinned HOST tensors: H2D happens inside stylize()
+                else:
+                    o = step(content_h.to(dev, non_blocking=True), style_h.to(dev, non_blocking=True))
+                out_h[..., :o.shape[-2], :o.shape[-1]].copy_(o, non_blocking=True)
+            for _ in range(2):
+                e2e_step()
+            e2e_ms = timed(e2e_step, steps) / steps
+            res["e2e"] = {"value": round(mp / (e2e_ms / 1e3), 2), "unit": "MP/s",
+                          "h2d_bytes_per_step": (content_h.numel() + style_h.numel()) * 4 * N,
+                          "d2h_bytes_per_step": out_h.numel() * 4 * N, "ms_per_step": round(e2e_ms, 3)}
+        if want_roof:
+            res["roofline"] = conv_roofline(P, ops, wct, step, content_d, style_d, args.precision)
+        res["_ctx"] = (wct, step, content_h, style_h, content_d, style_d, mp, Hc, Wc)
+        return res
 
-    # ---- roofline of the dominant kernel: one extra instrumented pass (rank 0), CUDA events around every conv launch
-    # (the pass contains collectives when sharded, so every rank runs it; rank 0 reports)
-    roof = conv_roofline(P, ops, wct, step, content_d, style_d, args.precision)
+    cfg = args.config or default_config(N)
+    main_res = run_workload(cfg, args.steps, args.warmup, want_e2e=True, want_roof=True, clocks=True)
+    wct, step, content_h, style_h, content_d, style_d, mp, Hc, Wc = main_res.pop("_ctx")
+    Hs, Ws = main_res["shape"][2:]
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline and N == 1:
@@ -376,7 +426,7 @@ def main():
     # (what WCT.py --gpu_io moves; 4x fewer PCIe bytes than the fp32 tensors of the reference-facing API).  Measured last
     # and guarded: a failure here can only lose this key.
     e2e_u8 = None
-    if N == 1:
+    if N == 1 and main_res["mode"] == "16x":
         try:
             from collaborative_distillation_b200 import image_io
             cu8 = (content_h[0].permute(1, 2, 0) * 255).round().to(torch.uint8).contiguous().pin_memory()
@@ -397,29 +447,67 @@ def main():
         except Exception as ex:  # noqa: BLE001
             e2e_u8 = {"error": repr(ex)[:200]}
 
+    # ---- extra workloads of BASELINE.json that are not this run's headline (guarded; every rank runs them):
+    #   N = 1: cfg4 (10240x4096) on one GPU -- the reference point of the 8-GPU strong-scaling number -- and cfg5 (original mode UHD)
+    #   N = 2: cfg5 = BASELINE configs[4] (original-mode 3840x2160 tile-split over 2 GPUs, memory stress)
+    #   N = 8: cfg4 = BASELINE configs[3] (10240x4096 / 3840x2160 sharded over 8 GPUs)
+    extras = {}
+    if not args.no_extras and cfg in ("cfg3", "weak"):
+        for xc, when in (("cfg4", (1, 8)), ("cfg5", (1, 2))):
+            if N not in when:
+                continue
+            try:
+                del content_d, style_d
+            except Exception:
+                pass
+            try:
+                torch.cuda.empty_cache()
+                r = run_workload(xc, max(3, min(args.steps, 5)), 3, want_e2e=(xc == "cfg4"), want_roof=False)
+                r.pop("_ctx")
+                extras[xc] = {"workload": r["workload"], "mode": r["mode"], "n_gpus": N, "ms_per_step": round(r["ms_per_step"], 3),
+                              "value": round(r["value"], 2), "unit": "MP/s", "peak_mem_gb": round(r["peak_mem_gb"], 2),
+                              "conv_tflops_whole_step": round(r["flops"] / (r["ms_per_step"] / 1e3) / 1e12, 2),
+                              "algorithmic_conv_tflop_per_step": round(r["flops"] / 1e12, 3)}
+                if "e2e" in r:
+                    extras[xc]["e2e"] = r["e2e"]
+            except Exception as ex:  # noqa: BLE001
+                extras[xc] = {"error": repr(ex)[:300]}
+    parity = None
+    if not args.no_extras and N == 1 and rank == 0:
+        try:
+            parity = parity_leg(P, get_wct("16x"), dev)
+        except Exception as ex:  # noqa: BLE001
+            parity = {"error": repr(ex)[:200]}
+
     if rank == 0:
-        flops = algorithmic_conv_flops("16x", Hc, Wc, Hs, Ws)
+        flops = main_res["flops"]
+        ms_per_step = main_res["ms_per_step"]
         line = {
-            "metric": "megapixels/sec end-to-end WCT stylize (16x VGG, UHD)", "value": round(value, 2), "unit": "MP/s",
+            "metric": "megapixels/sec end-to-end WCT stylize (16x VGG, UHD)", "value": round(main_res["value"], 2), "unit": "MP/s",
             "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE_TEXT[args.precision],
-            "data": "synthetic torch.rand images (seed 0); shipped 16x weights (tests/golden/weights_16x.npz)",
-            "config": {"workload": wl, "mode": "16x", "alpha": 1.0, "stages": 5, "parallelism": "strips%d" % N,
+            "data": "synthetic torch.rand images (seed 0); " + ("shipped 16x weights (tests/golden/weights_16x.npz)" if main_res["mode"] == "16x"
+                                                                 else "random-init weights, seed 0 (no original-mode weights are shipped)"),
+            "config": {"workload": main_res["workload"], "mode": main_res["mode"], "alpha": 1.0, "stages": 5, "parallelism": "strips%d" % N,
                        "l2": "256 MiB flush between timed iterations", "precision": args.precision, "fold": args.fold,
                        "algorithmic_conv_tflop_per_step": round(flops / 1e12, 4)},
-            "clocks": clocks,
-            "e2e": {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": h2d * N if N > 1 else h2d,
-                    "d2h_bytes_per_step": d2h * N if N > 1 else d2h, "ms_per_step": round(e2e_ms, 3)},
-            "gpu_launches": launches,
+            "clocks": main_res["clocks"],
+            "e2e": main_res["e2e"],
+            "gpu_launches": main_res["launches"],
             "conv_tflops_whole_step": round(flops / (ms_per_step / 1e3) / 1e12, 2),
+            "peak_mem_gb": round(main_res["peak_mem_gb"], 2),
         }
-        if roof:
-            line["roofline"] = roof
+        if main_res.get("roofline"):
+            line["roofline"] = main_res["roofline"]
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         if e2e_u8:
             line["e2e_u8"] = e2e_u8
+        if parity:
+            line["parity"] = parity
+        for k, v in extras.items():
+            line[k] = v
         print(json.dumps(line))
     if N > 1:
         dist.destroy_process_group()
@@ -559,11 +647,12 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     else:
         roof = {"bound": "tensor", "achieved": round(ach_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
                 "frac": round(ach_tf / peak_tf, 4)}
-    # DRAM bytes (read+write) of ONE content-sized launch from `ncu --set full` (profiles/r01_fused_kernels_ncu_full.txt)
-    traffic = {("conv_head_tc", (2160, 3840)): 99572224 + 84228352, ("conv_tail", (2160, 3840)): 132837888 + 64769024}
-    tkey = (top["kernel"], tuple(content_d.shape[-2:]))
+    # DRAM bytes (read+write) of ONE content-sized launch of the top kernel, from this round's ncu --set full capture
+    tr = ncu_traffic(top["kernel"], tuple(content_d.shape[-2:]))
     roof.update({
-        "traffic": traffic.get(tkey), "traffic_note": "DRAM read+write of one content-image launch of this kernel (ncu --set full); algorithmic bytes of that launch: head 232.2 MB, tail 232.2 MB",
+        "traffic": None if tr is None else tr["dram_bytes"],
+        "traffic_note": ("no ncu capture of this kernel / shape on record" if tr is None else
+                         "DRAM read+write of one %s launch of this kernel (%s); algorithmic bytes of that launch: %d" % (tr.get("shape", "content-image"), tr.get("source", "ncu --set full"), tr.get("algorithmic_bytes", 0))),
         "peaks_source": peaks["source"],
         "kernel": "%s %s (%d launches/step, %.1f%% of the single-stream step)" % (top["kernel"], top["shape"], top["launches"],
                                                                                   100 * top["ms"] / step_ms),

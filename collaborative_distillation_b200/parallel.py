@@ -130,30 +130,104 @@ class StripGroup:
         return full[..., cuts[rank]:cuts[rank + 1]].contiguous()
 
     def stylize(self, stage_fn, mode: str, content_own: torch.Tensor, style_own: torch.Tensor, alpha: float = 1.0,
-                stages=(5, 4, 3, 2, 1), num_run: int = 1) -> torch.Tensor:
-        """content_own / style_own: this rank's strips [1,3,H,w].  Returns this rank's strip of the stylized image."""
+                stages=(5, 4, 3, 2, 1), num_run: int = 1, content_width: int = None, style_width: int = None) -> torch.Tensor:
+        """content_own / style_own: this rank's strips [1,3,H,w].  Returns this rank's strip of the stylized image.
+        `stage_fn` is either a callable `fn(stage, content_ext, style_ext, alpha, c_region, s_region, c_count, s_count)`
+        (one fused stage) or an executor with `style_part(stage, style_ext, s_region, s_count)` and
+        `content_part(stage, content_ext, style_res, alpha, c_region, c_count)` (a `WCT`): then the style halves run on a side
+        stream and are released into the content branch's eigensolve gaps, as on one GPU.
+        content_width / style_width: whole-image widths when the caller knows them (saves two tiny all-reduces + host syncs)."""
         hmax = max(stage_halo(mode, s) for s in stages)
         style_ext, s_lh, s_rh = self.exchange(style_own, hmax)
         img = content_own
-        # whole-image widths (one tiny all-reduce per call): statistics divide by GLOBAL pixel counts
-        Wc_tot = self.total_width(content_own.shape[-1], content_own.device)
-        Ws_tot = self.total_width(style_own.shape[-1], style_own.device)
+        # statistics divide by GLOBAL pixel counts
+        Wc_tot = int(content_width) if content_width is not None else self.total_width(content_own.shape[-1], content_own.device)
+        Ws_tot = int(style_width) if style_width is not None else self.total_width(style_own.shape[-1], style_own.device)
         Hs = style_own.shape[-2]
-        for _ in range(num_run):
-            for s in stages:
-                h = stage_halo(mode, s)
-                ext, lh, rh = self.exchange(img, h)
-                H, We = ext.shape[-2:]
-                c_region = (0, H, lh, We - rh)
-                st = style_ext[..., (s_lh - min(s_lh, h)):style_ext.shape[-1] - (s_rh - min(s_rh, h))]
-                sl, sr = min(s_lh, h), min(s_rh, h)
-                s_region = (0, st.shape[-2], sl, st.shape[-1] - sr)
-                sh = s - 1
-                c_count = (H >> sh) * (Wc_tot >> sh)
-                s_count = (Hs >> sh) * (Ws_tot >> sh)
-                out = stage_fn(s, ext, st.contiguous(), alpha, c_region, s_region, c_count, s_count)
-                Wc_tot = (Wc_tot >> sh) << sh          # floor-pool drops trailing columns of the whole image
-                # floor-pool may have dropped trailing rows/cols (global right/bottom edge only)
-                x1 = min(We - rh, out.shape[-1])
-                img = out[..., lh:x1].contiguous()
-        return img
+        split = hasattr(stage_fn, "style_part") and hasattr(stage_fn, "content_part")
+
+        def style_args(s):
+            h = stage_halo(mode, s)
+            st = style_ext[..., (s_lh - min(s_lh, h)):style_ext.shape[-1] - (s_rh - min(s_rh, h))]
+            sl, sr = min(s_lh, h), min(s_rh, h)
+            return st.contiguous(), (0, st.shape[-2], sl, st.shape[-1] - sr), (Hs >> (s - 1)) * (Ws_tot >> (s - 1))
+
+        cuda = content_own.is_cuda
+        style_res, slots = {}, {}
+        if split:
+            if cuda:
+                cur = torch.cuda.current_stream()
+                if getattr(self, "_side", None) is None:
+                    self._main, self._side = torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=0)
+                main, side = self._main, self._side
+                main.wait_stream(cur)
+                side.wait_stream(cur)
+
+            def launch_style(s, after=None):
+                if s in style_res:
+                    return
+                st, s_region, s_count = style_args(s)
+                if not cuda:
+                    style_res[s] = (stage_fn.style_part(s, st, s_region, s_count), None)
+                    return
+                with torch.cuda.stream(side):
+                    if after is not None:
+                        side.wait_event(after)
+                    res = stage_fn.style_part(s, st, s_region, s_count)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    for t in res:
+                        t.record_stream(main)
+                    style_res[s] = (res, ev)
+            todo = list(dict.fromkeys(stages))
+            launch_style(todo[0])
+            slots[todo[0]] = todo[1:3]
+            for i in range(1, len(todo)):
+                if i + 2 < len(todo):
+                    slots[todo[i]] = [todo[i + 2]]
+
+        def content_chain(img, Wc_tot):
+            for _ in range(num_run):
+                for s in stages:
+                    h = stage_halo(mode, s)
+                    ext, lh, rh = self.exchange(img, h)
+                    H, We = ext.shape[-2:]
+                    c_region = (0, H, lh, We - rh)
+                    sh = s - 1
+                    c_count = (H >> sh) * (Wc_tot >> sh)
+                    if split:
+                        # the style stages assigned to this slot are issued BEFORE this stage's content work in program order
+                        # (NCCL runs collectives in issue order); on the device they wait for the content statistics
+                        pending = slots.pop(s, [])
+
+                        def release():          # content statistics enqueued: the eigensolve gap starts here
+                            ev_slot = None
+                            if cuda:
+                                ev_slot = torch.cuda.Event()
+                                ev_slot.record(torch.cuda.current_stream())
+                            for ss in pending:
+                                launch_style(ss, ev_slot)
+
+                        def get_style():
+                            res, ev = style_res[s]
+                            if ev is not None:
+                                torch.cuda.current_stream().wait_event(ev)
+                            return res
+                        out = stage_fn.content_part(s, ext, get_style, alpha, c_region, c_count, before_eig=release)
+                    else:
+                        st, s_region, s_count = style_args(s)
+                        out = stage_fn(s, ext, st, alpha, c_region, s_region, c_count, s_count)
+                    Wc_tot = (Wc_tot >> sh) << sh          # floor-pool drops trailing columns of the whole image
+                    # floor-pool may have dropped trailing rows/cols (global right/bottom edge only)
+                    x1 = min(We - rh, out.shape[-1])
+                    img = out[..., lh:x1].contiguous()
+            return img
+
+        if split and cuda:
+            with torch.cuda.stream(main):
+                img = content_chain(img, Wc_tot)
+                img.record_stream(cur)
+            cur.wait_stream(main)
+            cur.wait_stream(side)
+            return img
+        return content_chain(img, Wc_tot)

@@ -97,8 +97,11 @@ class WCT(nn.Module):
         # tile-invariant (sharded == single GPU to fp64 summation order).
         prec = nets.get_precision()
         C = x_p4.shape[0] * 4
-        fast = self.dist is None and ((prec == "tf32" and self.fast_stats) or
-                                      (prec == "h2" and self.fast_stats_h2 and count >= 65536 and count >= 64 * C))
+        # TF32 engine: fp32-product Gram only on a single GPU (its 1e-7 partition-dependent differences are amplified by the
+        # lossy pipeline: 0.185 max between partitions on a noise image).  h2 engine: large maps on one or many GPUs (the
+        # partition dependence, 1e-8 of the Gram, stays below the features' own 1e-6; tests/test_multi_gpu.py states the bound)
+        fast = ((prec == "tf32" and self.fast_stats and self.dist is None) or
+                (prec == "h2" and self.fast_stats_h2 and count >= 65536 and count >= 64 * C))
         ops.centered_gram(x_p4, mean, region, out=gram_out, fast=fast)
         return mean
 
@@ -168,6 +171,55 @@ class WCT(nn.Module):
         reg = lambda r: None if r is None else tuple(v >> sh for v in r)
         m, b, mc = self._wct_params(c4, s4, float(alpha), reg(c_region), reg(s_region), c_count, s_count)
         del s4
+        if self.fold_into_decoder:
+            L0 = getattr(dec, dec.layers[0]["name"])
+            w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
+            return dec.forward_p4(c4 if c8 is None else c8, first_override=(w, bb))
+        cs4 = ops.wct_apply(c4, m, b, mc, round_tf32=dec.first_layer_needs_tf32_input())
+        del c4
+        return dec.forward_p4(cs4)
+
+    # ---- the same stage in two halves, for the strip driver (parallel.StripGroup): the style half does not depend on the
+    # content image, so the driver runs it on a side stream / releases it into the content eigensolve gaps
+    @torch.no_grad()
+    def style_part(self, stage, style, s_region=None, s_count=None):
+        """-> (mean fp64 [C], eigenvalues [C], eigenvectors [C,C]) of the style features of this stage; statistics over
+        `s_region` (image pixels) only and all-reduced over the ranks when sharded (util_wct.py:93-100)"""
+        enc = getattr(self, "e%d" % stage)
+        sh = stage - 1
+        s4 = enc.forward_p4(style)
+        C = s4.shape[0] * 4
+        reg = (0, s4.shape[1], 0, s4.shape[2]) if s_region is None else tuple(v >> sh for v in s_region)
+        n = float(s_count if s_count is not None else (reg[1] - reg[0]) * (reg[3] - reg[2]))
+        gram = torch.zeros(1, C, C, device=s4.device, dtype=torch.float64)
+        mean = self._moments(s4, reg, n, gram[0])
+        if self.dist is not None:
+            self.dist.allreduce_(gram)
+        evals, evecs = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], early_stop=self._early())
+        return mean, evals[0], evecs[0]
+
+    @torch.no_grad()
+    def content_part(self, stage, content, style_res, alpha=1.0, c_region=None, c_count=None, before_eig=None):
+        """content half of styleTransfer (WCT.py:98-106) given the style half's result -> stylized image (extended strip).
+        style_res may be a callable returning it (evaluated after the eigensolve is enqueued); before_eig() is called when the
+        content statistics are enqueued, i.e. where the single-CTA eigensolve starts and the GPU has room for other work."""
+        enc, dec = getattr(self, "e%d" % stage), getattr(self, "d%d" % stage)
+        sh = stage - 1
+        c4, c8 = self._encode_content(enc, dec, content)
+        C = c4.shape[0] * 4
+        reg = (0, c4.shape[1], 0, c4.shape[2]) if c_region is None else tuple(v >> sh for v in c_region)
+        n = float(c_count if c_count is not None else (reg[1] - reg[0]) * (reg[3] - reg[2]))
+        gram = torch.zeros(1, C, C, device=c4.device, dtype=torch.float64)
+        c_mean = self._moments(c4, reg, n, gram[0])
+        if self.dist is not None:
+            self.dist.allreduce_(gram)
+        numpy_variant = bool(getattr(self.args, "numpy", False))
+        if before_eig is not None:
+            before_eig()
+        c_e, c_v = ops.eigh_jacobi(gram, [1.0 / (n - 1.0)], add_identity=numpy_variant, early_stop=self._early())
+        s_mean, s_e, s_v = style_res() if callable(style_res) else style_res
+        k = self._keep(C)
+        m, b, mc = ops.wct_matrix(c_e[0], c_v[0], c_mean, s_e, s_v, s_mean, self.tau, float(alpha), k, k)
         if self.fold_into_decoder:
             L0 = getattr(dec, dec.layers[0]["name"])
             w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)

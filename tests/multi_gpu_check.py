@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""Multi-GPU tile-invariance check (run under torchrun on N GPUs):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py [--native-halo]
-The strip-sharded stylization must equal the single-GPU result (same kernels per pixel; statistics differ only by
-fp64 summation order)."""
+"""Multi-GPU tile-invariance check (run under torchrun on N GPUs; tests/test_multi_gpu.py launches it on 2):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+The strip-sharded stylization (halo exchange + statistic all-reduces, overlapped two-stream schedule) against the DEFAULT
+single-GPU output of the same engine, and both against the CPU oracle.  Per pixel the convolution arithmetic is identical;
+the statistics differ by summation order (fp64 Gram) or by the partition of fp32 partial sums (h2 engine, large maps)."""
+import json
 import os
 import sys
 from types import SimpleNamespace
@@ -14,6 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import collaborative_distillation_b200 as P  # noqa: E402
 from collaborative_distillation_b200 import parallel  # noqa: E402
+from oracle import wct_oracle as O  # noqa: E402
+
+# (precision, max |sharded - single GPU default|, rms vs oracle) bounds; measured values in profiles/r02_multi_gpu_check.txt
+BOUNDS = {"h2": (2e-3, 3e-4), "fp32": (2e-3, 3e-4)}
 
 
 def main():
@@ -21,40 +27,55 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    ok = True
-    for precision, tol in (("fp32", 2e-4), ("tf32", 5e-3)):
+    big = "--big" in sys.argv
+    ok, report = True, []
+    wpath = os.path.join(ROOT, "tests", "golden", "weights_16x.npz")
+    for precision in (("h2",) if big else ("h2", "fp32")):
         P.set_precision(precision)
         wct = P.WCT(SimpleNamespace(mode="16x", numpy=False))
-        P.weights.load_npz_into(wct, os.path.join(ROOT, "tests", "golden", "weights_16x.npz"))
+        P.weights.load_npz_into(wct, wpath)
         wct = wct.to(dev)
         g = torch.Generator().manual_seed(0)
-        Wc = 336 * world + 8          # not a multiple of 16: exercises the floor-pool remainder on the last strip
-        content = torch.rand(1, 3, 200, Wc, generator=g)
-        style = torch.rand(1, 3, 180, 352 * world, generator=g)
-        ref = None
+        # width not a multiple of 16: exercises the floor-pool remainder on the last strip.  --big: maps large enough for the
+        # fp32-product Gram of the h2 engine (>= 65536 feature pixels), i.e. the partition-dependent statistics path
+        H, Wc, Hs, Ws = (1040, 544 * world + 8, 600, 512 * world) if big else (200, 336 * world + 8, 180, 352 * world)
+        content = torch.rand(1, 3, H, Wc, generator=g)
+        style = torch.rand(1, 3, Hs, Ws, generator=g)
+        ref = oracle = None
         if rank == 0:
             wct.dist = None
-            wct.fast_stats = False             # the sharded path always uses the fp64 Gram (partition independent)
-            wct.eig_early = 1e-4               # ... and the tight eigensolver early stop (WCT._early)
-            ref = wct.stylize(content.to(dev), style.to(dev))
-        grp = parallel.StripGroup(native_halo="--native-halo" in sys.argv)   # libwctb halo pack/unpack instead of torch slicing
+            ref = wct.stylize(content.to(dev), style.to(dev)).cpu()          # the default single-GPU path (graph, fast stats, ...)
+            oracle = O.stylize(O.load_weights_npz(wpath), "16x", content, style)
+        grp = parallel.StripGroup(native_halo="--native-halo" in sys.argv)
         wct.dist = grp
-        own = grp.stylize(wct.style_transfer_stage, "16x",
-                          grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev),
-                          grp.own_slice(style, parallel.strip_cuts(style.shape[-1], world), rank).to(dev))
-        parts = [None] * world
-        dist.all_gather_object(parts, own.cpu())
+        own = grp.stylize(wct, "16x", grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev),
+                          grp.own_slice(style, parallel.strip_cuts(Ws, world), rank).to(dev), content_width=Wc, style_width=Ws)
+        # the legacy one-call-per-stage executor must agree with the overlapped one
+        own2 = grp.stylize(wct.style_transfer_stage, "16x", grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev),
+                           grp.own_slice(style, parallel.strip_cuts(Ws, world), rank).to(dev))
+        full = grp.gather_strips(own)
+        full2 = grp.gather_strips(own2)
         if rank == 0:
-            got = torch.cat(parts, dim=-1)
+            got = full.cpu()
             assert got.shape == ref.shape, (got.shape, ref.shape)
-            d = (got - ref.cpu()).abs().max().item()
-            print("multi_gpu_check[%s]: world=%d shape=%s max|sharded - single| = %.3g (tol %g)" % (
-                precision, world, tuple(got.shape), d, tol))
-            ok = ok and d <= tol
+            d = (got - ref).abs().max().item()
+            d2 = (full2.cpu() - got).abs().max().item()
+            e = got - oracle
+            rms, mx = e.pow(2).mean().sqrt().item(), e.abs().max().item()
+            tol_d, tol_rms = BOUNDS[precision]
+            line = ("multi_gpu_check[%s%s]: world=%d shape=%s max|sharded - single| = %.3g (tol %g)  overlapped vs per-stage executor %.3g  "
+                    "sharded vs oracle rms %.3g max %.3g (rms tol %g)" % (precision, " big" if big else "", world, tuple(got.shape), d, tol_d, d2, rms, mx, tol_rms))
+            print(line, flush=True)
+            report.append(line)
+            ok = ok and d <= tol_d and rms <= tol_rms and d2 <= tol_d
     dist.barrier()
     dist.destroy_process_group()
-    if rank == 0 and not ok:
-        sys.exit(1)
+    if rank == 0:
+        out = os.environ.get("WCTB_CHECK_OUT")
+        if out:
+            json.dump({"ok": ok, "lines": report}, open(out, "w"))
+        if not ok:
+            sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -65,7 +65,49 @@ def cpu_stage_fn(weights, mode, group):
     return fn
 
 
-def _worker(rank, world, port, content, style, stages, out_path):
+class CpuExecutor:
+    """the same algorithm as cpu_stage_fn in the two halves the overlapped strip driver uses (WCT.style_part / content_part)"""
+
+    def __init__(self, weights, mode, group):
+        self.w, self.mode, self.group = weights, mode, group
+
+    def _moments(self, F, region, count):
+        y0, y1, x0, x1 = region
+        x = F[:, y0:y1, x0:x1].double().reshape(F.shape[0], -1)
+        s = x.sum(1)
+        self.group.allreduce_(s)
+        mean = s / float(count)
+        xc = x - mean[:, None]
+        g = xc @ xc.t()
+        self.group.allreduce_(g)
+        return float(count), mean, g
+
+    def style_part(self, stage, style, s_region, s_count):
+        with torch.no_grad():
+            sF = O.encoder_forward(self.w["e%d" % stage], self.mode, stage, style).squeeze(0)
+            ns, sm, sg = self._moments(sF, tuple(v >> (stage - 1) for v in s_region), s_count)
+            se, sv = torch.linalg.eigh(sg / (ns - 1))
+        return sm, se, sv
+
+    def content_part(self, stage, content, style_res, alpha, c_region, c_count, before_eig=None):
+        with torch.no_grad():
+            cF = O.encoder_forward(self.w["e%d" % stage], self.mode, stage, content).squeeze(0)
+            nc, cm, cg = self._moments(cF, tuple(v >> (stage - 1) for v in c_region), c_count)
+            if before_eig is not None:
+                before_eig()
+            ce, cv = torch.linalg.eigh(cg / (nc - 1))
+            sm, se, sv = style_res() if callable(style_res) else style_res
+            kc, ks = ce > 1e-7 * ce.max(), se > 1e-7 * se.max()
+            Wm = (cv[:, kc] * ce[kc].pow(-0.5)) @ cv[:, kc].t()
+            Cm = (sv[:, ks] * se[ks].pow(0.5)) @ sv[:, ks].t()
+            M = alpha * (Cm @ Wm) + (1 - alpha) * torch.eye(cF.shape[0], dtype=torch.float64)
+            b = alpha * sm + (1 - alpha) * cm
+            x = cF.double().reshape(cF.shape[0], -1)
+            cs = (M @ (x - cm[:, None]) + b[:, None]).float().view_as(cF).unsqueeze(0)
+            return O.decoder_forward(self.w["d%d" % stage], self.mode, stage, cs)
+
+
+def _worker(rank, world, port, content, style, stages, out_path, split=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -75,8 +117,10 @@ def _worker(rank, world, port, content, style, stages, out_path):
         grp = parallel.StripGroup()
         ccuts = parallel.strip_cuts(content.shape[-1], world)
         scuts = parallel.strip_cuts(style.shape[-1], world)
-        own = grp.stylize(cpu_stage_fn(weights, "16x", grp), "16x", grp.own_slice(content, ccuts, rank),
-                          grp.own_slice(style, scuts, rank), alpha=1.0, stages=stages)
+        fn = CpuExecutor(weights, "16x", grp) if split else cpu_stage_fn(weights, "16x", grp)
+        kw = dict(content_width=content.shape[-1], style_width=style.shape[-1]) if split else {}    # host-known widths: no all-reduce
+        own = grp.stylize(fn, "16x", grp.own_slice(content, ccuts, rank), grp.own_slice(style, scuts, rank), alpha=1.0,
+                          stages=stages, **kw)
         parts = [None] * world
         dist.all_gather_object(parts, own.numpy())
         if rank == 0:
@@ -93,8 +137,9 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,Wc,Ws,stages", [(2, 704, 672, (5, 4)), (3, 208, 170, (3, 2, 1))])
-def test_strip_parallel_equals_single_process(tmp_path, world, Wc, Ws, stages):
+@pytest.mark.parametrize("world,Wc,Ws,stages,split", [(2, 704, 672, (5, 4), False), (3, 208, 170, (3, 2, 1), False),
+                                                      (2, 704, 672, (5, 4), True), (3, 208, 170, (3, 2, 1), True)])
+def test_strip_parallel_equals_single_process(tmp_path, world, Wc, Ws, stages, split):
     g = torch.Generator().manual_seed(3)
     content = torch.rand(1, 3, 40, Wc, generator=g)
     style = torch.rand(1, 3, 36, Ws, generator=g)
@@ -108,7 +153,7 @@ def test_strip_parallel_equals_single_process(tmp_path, world, Wc, Ws, stages):
     ref = O.stylize(weights, "16x", content, style, stages=stages)
     assert (img - ref).abs().max().item() <= 1e-4
     out_path = str(tmp_path / "out.npy")
-    mp.spawn(_worker, args=(world, _free_port(), content, style, stages, out_path), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), content, style, stages, out_path, split), nprocs=world, join=True)
     got = torch.from_numpy(np.load(out_path))
     assert got.shape == img.shape
     # same algorithm per pixel; on CPU oneDNN picks width-dependent conv blockings, so strips differ from the
