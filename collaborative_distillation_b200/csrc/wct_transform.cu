@@ -1129,35 +1129,53 @@ extern "C" int wctb_wct_apply(const float* x, const float* m, const float* b, co
 // ------------------------------------------------------------------------------------------
 __global__ void fold_w_kernel(const float* __restrict__ w, const float* __restrict__ m, float* __restrict__ w_out,
                               int Cin, int Cout) {
-  // one thread per (o, i, t)
+  // one thread per (o, i, t); four independent fp64 accumulators (the kernel sits on the critical path of every stage and a
+  // single dependent DFMA chain of Cin links is latency-bound)
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long n = (long long)Cout * Cin * 9;
   if (idx >= n) return;
   int t = (int)(idx % 9);
   int i = (int)((idx / 9) % Cin);
   int o = (int)(idx / (9LL * Cin));
-  double acc = 0;
-  for (int j = 0; j < Cin; ++j) acc = fma((double)w[((long long)o * Cin + j) * 9 + t], (double)m[(long long)j * Cin + i], acc);
-  w_out[idx] = (float)acc;
-}
-__global__ void fold_b_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ m,
-                              const float* __restrict__ b, const float* __restrict__ mean_c, float* __restrict__ b_out,
-                              int Cin, int Cout) {
-  // one warp per output channel
-  int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (o >= Cout) return;
-  double acc = 0;
-  for (int j = lane; j < Cin; j += 32) {
-    double mm = 0;
-    for (int i = 0; i < Cin; ++i) mm = fma((double)m[(long long)j * Cin + i], (double)mean_c[i], mm);
-    double d = (double)b[j] - mm;
-    double ws = 0;
-    for (int t = 0; t < 9; ++t) ws += (double)w[((long long)o * Cin + j) * 9 + t];
-    acc = fma(ws, d, acc);
+  const float* wr = w + (long long)o * Cin * 9 + t;
+  const float* mc = m + i;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  int j = 0;
+  for (; j + 3 < Cin; j += 4) {
+    a0 = fma((double)wr[(long long)j * 9], (double)mc[(long long)j * Cin], a0);
+    a1 = fma((double)wr[(long long)(j + 1) * 9], (double)mc[(long long)(j + 1) * Cin], a1);
+    a2 = fma((double)wr[(long long)(j + 2) * 9], (double)mc[(long long)(j + 2) * Cin], a2);
+    a3 = fma((double)wr[(long long)(j + 3) * 9], (double)mc[(long long)(j + 3) * Cin], a3);
   }
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) b_out[o] = (float)((double)bias[o] + acc);
+  for (; j < Cin; ++j) a0 = fma((double)wr[(long long)j * 9], (double)mc[(long long)j * Cin], a0);
+  w_out[idx] = (float)((a0 + a1) + (a2 + a3));
+}
+// b_out[o] = bias[o] + sum_j (sum_t w[o][j][t]) * (b[j] - sum_i m[j][i] mean_c[i]).  One CTA: phase 1 computes the Cin
+// values d[j] once (one warp per j, coalesced over i), phase 2 one warp per output channel.
+__global__ void __launch_bounds__(512) fold_b_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ m,
+                                                     const float* __restrict__ b, const float* __restrict__ mean_c, float* __restrict__ b_out,
+                                                     int Cin, int Cout) {
+  extern __shared__ double fold_d[];     // [Cin]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < Cin; j += nw) {
+    double mm = 0;
+    for (int i = lane; i < Cin; i += 32) mm = fma((double)m[(long long)j * Cin + i], (double)mean_c[i], mm);
+    for (int s = 16; s > 0; s >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, s);
+    if (lane == 0) fold_d[j] = (double)b[j] - mm;
+  }
+  __syncthreads();
+  for (int o = warp; o < Cout; o += nw) {
+    double acc = 0;
+    for (int j = lane; j < Cin; j += 32) {
+      const float* wp = w + ((long long)o * Cin + j) * 9;
+      double ws = 0;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) ws += (double)wp[t];
+      acc = fma(ws, fold_d[j], acc);
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) b_out[o] = (float)((double)bias[o] + acc);
+  }
 }
 extern "C" int wctb_fold_wct_into_conv(const float* w, const float* bias, const float* m, const float* b,
                                        const float* mean_c, float* w_out, float* b_out, int Cin, int Cout, void* stream) {
@@ -1165,6 +1183,7 @@ extern "C" int wctb_fold_wct_into_conv(const float* w, const float* bias, const 
   cudaStream_t st = (cudaStream_t)stream;
   long long n = (long long)Cout * Cin * 9;
   fold_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, m, w_out, Cin, Cout);
-  fold_b_kernel<<<(Cout + 7) / 8, 256, 0, st>>>(w, bias, m, b, mean_c, b_out, Cin, Cout);
+  if (Cin > 4096) return WCTB_E_UNSUPPORTED;
+  fold_b_kernel<<<1, 512, (size_t)Cin * sizeof(double), st>>>(w, bias, m, b, mean_c, b_out, Cin, Cout);
   WCTB_RETURN_LAUNCH();
 }
