@@ -16,6 +16,14 @@ _i = ctypes.c_int
 _ll = ctypes.c_longlong
 _d = ctypes.c_double
 
+class TailShard(ctypes.Structure):
+    """wctb_tail_shard (include/wctb.h): output placement of the strip-sharded fused tail, incl. the neighbours' peer pointers"""
+    _fields_ = [("out", ctypes.c_void_p), ("out_pitch", ctypes.c_int), ("out_x0", ctypes.c_int),
+                ("own_x0", ctypes.c_int), ("own_w", ctypes.c_int), ("halo", ctypes.c_int),
+                ("peer_l", ctypes.c_void_p), ("peer_l_pitch", ctypes.c_int), ("peer_l_x0", ctypes.c_int),
+                ("peer_r", ctypes.c_void_p), ("peer_r_pitch", ctypes.c_int), ("peer_r_x0", ctypes.c_int)]
+
+
 # name -> argtypes ; every function returns int except where noted
 SIGNATURES = {
     "wctb_abi_version": [],
@@ -35,6 +43,7 @@ SIGNATURES = {
     "wctb_conv3x3_first_h2": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "wctb_conv_head_h2": [_p, _p, _p, ctypes.c_float, _p, _p, ctypes.c_float, _p, _i, _i, _p],
     "wctb_conv_tail_h2": [_p, _p, _p, ctypes.c_float, _p, _p, ctypes.c_float, _p, _i, _i, _i, _p],
+    "wctb_conv_tail_h2_sharded": [_p, _p, _p, ctypes.c_float, _p, _p, ctypes.c_float, _i, _i, _i, ctypes.POINTER(TailShard), _p],
     "wctb_nchw_to_h8": [_p, _p, _i, _i, _i, _p],
     "wctb_h8_to_nchw": [_p, _p, _i, _i, _i, _p],
     "wctb_p4_to_h8": [_p, _p, _i, _i, _i, _p],

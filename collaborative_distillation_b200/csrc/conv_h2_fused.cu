@@ -420,8 +420,17 @@ struct TailH2Args {
   const float* b12;     // [16]
   const float* b11;     // [3]
   float inv_s12, inv_s11;
-  float* img;           // [3][H][W]
+  float* img;           // [3][H][W]  (sharded: the rank's NEXT-stage extended strip, see TailShard)
   int H, W, ups, tiles_x, ntiles;
+  // Strip-sharded output (multi-GPU): only the rank's own columns [own_x0, own_x0 + own_w) of the computed image are kept.
+  // They go to the local buffer at column out_x0 (pitch out_pitch) and, for the `halo` columns next to a seam, ALSO straight
+  // into the neighbour's next-stage buffer through its peer-mapped pointer (st.global over NVLink): the halo exchange of
+  // the next stage happens inside this kernel's epilogue instead of a pack / send / recv / unpack sequence.
+  // Unsharded: own_x0 = 0, own_w = W, out_pitch = W, out_x0 = 0, peers null.
+  int own_x0, own_w, out_pitch, out_x0, halo;
+  long long out_plane;
+  float* peer_l; int peer_l_pitch, peer_l_x0; long long peer_l_plane;     // our first `halo` own columns -> left neighbour's right halo
+  float* peer_r; int peer_r_pitch, peer_r_x0; long long peer_r_plane;     // our last `halo` own columns -> right neighbour's left halo
 };
 using TC = FCfg<4>;                                           // tail tile: 16 rows x 28 columns
 constexpr int TL_IN_ROWS = 4 * TC::NB1 + 2;                   // 22 input rows (tile rows -2 .. 19)
@@ -519,7 +528,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
     const int q = warp & 3, grp = (warp - 2) >> 2;
     const uint32_t tq = tmem_base + F_ACC2 + ((uint32_t)(32 * q) << 16);
     const float b0 = __ldg(h.b11), b1 = __ldg(h.b11 + 1), b2 = __ldg(h.b11 + 2);
-    const long long HW = (long long)H * W;
     uint32_t g2 = 0;
     for (int i = 0; i < ntl; ++i) {
       const FTile t = f_tile<TC>((int)blockIdx.x + i * (int)gridDim.x, h.tiles_x, H);
@@ -541,11 +549,22 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
         for (int c = 0; c < 3; ++c)
           v[c] = (m[0][c] + m[3][c]) + __shfl_down_sync(0xffffffffu, m[1][c] + m[4][c], 1) + __shfl_down_sync(0xffffffffu, m[2][c] + m[5][c], 2);
         const int gy = t.ya + 4 * k + q, gx = t.x0 + lane;
-        if (lane < F_TW && gy < H && gx < W) {
-          const long long o = (long long)gy * W + gx;
-          h.img[o] = wctb_relu(fmaf(v[0], h.inv_s11, b0));
-          h.img[HW + o] = wctb_relu(fmaf(v[1], h.inv_s11, b1));
-          h.img[2 * HW + o] = wctb_relu(fmaf(v[2], h.inv_s11, b2));
+        const int ox = gx - h.own_x0;
+        if (lane < F_TW && gy < H && gx < W && ox >= 0 && ox < h.own_w) {
+          const float r0 = wctb_relu(fmaf(v[0], h.inv_s11, b0)), r1 = wctb_relu(fmaf(v[1], h.inv_s11, b1)),
+                      r2 = wctb_relu(fmaf(v[2], h.inv_s11, b2));
+          const long long o = (long long)gy * h.out_pitch + ox + h.out_x0;
+          h.img[o] = r0;
+          h.img[h.out_plane + o] = r1;
+          h.img[2 * h.out_plane + o] = r2;
+          if (h.peer_l && ox < h.halo) {                      // peer store: the left neighbour's right halo
+            const long long p = (long long)gy * h.peer_l_pitch + ox + h.peer_l_x0;
+            h.peer_l[p] = r0; h.peer_l[h.peer_l_plane + p] = r1; h.peer_l[2 * h.peer_l_plane + p] = r2;
+          }
+          if (h.peer_r && ox >= h.own_w - h.halo) {           // peer store: the right neighbour's left halo
+            const long long p = (long long)gy * h.peer_r_pitch + (ox - (h.own_w - h.halo)) + h.peer_r_x0;
+            h.peer_r[p] = r0; h.peer_r[h.peer_r_plane + p] = r1; h.peer_r[2 * h.peer_r_plane + p] = r2;
+          }
         }
       }
     }
@@ -625,20 +644,42 @@ extern "C" int wctb_conv_head_h2(const float* x_nchw, const void* w11_packed, co
   WCTB_RETURN_LAUNCH();
 }
 
+static int launch_tail_h2(TailH2Args h, cudaStream_t st) {
+  static bool done[64] = {};
+  int rc = ensure_smem_attr(conv_tail_h2_kernel, TL_SMEM, done);
+  if (rc != WCTB_OK) return rc;
+  h.tiles_x = (h.W + F_TW - 1) / F_TW;
+  h.ntiles = h.tiles_x * ((h.H + TC::TH - 1) / TC::TH);
+  const int grid = h.ntiles < wctb_num_sms() ? h.ntiles : wctb_num_sms();
+  conv_tail_h2_kernel<<<grid, F_THREADS, TL_SMEM, st>>>(h);
+  WCTB_RETURN_LAUNCH();
+}
+
 extern "C" int wctb_conv_tail_h2(const void* x_h8, const void* w12_packed, const float* b12, float inv_s12,
                                  const void* w11_packed, const float* b11, float inv_s11, float* y_nchw, int H, int W,
                                  int upsample_input, void* stream) {
   if (!x_h8 || !w12_packed || !b12 || !w11_packed || !b11 || !y_nchw || H < 2 || W < 2) return WCTB_E_BADARG;
   if (upsample_input && ((H & 1) || (W & 1))) return WCTB_E_BADARG;
   if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
-  static bool done[64] = {};
-  int rc = ensure_smem_attr(conv_tail_h2_kernel, TL_SMEM, done);
-  if (rc != WCTB_OK) return rc;
   TailH2Args h{(const uint4*)x_h8, (const __half*)w12_packed, (const __half*)w11_packed, b12, b11, inv_s12, inv_s11, y_nchw,
-               H, W, upsample_input ? 1 : 0, 0, 0};
-  h.tiles_x = (W + F_TW - 1) / F_TW;
-  h.ntiles = h.tiles_x * ((H + TC::TH - 1) / TC::TH);
-  const int grid = h.ntiles < wctb_num_sms() ? h.ntiles : wctb_num_sms();
-  conv_tail_h2_kernel<<<grid, F_THREADS, TL_SMEM, (cudaStream_t)stream>>>(h);
-  WCTB_RETURN_LAUNCH();
+               H, W, upsample_input ? 1 : 0, 0, 0, 0, W, W, 0, 0, (long long)H * W, nullptr, 0, 0, 0, nullptr, 0, 0, 0};
+  return launch_tail_h2(h, (cudaStream_t)stream);
+}
+
+extern "C" int wctb_conv_tail_h2_sharded(const void* x_h8, const void* w12_packed, const float* b12, float inv_s12,
+                                         const void* w11_packed, const float* b11, float inv_s11, int H, int W, int upsample_input,
+                                         const wctb_tail_shard* sh, void* stream) {
+  if (!x_h8 || !w12_packed || !b12 || !w11_packed || !b11 || !sh || !sh->out || H < 2 || W < 2) return WCTB_E_BADARG;
+  if (upsample_input && ((H & 1) || (W & 1))) return WCTB_E_BADARG;
+  if ((long long)H * W >= (1LL << 31)) return WCTB_E_UNSUPPORTED;
+  if (sh->own_x0 < 0 || sh->own_w <= 0 || sh->own_x0 + sh->own_w > W || sh->halo < 0 || sh->halo > sh->own_w ||
+      sh->out_x0 < 0 || sh->out_x0 + sh->own_w > sh->out_pitch)
+    return WCTB_E_BADARG;
+  if ((sh->peer_l && sh->peer_l_x0 + sh->halo > sh->peer_l_pitch) || (sh->peer_r && sh->peer_r_x0 + sh->halo > sh->peer_r_pitch))
+    return WCTB_E_BADARG;
+  TailH2Args h{(const uint4*)x_h8, (const __half*)w12_packed, (const __half*)w11_packed, b12, b11, inv_s12, inv_s11, sh->out,
+               H, W, upsample_input ? 1 : 0, 0, 0, sh->own_x0, sh->own_w, sh->out_pitch, sh->out_x0, sh->halo,
+               (long long)H * sh->out_pitch, sh->peer_l, sh->peer_l_pitch, sh->peer_l_x0, (long long)H * sh->peer_l_pitch,
+               sh->peer_r, sh->peer_r_pitch, sh->peer_r_x0, (long long)H * sh->peer_r_pitch};
+  return launch_tail_h2(h, (cudaStream_t)stream);
 }

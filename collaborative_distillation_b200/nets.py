@@ -250,9 +250,10 @@ class _Encoder(_Net):
 class _Decoder(_Net):
     KIND = "dec"
 
-    def forward_p4(self, y, precision=None, first_override=None):
+    def forward_p4(self, y, precision=None, first_override=None, tail_shard=None):
         """y P4 [C/4,h,w,4] -> image [1,3,H,W].  first_override=(w_oihw, bias) replaces the first conv's
-        parameters (used to fold the WCT matrix into it)."""
+        parameters (used to fold the WCT matrix into it).  tail_shard: see ops.conv_tail_h2 (strip-sharded output written
+        by the fused tail kernel; ignored -- a plain image is returned -- when this decoder has no fused h2 tail)."""
         self._check_cuda(y)
         precision = precision or _PRECISION
         pk = list(self.packed(precision))
@@ -260,7 +261,7 @@ class _Decoder(_Net):
             pk[0] = self._pack_layer(0, precision, first_override[0], first_override[1])
         n = len(self.layers)
         if precision == "h2":
-            return self._forward_h2(y, pk)
+            return self._forward_h2(y, pk, tail_shard)
         if y.dtype == torch.float16:
             raise WctbError("an H8 feature needs the h2 engine")
         if y.shape[1] < 2 or y.shape[2] < 2:
@@ -282,7 +283,7 @@ class _Decoder(_Net):
             return ops.conv3x3_p4(y, pk[n - 1]["w_last_tc"], pk[n - 1]["b_last_tc"], 16, ops.EPI_NCHW3, False, ops.ENGINE_TF32)
         return ops.conv3x3_last(y, pk[n - 1]["w"], pk[n - 1]["b"])
 
-    def _forward_h2(self, y, pk):
+    def _forward_h2(self, y, pk, tail_shard=None):
         """h2 engine: y is an H8 feature (or fp32 P4, converted) -> image [1,3,H,W]"""
         if y.dtype != torch.float16:
             y = ops.p4_to_h8(y)
@@ -298,7 +299,7 @@ class _Decoder(_Net):
             y, _ = ops.conv3x3_h2(y, pk[i]["w"], pk[i]["ws"], pk[i]["b"], L["cin"], L["cout"], epi)
         if fuse_tail:
             return ops.conv_tail_h2(y, pk[n - 2]["w_dx"], pk[n - 2]["inv_s_dx"], pk[n - 2]["b"], pk[n - 1]["w_dx"], pk[n - 1]["inv_s_dx"],
-                                    pk[n - 1]["b"], bool(self.layers[n - 3]["up_after"]))
+                                    pk[n - 1]["b"], bool(self.layers[n - 3]["up_after"]), shard=tail_shard)
         L = self.layers[n - 1]
         return ops.conv3x3_h2(y, pk[n - 1]["w"], pk[n - 1]["ws"], pk[n - 1]["b"], L["cin"], 16, ops.EPI_NCHW3)[1]
 

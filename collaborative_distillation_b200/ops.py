@@ -516,14 +516,35 @@ def conv_head_h2(x_nchw: torch.Tensor, w11p, inv_s11: float, b11, w12p, inv_s12:
     return y
 
 
-def conv_tail_h2(x_h8: torch.Tensor, w12p, inv_s12: float, b12, w11p, inv_s11: float, b11, upsample_input: bool) -> torch.Tensor:
-    """fused [nearest x2 +] conv12(16->16)+ReLU+conv11(16->3)+ReLU of the 16x decoders: H8 [2,2,h,w,8] -> image [1,3,H,W]"""
+def conv_tail_h2(x_h8: torch.Tensor, w12p, inv_s12: float, b12, w11p, inv_s11: float, b11, upsample_input: bool,
+                 shard: dict = None) -> torch.Tensor:
+    """fused [nearest x2 +] conv12(16->16)+ReLU+conv11(16->3)+ReLU of the 16x decoders: H8 [2,2,h,w,8] -> image [1,3,H,W].
+    shard (multi-GPU): {"out": next-stage extended strip [1,3,H,We] (written in place and returned), "out_x0", "own_x0", "own_w",
+    "halo", "peer_l": (ptr, pitch, x0) | None, "peer_r": ...}: only the own columns are kept; the seam-side `halo` columns also go
+    straight into the neighbours' buffers over NVLink (wctb_conv_tail_h2_sharded)."""
     _need_h8(x_h8)
     _, _, h, w, _ = x_h8.shape
     H, W = (2 * h, 2 * w) if upsample_input else (h, w)
-    y = torch.empty(1, 3, H, W, device=x_h8.device, dtype=torch.float32)
-    check(_lib.load().wctb_conv_tail_h2(_need(x_h8, torch.float16), _need(w12p, torch.float16), _need(b12), float(inv_s12),
-                                        _need(w11p, torch.float16), _need(b11), float(inv_s11), _need(y), H, W,
-                                        int(upsample_input), _stream()), "conv_tail_h2")
+    lib = _lib.load()
+    if shard is None:
+        y = torch.empty(1, 3, H, W, device=x_h8.device, dtype=torch.float32)
+        check(lib.wctb_conv_tail_h2(_need(x_h8, torch.float16), _need(w12p, torch.float16), _need(b12), float(inv_s12),
+                                    _need(w11p, torch.float16), _need(b11), float(inv_s11), _need(y), H, W,
+                                    int(upsample_input), _stream()), "conv_tail_h2")
+        _count("conv_tail_h2")
+        return y
+    out = shard["out"]
+    if out.shape[-2] != H or out.dim() != 4 or out.shape[1] != 3:
+        raise _lib.WctbError("sharded tail: output strip %s does not match the image height %d" % (tuple(out.shape), H))
+    ts = _lib.TailShard()
+    ts.out, ts.out_pitch, ts.out_x0 = _need(out), out.shape[-1], int(shard["out_x0"])
+    ts.own_x0, ts.own_w, ts.halo = int(shard["own_x0"]), int(shard["own_w"]), int(shard["halo"])
+    pl, pr = shard.get("peer_l"), shard.get("peer_r")
+    ts.peer_l, ts.peer_l_pitch, ts.peer_l_x0 = (pl[0], pl[1], pl[2]) if pl else (None, 0, 0)
+    ts.peer_r, ts.peer_r_pitch, ts.peer_r_x0 = (pr[0], pr[1], pr[2]) if pr else (None, 0, 0)
+    import ctypes
+    check(lib.wctb_conv_tail_h2_sharded(_need(x_h8, torch.float16), _need(w12p, torch.float16), _need(b12), float(inv_s12),
+                                        _need(w11p, torch.float16), _need(b11), float(inv_s11), H, W, int(upsample_input),
+                                        ctypes.byref(ts), _stream()), "conv_tail_h2_sharded")
     _count("conv_tail_h2")
-    return y
+    return out

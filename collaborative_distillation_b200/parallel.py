@@ -47,6 +47,52 @@ def strip_cuts(W: int, world: int):
     return cuts
 
 
+class PeerHalo:
+    """Peer-mapped next-stage strip buffers for the fused tail kernel (compute + halo exchange in one kernel).
+
+    Every rank owns two device buffers (double buffer: a neighbour may already write stage k-1's halo while the owner still
+    reads stage k's strip) and opens its neighbours' buffers through CUDA IPC, so `wctb_conv_tail_h2_sharded` can store the
+    seam-side columns of its output straight into the neighbours' next-stage strips over NVLink.  One tiny all-reduce per stage
+    is the cross-rank barrier (stream-ordered: every rank's tail kernel has completed before any rank's next encoder starts)."""
+
+    def __init__(self, group, nbytes: int, device):
+        import torch.distributed as dist
+        self.group, self.rank, self.world = group, dist.get_rank(group), dist.get_world_size(group)
+        self.nbytes = int(nbytes)
+        self.local = [torch.empty(self.nbytes, dtype=torch.uint8, device=device) for _ in range(2)]
+        mine = [t.untyped_storage()._share_cuda_() for t in self.local]
+        table = [None] * self.world
+        dist.all_gather_object(table, mine, group=group)
+        self.peer = {}
+        self._keep = []
+        for r in (self.rank - 1, self.rank + 1):
+            if 0 <= r < self.world:
+                bufs = []
+                for h in table[r]:
+                    with torch.cuda.device(h[0]):
+                        st = torch.UntypedStorage._new_shared_cuda(*h)
+                    t = torch.empty(0, dtype=torch.uint8, device=st.device).set_(st)
+                    # first touch from this device: makes torch enable peer access between the two devices
+                    self.local[0][:16].copy_(t[:16])
+                    self.local[0][:16].zero_()
+                    bufs.append(t)
+                    self._keep.append(st)
+                self.peer[r] = bufs
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def local_view(self, b: int, H: int, We: int) -> torch.Tensor:
+        return self.local[b][:3 * H * We * 4].view(torch.float32).view(1, 3, H, We)
+
+    def peer_ptr(self, r: int, b: int) -> int:
+        return self.peer[r][b].data_ptr()
+
+    def barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.flag, group=self.group)
+
+
 class StripGroup:
     """Strip-parallel driver.  `stage_fn(stage, content_ext, style_ext, alpha, c_region, s_region, c_count, s_count) -> image_ext`
     is `WCT.style_transfer_stage` in production (with `wct.dist = self`), or a CPU restatement in the gloo tests."""
@@ -59,6 +105,11 @@ class StripGroup:
         # (wctb_halo_pack / wctb_halo_unpack) instead of torch slicing + cat.  Same bytes either way; off until its first
         # multi-GPU run is on record (the kernels themselves are covered by the single-GPU tests).
         self.native_halo = native_halo
+        # peer_halo: let the fused tail kernel write the next stage's halo straight into the neighbours' buffers (PeerHalo);
+        # WCTB_PEER_HALO=0 falls back to pack / send / recv / cat for every stage
+        import os
+        self.peer_halo = os.environ.get("WCTB_PEER_HALO", "1") == "1"
+        self._peer = None
 
     # ---- collectives used by WCT._moments
     def allreduce_(self, t: torch.Tensor):
@@ -166,13 +217,14 @@ class StripGroup:
             def launch_style(s, after=None):
                 if s in style_res:
                     return
-                st, s_region, s_count = style_args(s)
                 if not cuda:
+                    st, s_region, s_count = style_args(s)
                     style_res[s] = (stage_fn.style_part(s, st, s_region, s_count), None)
                     return
                 with torch.cuda.stream(side):
                     if after is not None:
                         side.wait_event(after)
+                    st, s_region, s_count = style_args(s)        # the strip copy must run on the stream that consumes it
                     res = stage_fn.style_part(s, st, s_region, s_count)
                     ev = torch.cuda.Event()
                     ev.record(side)
@@ -186,41 +238,92 @@ class StripGroup:
                 if i + 2 < len(todo):
                     slots[todo[i]] = [todo[i + 2]]
 
+        # per-rank own widths (every rank can compute every rank's geometry: cuts are a pure function of the total width)
+        widths = None
+        use_peer = split and cuda and self.peer_halo and self.world > 1 and content_width is not None
+        if use_peer:
+            cuts = strip_cuts(int(content_width), self.world)
+            widths = [cuts[i + 1] - cuts[i] for i in range(self.world)]
+            if widths[self.rank] != content_own.shape[-1]:
+                use_peer = False                      # caller did not use strip_cuts(): geometry of the neighbours unknown
+        if use_peer:
+            H0 = content_own.shape[-2]
+            need = 3 * H0 * (max(widths) + 2 * hmax) * 4
+            if self._peer is None or self._peer.nbytes < need:
+                self._peer = PeerHalo(self.group, need, content_own.device)
+
         def content_chain(img, Wc_tot):
-            for _ in range(num_run):
-                for s in stages:
-                    h = stage_halo(mode, s)
+            nonlocal widths
+            r, n = self.rank, self.world
+            pending_ext = None                        # (ext, lh, rh) already assembled in a peer buffer by the previous stage's tail
+            pbuf = 0
+            seq = [s for _ in range(num_run) for s in stages]
+            for idx, s in enumerate(seq):
+                h = stage_halo(mode, s)
+                if pending_ext is not None:
+                    ext, lh, rh = pending_ext
+                    pending_ext = None
+                else:
                     ext, lh, rh = self.exchange(img, h)
-                    H, We = ext.shape[-2:]
-                    c_region = (0, H, lh, We - rh)
-                    sh = s - 1
-                    c_count = (H >> sh) * (Wc_tot >> sh)
-                    if split:
-                        # the style stages assigned to this slot are issued BEFORE this stage's content work in program order
-                        # (NCCL runs collectives in issue order); on the device they wait for the content statistics
-                        pending = slots.pop(s, [])
+                H, We = ext.shape[-2:]
+                c_region = (0, H, lh, We - rh)
+                sh = s - 1
+                c_count = (H >> sh) * (Wc_tot >> sh)
+                if split:
+                    # the style stages assigned to this slot are issued BEFORE this stage's content work in program order
+                    # (NCCL runs collectives in issue order); on the device they wait for the content statistics
+                    pending = slots.pop(s, [])
 
-                        def release():          # content statistics enqueued: the eigensolve gap starts here
-                            ev_slot = None
-                            if cuda:
-                                ev_slot = torch.cuda.Event()
-                                ev_slot.record(torch.cuda.current_stream())
-                            for ss in pending:
-                                launch_style(ss, ev_slot)
+                    def release():          # content statistics enqueued: the eigensolve gap starts here
+                        ev_slot = None
+                        if cuda:
+                            ev_slot = torch.cuda.Event()
+                            ev_slot.record(torch.cuda.current_stream())
+                        for ss in pending:
+                            launch_style(ss, ev_slot)
 
-                        def get_style():
-                            res, ev = style_res[s]
-                            if ev is not None:
-                                torch.cuda.current_stream().wait_event(ev)
-                            return res
-                        out = stage_fn.content_part(s, ext, get_style, alpha, c_region, c_count, before_eig=release)
-                    else:
-                        st, s_region, s_count = style_args(s)
-                        out = stage_fn(s, ext, st, alpha, c_region, s_region, c_count, s_count)
-                    Wc_tot = (Wc_tot >> sh) << sh          # floor-pool drops trailing columns of the whole image
-                    # floor-pool may have dropped trailing rows/cols (global right/bottom edge only)
-                    x1 = min(We - rh, out.shape[-1])
-                    img = out[..., lh:x1].contiguous()
+                    def get_style():
+                        res, ev = style_res[s]
+                        if ev is not None:
+                            torch.cuda.current_stream().wait_event(ev)
+                        return res
+                    shard = None
+                    if use_peer and idx + 1 < len(seq):
+                        # geometry of the NEXT stage's extended strips on this rank and on both neighbours
+                        hn = stage_halo(mode, seq[idx + 1])
+                        wn = list(widths)
+                        wn[-1] = (wn[-1] >> sh) << sh                      # floor-pool drops trailing columns (global right edge)
+                        Hn = (H >> sh) << sh
+                        geo = lambda q: ((hn if q > 0 else 0), wn[q], (hn if q < n - 1 else 0))
+                        lhn, wown, rhn = geo(r)
+                        if min(wn) >= hn and wown > 0:
+                            out = self._peer.local_view(pbuf, Hn, lhn + wown + rhn)
+                            shard = {"out": out, "out_x0": lhn, "own_x0": lh, "own_w": wown, "halo": hn, "peer_l": None, "peer_r": None}
+                            if r > 0:
+                                ll, wl, rl = geo(r - 1)
+                                shard["peer_l"] = (self._peer.peer_ptr(r - 1, pbuf), ll + wl + rl, ll + wl)
+                            if r < n - 1:
+                                lr, wr, rr = geo(r + 1)
+                                shard["peer_r"] = (self._peer.peer_ptr(r + 1, pbuf), lr + wr + rr, 0)
+                    out = stage_fn.content_part(s, ext, get_style, alpha, c_region, c_count, before_eig=release, tail_shard=shard)
+                    if shard is not None and out is shard["out"]:
+                        # the fused tail wrote our strip and both neighbours' halos: one stream-ordered barrier, no exchange
+                        self._peer.barrier()
+                        widths = wn
+                        Wc_tot = (Wc_tot >> sh) << sh
+                        pending_ext = (out, lhn, rhn)
+                        pbuf ^= 1
+                        img = None
+                        continue
+                else:
+                    st, s_region, s_count = style_args(s)
+                    out = stage_fn(s, ext, st, alpha, c_region, s_region, c_count, s_count)
+                if widths is not None:
+                    widths[-1] = (widths[-1] >> sh) << sh
+                Wc_tot = (Wc_tot >> sh) << sh          # floor-pool drops trailing columns of the whole image
+                # floor-pool may have dropped trailing rows/cols (global right/bottom edge only)
+                x1 = min(We - rh, out.shape[-1])
+                img = out[..., lh:x1].contiguous()
             return img
 
         if split and cuda:

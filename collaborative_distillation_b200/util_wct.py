@@ -199,10 +199,12 @@ class WCT(nn.Module):
         return mean, evals[0], evecs[0]
 
     @torch.no_grad()
-    def content_part(self, stage, content, style_res, alpha=1.0, c_region=None, c_count=None, before_eig=None):
+    def content_part(self, stage, content, style_res, alpha=1.0, c_region=None, c_count=None, before_eig=None, tail_shard=None):
         """content half of styleTransfer (WCT.py:98-106) given the style half's result -> stylized image (extended strip).
         style_res may be a callable returning it (evaluated after the eigensolve is enqueued); before_eig() is called when the
-        content statistics are enqueued, i.e. where the single-CTA eigensolve starts and the GPU has room for other work."""
+        content statistics are enqueued, i.e. where the single-CTA eigensolve starts and the GPU has room for other work.
+        tail_shard: output placement for the fused tail kernel incl. the neighbours' peer pointers (ops.conv_tail_h2); the
+        returned tensor IS tail_shard["out"] when the decoder used it."""
         enc, dec = getattr(self, "e%d" % stage), getattr(self, "d%d" % stage)
         sh = stage - 1
         c4, c8 = self._encode_content(enc, dec, content)
@@ -223,10 +225,10 @@ class WCT(nn.Module):
         if self.fold_into_decoder:
             L0 = getattr(dec, dec.layers[0]["name"])
             w, bb = ops.fold_wct_into_conv(L0.weight.detach().contiguous(), L0.bias.detach().contiguous(), m, b, mc)
-            return dec.forward_p4(c4 if c8 is None else c8, first_override=(w, bb))
+            return dec.forward_p4(c4 if c8 is None else c8, first_override=(w, bb), tail_shard=tail_shard)
         cs4 = ops.wct_apply(c4, m, b, mc, round_tf32=dec.first_layer_needs_tf32_input())
         del c4
-        return dec.forward_p4(cs4)
+        return dec.forward_p4(cs4, tail_shard=tail_shard)
 
     def _encode_content(self, enc, dec, img):
         """content features as (fp32 P4 for the statistics, H8 for the decoder's folded first conv | None)"""

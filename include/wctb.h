@@ -155,6 +155,22 @@ int wctb_conv_head_h2(const float* x_nchw, const void* w11_packed, const float* 
  * w12_packed / w11_packed: ops.pack_dx_h2 layout (conv11's 3 output channels in rows dx*16 + {0,1,2}); b11: [3].        */
 int wctb_conv_tail_h2(const void* x_h8, const void* w12_packed, const float* b12, float inv_s12, const void* w11_packed,
                       const float* b11, float inv_s11, float* y_nchw, int H, int W, int upsample_input, void* stream);
+/* Strip-sharded variant of the fused tail (multi-GPU): compute + halo exchange in ONE kernel.  The image is
+ * computed for the whole extended strip (W columns), but only the rank's own columns [own_x0, own_x0 + own_w) are kept; they
+ * are written to `out` -- the rank's NEXT-stage extended strip [3][H][out_pitch] at column out_x0 -- and the `halo` columns next
+ * to a seam are additionally stored straight into the neighbours' next-stage strips through peer-mapped pointers (st.global
+ * over NVLink: peer_l = left neighbour's buffer, our columns land at peer_l_x0; peer_r likewise; NULL at a true image border).
+ * No pack / send / recv / unpack: the next stage starts after one cross-rank barrier.  All pointers are device pointers valid
+ * in THIS process (peer buffers opened through CUDA IPC / symmetric memory by the caller).                                  */
+typedef struct wctb_tail_shard {
+  float* out;    int out_pitch, out_x0;
+  int own_x0, own_w, halo;
+  float* peer_l; int peer_l_pitch, peer_l_x0;
+  float* peer_r; int peer_r_pitch, peer_r_x0;
+} wctb_tail_shard;
+int wctb_conv_tail_h2_sharded(const void* x_h8, const void* w12_packed, const float* b12, float inv_s12, const void* w11_packed,
+                              const float* b11, float inv_s11, int H, int W, int upsample_input, const wctb_tail_shard* shard,
+                              void* stream);
 /* layout conversion: NCHW fp32 <-> H8, fp32 P4 -> H8 */
 int wctb_nchw_to_h8(const float* src_nchw, void* dst_h8, int C, int H, int W, void* stream);
 int wctb_h8_to_nchw(const void* src_h8, float* dst_nchw, int C, int H, int W, void* stream);

@@ -47,6 +47,7 @@ def main():
             ref = wct.stylize(content.to(dev), style.to(dev)).cpu()          # the default single-GPU path (graph, fast stats, ...)
             oracle = O.stylize(O.load_weights_npz(wpath), "16x", content, style)
         grp = parallel.StripGroup(native_halo="--native-halo" in sys.argv)
+        grp.peer_halo = "--no-peer" not in sys.argv       # fused tail writes the neighbours' halos over NVLink (default) vs NCCL exchange
         wct.dist = grp
         own = grp.stylize(wct, "16x", grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev),
                           grp.own_slice(style, parallel.strip_cuts(Ws, world), rank).to(dev), content_width=Wc, style_width=Ws)
@@ -63,8 +64,10 @@ def main():
             e = got - oracle
             rms, mx = e.pow(2).mean().sqrt().item(), e.abs().max().item()
             tol_d, tol_rms = BOUNDS[precision]
-            line = ("multi_gpu_check[%s%s]: world=%d shape=%s max|sharded - single| = %.3g (tol %g)  overlapped vs per-stage executor %.3g  "
-                    "sharded vs oracle rms %.3g max %.3g (rms tol %g)" % (precision, " big" if big else "", world, tuple(got.shape), d, tol_d, d2, rms, mx, tol_rms))
+            dl = (full2.cpu() - ref).abs().max().item()
+            line = ("multi_gpu_check[%s%s%s]: world=%d shape=%s max|sharded - single| = %.3g (tol %g)  overlapped vs per-stage executor %.3g  "
+                    "(per-stage executor vs single %.3g)  sharded vs oracle rms %.3g max %.3g (rms tol %g)"
+                    % (precision, " big" if big else "", "" if grp.peer_halo else " no-peer", world, tuple(got.shape), d, tol_d, d2, dl, rms, mx, tol_rms))
             print(line, flush=True)
             report.append(line)
             ok = ok and d <= tol_d and rms <= tol_rms and d2 <= tol_d

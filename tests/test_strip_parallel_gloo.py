@@ -89,7 +89,7 @@ class CpuExecutor:
             se, sv = torch.linalg.eigh(sg / (ns - 1))
         return sm, se, sv
 
-    def content_part(self, stage, content, style_res, alpha, c_region, c_count, before_eig=None):
+    def content_part(self, stage, content, style_res, alpha, c_region, c_count, before_eig=None, tail_shard=None):
         with torch.no_grad():
             cF = O.encoder_forward(self.w["e%d" % stage], self.mode, stage, content).squeeze(0)
             nc, cm, cg = self._moments(cF, tuple(v >> (stage - 1) for v in c_region), c_count)
