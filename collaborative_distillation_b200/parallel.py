@@ -65,16 +65,18 @@ class PeerHalo:
         dist.all_gather_object(table, mine, group=group)
         self.peer = {}
         self._keep = []
+        me = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
         for r in (self.rank - 1, self.rank + 1):
             if 0 <= r < self.world:
+                if table[r][0][0] != me and not torch.cuda.can_device_access_peer(me, table[r][0][0]):
+                    raise RuntimeError("no peer access from cuda:%d to cuda:%d" % (me, table[r][0][0]))
                 bufs = []
                 for h in table[r]:
-                    with torch.cuda.device(h[0]):
-                        st = torch.UntypedStorage._new_shared_cuda(*h)
+                    # open the neighbour's allocation in THIS device's context (cudaIpcOpenMemHandle with
+                    # cudaIpcMemLazyEnablePeerAccess): the mapping is then addressable by kernels running on this GPU
+                    with torch.cuda.device(me):
+                        st = torch.UntypedStorage._new_shared_cuda(me, *h[1:])
                     t = torch.empty(0, dtype=torch.uint8, device=st.device).set_(st)
-                    # first touch from this device: makes torch enable peer access between the two devices
-                    self.local[0][:16].copy_(t[:16])
-                    self.local[0][:16].zero_()
                     bufs.append(t)
                     self._keep.append(st)
                 self.peer[r] = bufs
@@ -250,7 +252,16 @@ class StripGroup:
             H0 = content_own.shape[-2]
             need = 3 * H0 * (max(widths) + 2 * hmax) * 4
             if self._peer is None or self._peer.nbytes < need:
-                self._peer = PeerHalo(self.group, need, content_own.device)
+                try:
+                    self._peer = PeerHalo(self.group, need, content_own.device)
+                    ok = 1
+                except Exception as e:  # noqa: BLE001  (e.g. no NVLink / IPC not permitted): every rank falls back together
+                    print("wct-b200: peer-memory halo unavailable (%s); using the NCCL halo exchange" % (e,))
+                    self._peer, ok = None, 0
+                t = torch.tensor([ok], dtype=torch.int32, device=content_own.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+                if int(t.item()) == 0:
+                    self._peer, self.peer_halo, use_peer = None, False, False
 
         def content_chain(img, Wc_tot):
             nonlocal widths

@@ -11,17 +11,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "pending_hw: written without GPU access (round-1 GPU budget was spent); runs only with "
-                            "WCTB_PENDING_HW=1 until its first green run on a B200 is recorded in profiles/")
+    # round 1's `pending_hw` marker is retired: those 40 tests had their first green B200 run in round 2
+    # (profiles/r02_pytest_pending_hw.log) and are ordinary `gpu` tests now
 
 
 def pytest_collection_modifyitems(config, items):
     import torch
-    if os.environ.get("WCTB_PENDING_HW") != "1":
-        pend = pytest.mark.skip(reason="pending first hardware validation (set WCTB_PENDING_HW=1)")
-        for item in items:
-            if "pending_hw" in item.keywords:
-                item.add_marker(pend)
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

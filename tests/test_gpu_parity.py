@@ -123,7 +123,6 @@ def test_moments_match_fp64(C, H, W, region):
     assert (gf - gf.t()).abs().max().item() <= 1e-13 * ref.abs().max().item()
 
 
-@pytest.mark.pending_hw
 @pytest.mark.parametrize("variant", [3, 4])
 @pytest.mark.parametrize("C,H,W,region", [(24, 31, 47, None), (24, 300, 310, None), (32, 257, 300, None), (24, 40, 50, (3, 37, 8, 50)),
                                           (32, 33, 70, (0, 33, 5, 64)), (24, 3, 5, None), (32, 700, 900, (10, 690, 0, 900)),
@@ -416,7 +415,6 @@ def test_style_cache_equals_full_path(golden_dir):
 
 
 # ------------------------------------------------------------------ strip halos (multi-GPU data movement, single-GPU check)
-@pytest.mark.pending_hw
 @pytest.mark.parametrize("C,H,W,halo", [(3, 37, 200, 16), (3, 64, 160, 160), (3, 5, 33, 1), (24, 9, 70, 32)])
 def test_halo_pack_unpack_bit_exact(C, H, W, halo):
     """wctb_halo_pack / wctb_halo_unpack == torch slicing + cat (what StripGroup.exchange does by default)"""
@@ -438,7 +436,6 @@ def _pinv_sqrt(S, tau=1e-10):
     return (v[:, keep] * w[keep].pow(-0.5)) @ v[:, keep].t()
 
 
-@pytest.mark.pending_hw
 @pytest.mark.parametrize("kind", ["golden5", "golden4", "golden3", "syn128", "syn24", "syn32_illcond", "plus_identity", "zero"])
 def test_whiten_ns_vs_lapack(golden_dir, kind):
     """wctb_whiten_ns (pivoted Cholesky + Newton-Schulz, cooperative grid) == LAPACK pseudo-inverse square root.
@@ -473,7 +470,6 @@ def test_whiten_ns_vs_lapack(golden_dir, kind):
     assert (W - W.t()).abs().max().item() <= 1e-11 * ref.abs().max().item()
 
 
-@pytest.mark.pending_hw
 @pytest.mark.parametrize("case", ["full_rank", "wide", "dead_channels", "hw_lt_c"])
 def test_whiten_and_color_ns_solver_vs_reference_golden(golden_dir, case):
     g = np.load(os.path.join(golden_dir, "golden_wct.npz"))
@@ -489,7 +485,6 @@ def test_whiten_and_color_ns_solver_vs_reference_golden(golden_dir, case):
         assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
 
 
-@pytest.mark.pending_hw
 def test_five_stage_ns_solver_equals_jacobi_solver(golden_dir):
     g = np.load(os.path.join(golden_dir, "golden_16x.npz"))
     content, style = torch.from_numpy(g["content"]).to(DEV), torch.from_numpy(g["style"]).to(DEV)

@@ -141,7 +141,6 @@ def test_load_and_save_image_mirror_the_reference_loader(tmp_path):
     assert back.shape == (300, 420, 3) and np.abs(back - img).mean() <= 4.0
 
 
-@pytest.mark.pending_hw
 @pytest.mark.parametrize("backend,interp", [("gpu_hybrid", False), ("hybrid", False), ("default", True)])
 def test_jpeg_decode_other_backends(backend, interp):
     """wctb_io_create_ex: GPU-assisted Huffman backend / interpolated chroma upsampling decode the same picture"""

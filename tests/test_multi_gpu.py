@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("extra", [[], ["--no-peer"], ["--big"]])
+@pytest.mark.parametrize("extra", [["--no-peer"], [], ["--big"]])
 def test_sharded_equals_single_gpu_two_ranks(tmp_path, extra):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
