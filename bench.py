@@ -595,11 +595,11 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
         return timed_call(("conv_head_h2", "3->16->16 pool"), originals["conv_head_h2"], (x, w11p, is11, b11, w12p, is12, b12), {},
                           lambda y: (2.0 * H * W * (9 + 9 * 3 * 16 + 9 * 16 * 16), 4.0 * (3 * H * W + 16 * (H // 2) * (W // 2)), mma_cyc))
 
-    def wrap_tail_h2(x, w12p, is12, b12, w11p, is11, b11, upsample_input):
+    def wrap_tail_h2(x, w12p, is12, b12, w11p, is11, b11, upsample_input, shard=None):
         H, W = (2 * x.shape[2], 2 * x.shape[3]) if upsample_input else (x.shape[2], x.shape[3])
         mma_cyc = tiles(H, W, 32, 28) * (9 * 3 * (CYC16[96] + CYC16[48]) + 8 * 3 * (CYC16[96] + CYC16[48]))
         return timed_call(("conv_tail_h2", "16->16->3 up%d" % int(upsample_input)), originals["conv_tail_h2"],
-                          (x, w12p, is12, b12, w11p, is11, b11, upsample_input), {},
+                          (x, w12p, is12, b12, w11p, is11, b11, upsample_input), {"shard": shard},
                           lambda y: (2.0 * H * W * 9 * (16 * 16 + 16 * 3), 4.0 * (x.numel() / 2 + 3 * H * W), mma_cyc))
 
     wrappers = {"conv3x3_p4": wrap_p4, "conv_head_tc": wrap_head_tc, "conv_head": wrap_head, "conv_tail": wrap_tail,
