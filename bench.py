@@ -375,17 +375,19 @@ def main():
         for _ in range(warmup):
             step(content_d, style_d)
         l0 = ops.launches()
+        h0 = dict(grp.counters) if grp is not None else None
         if clocks:
             with ClockSampler(local) as cs:
                 total_ms = timed(lambda: step(content_d, style_d), steps)
         else:
             cs, total_ms = None, timed(lambda: step(content_d, style_d), steps)
         launches = ops.launches() - l0
+        halo = None if grp is None else {k: (grp.counters[k] - h0[k]) / float(steps) for k in h0}
         ms_per_step = total_ms / steps
         mp = Hc * Wc / 1e6
         res = {"cfg": cfg, "mode": mode, "workload": wl, "ms_per_step": ms_per_step, "value": mp / (ms_per_step / 1e3), "launches": launches,
                "shape": (Hc, Wc, Hs, Ws), "clocks": cs.summary() if cs else None, "flops": algorithmic_conv_flops(mode, Hc, Wc, Hs, Ws),
-               "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+               "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "halo_exchanges_per_step": halo}
         if want_e2e:
             # e2e: pinned host -> device -> stylize -> host, every step.  Sharded: the uploads go on a copy stream so the style
             # strip's H2D overlaps the first content kernels, and the download of step i overlaps nothing (it is the result)
@@ -498,6 +500,10 @@ def main():
             "conv_tflops_whole_step": round(flops / (ms_per_step / 1e3) / 1e12, 2),
             "peak_mem_gb": round(main_res["peak_mem_gb"], 2),
         }
+        if main_res.get("halo_exchanges_per_step"):
+            # peer_halo: stage transitions whose halo was stored into the neighbours' buffers by the fused tail kernel (NVLink peer
+            # memory); nccl_halo: batch_isend_irecv exchanges (first content halo, style strips, stages without a fused tail)
+            line["config"]["halo_exchanges_per_step"] = main_res["halo_exchanges_per_step"]
         if main_res.get("roofline"):
             line["roofline"] = main_res["roofline"]
         if cpu_base:

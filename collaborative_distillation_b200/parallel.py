@@ -112,6 +112,7 @@ class StripGroup:
         import os
         self.peer_halo = os.environ.get("WCTB_PEER_HALO", "1") == "1"
         self._peer = None
+        self.counters = {"peer_halo": 0, "nccl_halo": 0}     # halo exchanges by mechanism (bench.py reports them)
 
     # ---- collectives used by WCT._moments
     def allreduce_(self, t: torch.Tensor):
@@ -151,6 +152,7 @@ class StripGroup:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         lh, rh = (halo if left is not None else 0), (halo if right is not None else 0)
+        self.counters["nccl_halo"] += 1
         if native:
             ext = torch.empty(own.shape[:-1] + (lh + w + rh,), dtype=own.dtype, device=own.device)
             if left is not None:
@@ -320,6 +322,7 @@ class StripGroup:
                     if shard is not None and out is shard["out"]:
                         # the fused tail wrote our strip and both neighbours' halos: one stream-ordered barrier, no exchange
                         self._peer.barrier()
+                        self.counters["peer_halo"] += 1
                         widths = wn
                         Wc_tot = (Wc_tot >> sh) << sh
                         pending_ext = (out, lhn, rhn)
