@@ -121,6 +121,7 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         rank = dist.get_rank()
         grp = parallel.StripGroup()
+        grp.use_graph = False      # every pair is seen once: a graph per pair would run the path twice
 
     os.makedirs(args.outf, exist_ok=True)
     log = LogPrinter(args.debug, os.path.join(args.outf, "log_%s_%s.txt" % (args.log_mark, args.mode))) if rank == 0 else (lambda sth: None)

@@ -78,7 +78,9 @@ SIGNATURES = {
     "wctb_debug_set_trace": [_p],
     "wctb_debug_mma_rate": [_p, _i, _i, _i, _i, _i, _p],
     "wctb_selftest_umma": [_p, _p, _p, _i, _i, _p],
+    "wctb_debug_set_h2_resident": [_i],
     "wctb_debug_mma_rate_f16": [_p, _i, _i, _i, _i, _p],
+    "wctb_debug_mma_rate_f16_off": [_p, _i, _i, _i, _i, _i, _p],
     "wctb_debug_ldtm_rate": [_p, _i, _i, _i, _i, _p],
 }
 
@@ -119,6 +121,8 @@ def load():
     lib.wctb_h2_packed_halves.restype = _ll
     if lib.wctb_abi_version() != 1:
         raise WctbError("libwctb ABI version mismatch")
+    if os.environ.get("WCTB_H2_RESIDENT"):           # A/B: 0 = stream the weights with every pipeline stage (round-2a kernels)
+        lib.wctb_debug_set_h2_resident(int(os.environ["WCTB_H2_RESIDENT"]))
     if os.environ.get("WCTB_GRAM_VARIANT"):          # A/B switch for tools / bench runs (see wctb.h, debug section)
         lib.wctb_debug_set_gram_variant(int(os.environ["WCTB_GRAM_VARIANT"]))
     if os.environ.get("WCTB_FIRST_VARIANT"):

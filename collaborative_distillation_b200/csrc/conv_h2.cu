@@ -19,14 +19,15 @@
 // memory IS the A operand and the nine filter taps are nine descriptor start addresses (linear-pitch trick, row pitch
 // 64 pixels, the two rightmost positions of a row are masked garbage).
 //
-// Kernel structure (persistent, one CTA per SM, 192 threads):
+// Kernel structure (persistent, one CTA per SM, 320 threads):
 //   warp 0   producer: per 16-channel K group ONE tensor-map TMA box (cp.async.bulk.tensor.4d, 4 planes x (TH+2) rows x
 //            64 px) + one bulk copy of the weight slab; tiles touching a true image border use per-row bulk copies with
 //            the reflection resolved in the source address instead (5 % of the tiles at UHD).
 //   warp 1   single-thread tcgen05.mma issuer; accumulators double-buffered in TMEM (2 x NB blocks of 128 px), so the
 //            MMAs of tile t+1 overlap the epilogue of tile t inside the CTA.
-//   warps 2-5 epilogue: tcgen05.ld -> (main + minor) * 1/s + bias -> ReLU -> [pool | up2] -> hi/lo split -> 16-byte
-//            stores (H8 for the next conv and/or fp32 P4 for the statistics kernels / public API).
+//   warps 2-9 epilogue (two groups of four, alternating accumulator blocks): tcgen05.ld -> (main + minor) * 1/s + bias -> ReLU
+//            -> [pool | up2] -> hi/lo split -> 16-byte stores (H8 for the next conv and/or fp32 P4 for the statistics kernels /
+//            public API).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -36,28 +37,47 @@ namespace {
 using namespace wctb_umma;
 
 // ---------------------------------------------------------------------------------- geometry
-template <int N_, int NB_, int STACK_>
+template <int N_, int NB_, int STACK_, int RESW_ = 0>
 struct H2Cfg {
   static constexpr int N = N_, NB = NB_, STACK = STACK_;
+  // RESW: the packed weights of the whole layer (<= MAXKG 16-channel K groups, Cout == N) stay RESIDENT in shared memory for the
+  // life of the persistent CTA instead of being re-fetched with every pipeline stage.  Why: for N <= 64 the tcgen05.mma rate is
+  // bound by the 128 B/clk shared-memory read port (cycles per MMA = (4 KB A slab + 32 N bytes of B) / 128: 40 / 48 / 64 for
+  // N = 32 / 64 / 128, tools/h2_rates.py), the TMA writes of a stage share that port with the operand reads, and the weight slab
+  // was 30-47 % of every stage (ncu: L2 -> SM reads 3.4-3.8x the input tensor).
+  static constexpr int RESW = RESW_;
+  static constexpr int MAXKG = 4;
   static constexpr int NACC = 2;                                 // accumulator sets (double buffer)
   static constexpr int TH = 2 * NB;                              // output rows per tile
   static constexpr int ROWS = TH + 2;
   static constexpr int PLANE_BYTES = ROWS * PW * 16;             // one 8-channel half-plane of the halo tile
   static constexpr int IN_BYTES = 4 * PLANE_BYTES;               // hi0, lo0, hi1, lo1
   static constexpr int W_BYTES = 9 * 2 * (2 * N) * 16;           // [tap][kchunk][hi N rows | lo N rows][8 halves]
-  static constexpr int STAGE_BYTES = IN_BYTES + W_BYTES;
+  static constexpr int STAGE_BYTES = IN_BYTES + (RESW ? 0 : W_BYTES);
+  static constexpr int RES_BYTES = RESW ? MAXKG * W_BYTES : 0;
   static constexpr int COLS = STACK ? 2 * N : N;                 // TMEM columns per accumulator block
   static constexpr int ACC_COLS = NB * COLS;
-  static constexpr int POOL_BYTES = 2 * 64 * 20 * 4;
-  static constexpr int AUX_BYTES = 1024;
-  static constexpr int NSTAGE_MAX = (227 * 1024 - POOL_BYTES - AUX_BYTES - 128) / STAGE_BYTES;
-  static constexpr int NSTAGE = NSTAGE_MAX > 4 ? 4 : NSTAGE_MAX;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + POOL_BYTES + AUX_BYTES + 128;
-  static_assert(NSTAGE >= 2, "pipeline needs two stages");
+  static constexpr int AUX_BYTES = 512;
   static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
-  static_assert(STAGE_BYTES % 128 == 0, "TMA destination alignment");
+  static_assert(STAGE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "TMA destination alignment");
   static_assert(COLS <= 256, "tcgen05.mma N <= 256");
 };
+// shared-memory plan of one (config, epilogue) instantiation: [resident weights][stages][pool exchange][barriers]
+template <class C, int EPI>
+struct H2Lay {
+  static constexpr int POOL_BYTES = (EPI == WCTB_EPI_POOL2) ? 2 * 2 * 64 * 20 * 4 : 0;   // [warp group][parity][64 px][16 + 4 pad]
+  static constexpr int NSTAGE_MAX = (227 * 1024 - C::RES_BYTES - POOL_BYTES - C::AUX_BYTES - 128) / C::STAGE_BYTES;
+  static constexpr int NSTAGE = NSTAGE_MAX > 4 ? 4 : NSTAGE_MAX;
+  static constexpr int STAGES_OFF = C::RES_BYTES;
+  static constexpr int POOL_OFF = STAGES_OFF + NSTAGE * C::STAGE_BYTES;
+  static constexpr int AUX_OFF = POOL_OFF + POOL_BYTES;
+  static constexpr int SMEM_BYTES = AUX_OFF + C::AUX_BYTES + 128;
+  static_assert(NSTAGE >= 2, "pipeline needs two stages");
+  static_assert((2 * NSTAGE + 2 * C::NACC + C::MAXKG) * 8 + 8 <= C::AUX_BYTES, "barrier area");
+};
+
+constexpr int H2_EPI_WARPS = 8;                     // two warp groups of four (one warp per TMEM lane quarter each)
+constexpr int H2_THREADS = 64 + 32 * H2_EPI_WARPS;   // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
 
 struct H2Args {
   const __half* x;        // H8 [C8in][2][H][W][8]
@@ -131,103 +151,126 @@ __device__ __forceinline__ void h2_store16(const H2Args& a, int gg, long long HW
   }
 }
 
+// One accumulator item = 16 output channels (group g) of one 128-pixel block b: bias, ReLU, [pool | up2], hi/lo split, stores.
 template <class C, int EPI>
-__device__ __forceinline__ void h2_epilogue_tile(const H2Args& a, uint32_t tmem_acc, float* poolbuf, int q, int lane,
-                                                 int x0, int y0, int nblk, float inv_s, int& it) {
+__device__ __forceinline__ void h2_epilogue_item(const H2Args& a, const uint32_t (&m0)[16], const uint32_t (&m1)[16], const float (&bv)[16],
+                                                 float* poolbuf, int half, int q, int lane, int x0, int y0, int nblk, int g, int b,
+                                                 float inv_s, int& it) {
   constexpr int N = C::N;
   const int H = a.H, W = a.W;
   const long long HW = (long long)H * W;
-  const uint32_t tq = tmem_acc + ((uint32_t)(32 * q) << 16);
-#pragma unroll 1
-  for (int g = 0; g < N / 16; ++g) {
-    float bv[16];
+  const int gg = nblk * (N / 16) + g;
+  float v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) bv[i] = __ldg(a.bias + nblk * N + 16 * g + i);
-    const int gg = nblk * (N / 16) + g;
-    // the TMEM loads of block b+1 fly while block b is processed
-    uint32_t mb0[2][16], mb1[2][16];
-    tmem_ld16_issue(tq + (uint32_t)(16 * g), mb0[0]);
-    if (C::STACK) tmem_ld16_issue(tq + (uint32_t)(N + 16 * g), mb1[0]);
-#pragma unroll
-    for (int b = 0; b < C::NB; ++b, ++it) {
-      uint32_t(&m0)[16] = mb0[b & 1];
-      uint32_t(&m1)[16] = mb1[b & 1];
-      tmem_ld16_wait(m0);
-      if (C::STACK) tmem_ld16_wait(m1);
-      if (b + 1 < C::NB) {
-        tmem_ld16_issue(tq + (uint32_t)((b + 1) * C::COLS + 16 * g), mb0[(b + 1) & 1]);
-        if (C::STACK) tmem_ld16_issue(tq + (uint32_t)((b + 1) * C::COLS + N + 16 * g), mb1[(b + 1) & 1]);
-      }
-      float v[16];
+  for (int i = 0; i < 16; ++i) {
+    const float s = C::STACK ? (__uint_as_float(m0[i]) + __uint_as_float(m1[i])) : __uint_as_float(m0[i]);
+    v[i] = wctb_relu(fmaf(s, inv_s, bv[i]));
+  }
+  if (EPI == WCTB_EPI_POOL2) {
+    // block b = tile rows 2b (lanes 0..63) and 2b+1 (lanes 64..127): row exchange through shared memory (per warp group)
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int cpos = (q & 1) * 32 + lane;
+    const int oy = (y0 >> 1) + b, ox = (x0 + cpos) >> 1;
+    const bool ok = (cpos < TW) && oy < Ho && ox < Wo && ((lane & 1) == 0);
+    float* pb = poolbuf + (half * 2 + (it & 1)) * (64 * 20);
+    if (q >= 2) {
+      float4* d = reinterpret_cast<float4*>(pb + cpos * 20);
+      d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+      d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+    if (q < 2) {
+      const float4* s = reinterpret_cast<const float4*>(pb + cpos * 20);
+      const float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+      const float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float s = C::STACK ? (__uint_as_float(m0[i]) + __uint_as_float(m1[i])) : __uint_as_float(m0[i]);
-        v[i] = wctb_relu(fmaf(s, inv_s, bv[i]));
+        const float m = fmaxf(v[i], o[i]);
+        v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
       }
-      if (EPI == WCTB_EPI_POOL2) {
-        // block b = tile rows 2b (lanes 0..63) and 2b+1 (lanes 64..127): row exchange through shared memory
-        const int Ho = H >> 1, Wo = W >> 1;
-        const int cpos = (q & 1) * 32 + lane;
-        const int oy = (y0 >> 1) + b, ox = (x0 + cpos) >> 1;
-        const bool ok = (cpos < TW) && oy < Ho && ox < Wo && ((lane & 1) == 0);
-        float* pb = poolbuf + (it & 1) * (64 * 20);
-        if (q >= 2) {
-          float4* d = reinterpret_cast<float4*>(pb + cpos * 20);
-          d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
-          d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
+      if (ok) h2_store16(a, gg, (long long)Ho * Wo, (long long)oy * Wo + ox, v);
+    }
+  } else {
+    const int p = 128 * b + 32 * q + lane;
+    const int r = p >> 6, c = p & 63;
+    const int gy = y0 + r, gx = x0 + c;
+    if ((c < TW) && gy < H && gx < W) {
+      if (EPI == WCTB_EPI_NONE) {
+        h2_store16(a, gg, HW, (long long)gy * W + gx, v);
+      } else if (EPI == WCTB_EPI_NCHW3) {
+        if (g == 0 && nblk == 0) {
+          float* img = reinterpret_cast<float*>(a.y_p4);
+          const long long off = (long long)gy * W + gx;
+          img[off] = v[0]; img[HW + off] = v[1]; img[2 * HW + off] = v[2];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q < 2) {
-          const float4* s = reinterpret_cast<const float4*>(pb + cpos * 20);
-          const float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
-          const float o[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+      } else {   // nearest x2
+        const int Wo = 2 * W;
+        const long long off = (long long)(2 * gy) * Wo + 2 * gx;
+        if (a.y_h8) {
+          uint4* base = reinterpret_cast<uint4*>(a.y_h8);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float m = fmaxf(v[i], o[i]);
-            v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          for (int j = 0; j < 2; ++j) {
+            uint4 hi, lo;
+            split8(v + 8 * j, hi, lo);
+            uint4* ph = base + (long long)(2 * gg + j) * 2 * (4 * HW);
+            uint4* pl = ph + 4 * HW;
+            ph[off] = hi; ph[off + 1] = hi; ph[off + Wo] = hi; ph[off + Wo + 1] = hi;
+            pl[off] = lo; pl[off + 1] = lo; pl[off + Wo] = lo; pl[off + Wo + 1] = lo;
           }
-          if (ok) h2_store16(a, gg, (long long)Ho * Wo, (long long)oy * Wo + ox, v);
         }
-      } else {
-        const int p = 128 * b + 32 * q + lane;
-        const int r = p >> 6, c = p & 63;
-        const int gy = y0 + r, gx = x0 + c;
-        if ((c < TW) && gy < H && gx < W) {
-          if (EPI == WCTB_EPI_NONE) {
-            h2_store16(a, gg, HW, (long long)gy * W + gx, v);
-          } else if (EPI == WCTB_EPI_NCHW3) {
-            if (g == 0 && nblk == 0) {
-              float* img = reinterpret_cast<float*>(a.y_p4);
-              const long long off = (long long)gy * W + gx;
-              img[off] = v[0]; img[HW + off] = v[1]; img[2 * HW + off] = v[2];
-            }
-          } else {   // nearest x2
-            const int Wo = 2 * W;
-            const long long off = (long long)(2 * gy) * Wo + 2 * gx;
-            if (a.y_h8) {
-              uint4* base = reinterpret_cast<uint4*>(a.y_h8);
+        if (a.y_p4) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 hi, lo;
-                split8(v + 8 * j, hi, lo);
-                uint4* ph = base + (long long)(2 * gg + j) * 2 * (4 * HW);
-                uint4* pl = ph + 4 * HW;
-                ph[off] = hi; ph[off + 1] = hi; ph[off + Wo] = hi; ph[off + Wo + 1] = hi;
-                pl[off] = lo; pl[off + 1] = lo; pl[off + Wo] = lo; pl[off + Wo + 1] = lo;
-              }
-            }
-            if (a.y_p4) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                float4* pl = a.y_p4 + (long long)(4 * gg + j) * (4 * HW);
-                pl[off] = o; pl[off + 1] = o; pl[off + Wo] = o; pl[off + Wo + 1] = o;
-              }
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            float4* pl = a.y_p4 + (long long)(4 * gg + j) * (4 * HW);
+            pl[off] = o; pl[off + 1] = o; pl[off + Wo] = o; pl[off + Wo + 1] = o;
           }
         }
       }
     }
+  }
+  ++it;
+}
+
+// The epilogue of one tile, as seen by ONE of the two warp groups (half = 0 / 1: four warps each, one per TMEM lane quarter).
+// A group takes the blocks b = half (mod 2) of every 16-channel group: with a single warp per SM sub-partition the epilogue
+// was bound by its own dependent-instruction latency (tcgen05.ld -> math -> stores, ~500 cycles per item at 13 % issue
+// utilisation) and, not the MMAs, set the tile time of every layer up to 64 channels; two warps per sub-partition halve it.
+// Items are walked g-major with the TMEM load of item i+1 in flight while item i is processed.
+template <class C, int EPI>
+__device__ __forceinline__ void h2_epilogue_tile(const H2Args& a, uint32_t tmem_acc, float* poolbuf, int half, int q, int lane,
+                                                 int x0, int y0, int nblk, float inv_s, int& it) {
+  constexpr int N = C::N, BH = C::NB / 2, ITEMS = (N / 16) * BH;
+  static_assert(C::NB % 2 == 0 && ITEMS % 2 == 0, "two warp groups, items processed in pairs");
+  const uint32_t tq = tmem_acc + ((uint32_t)(32 * q) << 16);
+  auto issue = [&](int i, uint32_t (&r0)[16], uint32_t (&r1)[16]) {
+    const int g = i / BH, b = 2 * (i - g * BH) + half;
+    tmem_ld16_issue(tq + (uint32_t)(b * C::COLS + 16 * g), r0);
+    if (C::STACK) tmem_ld16_issue(tq + (uint32_t)(b * C::COLS + N + 16 * g), r1);
+  };
+  float bv[16];
+  int g_loaded = -1;
+  auto run = [&](int i, uint32_t (&r0)[16], uint32_t (&r1)[16]) {
+    const int g = i / BH, b = 2 * (i - g * BH) + half;
+    if (g != g_loaded) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bv[k] = __ldg(a.bias + nblk * N + 16 * g + k);
+      g_loaded = g;
+    }
+    h2_epilogue_item<C, EPI>(a, r0, r1, bv, poolbuf, half, q, lane, x0, y0, nblk, g, b, inv_s, it);
+  };
+  uint32_t ma0[16], ma1[16], mb0[16], mb1[16];
+  issue(0, ma0, ma1);
+#pragma unroll 1
+  for (int i = 0; i < ITEMS; i += 2) {
+    tmem_ld16_wait(ma0);
+    if (C::STACK) tmem_ld16_wait(ma1);
+    issue(i + 1, mb0, mb1);
+    run(i, ma0, ma1);
+    tmem_ld16_wait(mb0);
+    if (C::STACK) tmem_ld16_wait(mb1);
+    if (i + 2 < ITEMS) issue(i + 2, ma0, ma1);
+    run(i + 1, mb0, mb1);
   }
 }
 
@@ -245,8 +288,8 @@ __device__ __forceinline__ void h2_load_border(const H2Args& a, uint8_t* st, uin
   const int jr = W - x0 + 1;                         // tile col of gx == W
   const bool right = jr < PW;
   const uint32_t row_bytes = (uint32_t)(ncols + (left ? 1 : 0) + (right ? 1 : 0)) * 16u;
-  mbar_expect_tx(bar, (uint32_t)C::W_BYTES + 4u * C::ROWS * row_bytes);
-  bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, bar);
+  mbar_expect_tx(bar, (C::RESW ? 0u : (uint32_t)C::W_BYTES) + 4u * C::ROWS * row_bytes);
+  if (!C::RESW) bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, bar);
   const uint4* xb = reinterpret_cast<const uint4*>(a.x);
 #pragma unroll 1
   for (int pl = 0; pl < 4; ++pl) {
@@ -266,24 +309,28 @@ __device__ __forceinline__ void h2_load_border(const H2Args& a, uint8_t* st, uin
 }
 
 template <class C, int EPI>
-__global__ void __launch_bounds__(192, 1) conv_h2_kernel(const __grid_constant__ CUtensorMap tmap, const H2Args a) {
+__global__ void __launch_bounds__(H2_THREADS, 1) conv_h2_kernel(const __grid_constant__ CUtensorMap tmap, const H2Args a) {
+  using L = H2Lay<C, EPI>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* stages = smem;
-  float* poolbuf = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES + C::POOL_BYTES);
-  uint64_t* empty = full + C::NSTAGE;
-  uint64_t* acc_full = empty + C::NSTAGE;
+  uint8_t* resw = smem;                                         // RESW: [nkg][W_BYTES]
+  uint8_t* stages = smem + L::STAGES_OFF;
+  float* poolbuf = reinterpret_cast<float*>(smem + L::POOL_OFF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::AUX_OFF);
+  uint64_t* empty = full + L::NSTAGE;
+  uint64_t* acc_full = empty + L::NSTAGE;
   uint64_t* acc_empty = acc_full + C::NACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + C::NACC);
+  uint64_t* wfull = acc_empty + C::NACC;                        // RESW: one per K group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + C::MAXKG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkg = (a.Cin + 15) / 16;
   const int tiles_xy = a.tiles_x * a.tiles_y;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+    for (int s = 0; s < L::NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, H2_EPI_WARPS); }
+    for (int s = 0; s < C::MAXKG; ++s) mbar_init(wfull + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmap);
   }
@@ -296,6 +343,12 @@ __global__ void __launch_bounds__(192, 1) conv_h2_kernel(const __grid_constant__
   if (warp == 0) {
     // =========================== producer ===========================
     if (elect_one()) {
+      if (C::RESW) {                       // the layer's weights, once per CTA (K group by K group: the first MMAs need only slab 0)
+        for (int kg = 0; kg < nkg; ++kg) {
+          mbar_expect_tx(wfull + kg, (uint32_t)C::W_BYTES);
+          bulk_g2s(smem_u32(resw + (size_t)kg * C::W_BYTES), a.w + (size_t)kg * (C::W_BYTES / 2), C::W_BYTES, wfull + kg);
+        }
+      }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int nblk = tile / tiles_xy, rem = tile - nblk * tiles_xy;
@@ -304,14 +357,14 @@ __global__ void __launch_bounds__(192, 1) conv_h2_kernel(const __grid_constant__
         const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= a.W) || (y0 + C::TH >= a.H);
         const __half* wblk = a.w + (size_t)nblk * nkg * (C::W_BYTES / 2);
         for (int kg = 0; kg < nkg; ++kg, ++it) {
-          const int slot = it % C::NSTAGE;
-          mbar_wait(empty + slot, ((it / C::NSTAGE) & 1) ^ 1);
+          const int slot = it % L::NSTAGE;
+          mbar_wait(empty + slot, ((it / L::NSTAGE) & 1) ^ 1);
           uint8_t* st = stages + slot * C::STAGE_BYTES;
           const __half* wsrc = wblk + (size_t)kg * (C::W_BYTES / 2);
           if (!border) {
             mbar_expect_tx(full + slot, (uint32_t)C::STAGE_BYTES);
             tma_load_4d(smem_u32(st), &tmap, 0, x0 - 1, y0 - 1, 4 * kg, full + slot);   // planes beyond the tensor: zero fill
-            bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, full + slot);
+            if (!C::RESW) bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, full + slot);
           } else {
             h2_load_border<C>(a, st, full + slot, kg, x0, y0, wsrc);
           }
@@ -329,11 +382,13 @@ __global__ void __launch_bounds__(192, 1) conv_h2_kernel(const __grid_constant__
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc * C::ACC_COLS;
         for (int kg = 0; kg < nkg; ++kg, ++it) {
-          const int slot = it % C::NSTAGE;
-          mbar_wait(full + slot, (it / C::NSTAGE) & 1);
+          const int slot = it % L::NSTAGE;
+          if (C::RESW && t == 0) mbar_wait(wfull + kg, 0);
+          mbar_wait(full + slot, (it / L::NSTAGE) & 1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(stages + slot * C::STAGE_BYTES);
-          h2_issue_stage<C>(a_base, a_base + C::IN_BYTES, tmem_acc, kg == 0);
+          const uint32_t w_base = C::RESW ? smem_u32(resw + (size_t)kg * C::W_BYTES) : a_base + C::IN_BYTES;
+          h2_issue_stage<C>(a_base, w_base, tmem_acc, kg == 0);
           tc_commit(empty + slot);
         }
         tc_commit(acc_full + acc);
@@ -342,7 +397,7 @@ __global__ void __launch_bounds__(192, 1) conv_h2_kernel(const __grid_constant__
     __syncwarp();
   } else {
     // =========================== epilogue ===========================
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const float inv_s = __ldg(a.wscale + 1);
     uint32_t t = 0;
     int it = 0;
@@ -352,7 +407,7 @@ __global__ void __launch_bounds__(192, 1) conv_h2_kernel(const __grid_constant__
       const uint32_t acc = t % C::NACC;
       mbar_wait(acc_full + acc, (t / C::NACC) & 1);
       tc_fence_after();
-      h2_epilogue_tile<C, EPI>(a, tmem_base + acc * C::ACC_COLS, poolbuf, q, lane, tx * TW, ty * C::TH, nblk, inv_s, it);
+      h2_epilogue_tile<C, EPI>(a, tmem_base + acc * C::ACC_COLS, poolbuf, half, q, lane, tx * TW, ty * C::TH, nblk, inv_s, it);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + acc);
@@ -396,7 +451,9 @@ int make_h8_tmap(CUtensorMap* m, const void* base, int planes, int H, int W, int
 template <class C, int EPI>
 int launch_h2(H2Args a, cudaStream_t st) {
   static bool done[64] = {};
-  int rc = ensure_smem_attr(conv_h2_kernel<C, EPI>, C::SMEM_BYTES, done);
+  using L = H2Lay<C, EPI>;
+  if (C::RESW && (a.Cout != C::N || (a.Cin + 15) / 16 > C::MAXKG)) return WCTB_E_UNSUPPORTED;
+  int rc = ensure_smem_attr(conv_h2_kernel<C, EPI>, L::SMEM_BYTES, done);
   if (rc != WCTB_OK) return rc;
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + C::TH - 1) / C::TH;
@@ -405,7 +462,7 @@ int launch_h2(H2Args a, cudaStream_t st) {
   rc = make_h8_tmap(&tmap, a.x, a.planes_in, a.H, a.W, C::ROWS);
   if (rc != WCTB_OK) return rc;
   const int grid = a.ntiles < wctb_num_sms() ? a.ntiles : wctb_num_sms();
-  conv_h2_kernel<C, EPI><<<grid, 192, C::SMEM_BYTES, st>>>(tmap, a);
+  conv_h2_kernel<C, EPI><<<grid, H2_THREADS, L::SMEM_BYTES, st>>>(tmap, a);
   WCTB_RETURN_LAUNCH();
 }
 template <class C>
@@ -417,6 +474,7 @@ int launch_h2_epi(const H2Args& a, int epi, cudaStream_t st) {
     default: return WCTB_E_BADARG;
   }
 }
+int g_h2_resident = 1;   // debug A/B switch (wctb_debug_set_h2_resident): 0 = round-2a kernels (weights streamed with every stage)
 inline int h2_pick_n(int Cout) {
   if (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128) return Cout;
   if (Cout > 128 && Cout % 128 == 0) return 128;
@@ -575,7 +633,7 @@ __global__ void __launch_bounds__(256) conv_first_h2_kernel(const float* __restr
 // cycles per tcgen05.mma.kind::f16 (M = 128, K = 16) for a given N with `nacc` independent accumulators, operands in the
 // no-swizzle plane layout the conv kernels use (contents irrelevant).
 template <int N>
-__global__ void __launch_bounds__(128, 1) h2_mma_rate_kernel(long long* out, int nacc, int iters) {
+__global__ void __launch_bounds__(128, 1) h2_mma_rate_kernel(long long* out, int nacc, int iters, int a_off16) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -593,7 +651,7 @@ __global__ void __launch_bounds__(128, 1) h2_mma_rate_kernel(long long* out, int
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       for (int k = 0; k < 4; ++k) {
-        const uint64_t ad = umma_desc(a0 + k * 64 * 16, 18432u * 2u, 128u);
+        const uint64_t ad = umma_desc(a0 + k * 64 * 16 + (uint32_t)((k % 3) * a_off16) * 16u, 18432u * 2u, 128u);   // taps dx = 0, 1, 2
         const uint64_t bd = umma_desc(b0 + k * 2 * N * 16, N * 16u, 128u);
 #pragma unroll 1
         for (int b = 0; b < nacc; ++b) umma_f16(tmem + (uint32_t)(b * N), ad, bd, idesc, 1u);
@@ -673,12 +731,15 @@ extern "C" int wctb_conv3x3_h2(const void* x_h8, const void* w_packed, const flo
   if (epilogue == WCTB_EPI_NCHW3) {
     if (Cout != 16 || !y_p4) return WCTB_E_BADARG;
     a.y_h8 = nullptr;
+    if (g_h2_resident && (Cin + 15) / 16 <= 4) return launch_h2<H2Cfg<16, 8, 1, 1>, WCTB_EPI_NCHW3>(a, st);
     return launch_h2<H2Cfg<16, 8, 1>, WCTB_EPI_NCHW3>(a, st);
   }
+  // layers whose packed weights fit next to the input stages (Cout = N <= 64, Cin <= 64) keep them resident in shared memory
+  const bool resw = g_h2_resident && Cout <= 64 && (Cin + 15) / 16 <= 4;
   switch (h2_pick_n(Cout)) {
-    case 16: return launch_h2_epi<H2Cfg<16, 8, 1>>(a, epilogue, st);
-    case 32: return launch_h2_epi<H2Cfg<32, 4, 1>>(a, epilogue, st);
-    case 64: return launch_h2_epi<H2Cfg<64, 4, 0>>(a, epilogue, st);
+    case 16: return resw ? launch_h2_epi<H2Cfg<16, 8, 1, 1>>(a, epilogue, st) : launch_h2_epi<H2Cfg<16, 8, 1>>(a, epilogue, st);
+    case 32: return resw ? launch_h2_epi<H2Cfg<32, 4, 1, 1>>(a, epilogue, st) : launch_h2_epi<H2Cfg<32, 4, 1>>(a, epilogue, st);
+    case 64: return resw ? launch_h2_epi<H2Cfg<64, 2, 1, 1>>(a, epilogue, st) : launch_h2_epi<H2Cfg<64, 4, 0>>(a, epilogue, st);
     default: return launch_h2_epi<H2Cfg<128, 2, 0>>(a, epilogue, st);
   }
 }
@@ -719,15 +780,20 @@ extern "C" int wctb_conv3x3_first_h2(const float* x, const float* w, const float
   WCTB_RETURN_LAUNCH();
 }
 
-extern "C" int wctb_debug_mma_rate_f16(long long* out_cycles, int N, int nacc, int iters, int ctas, void* stream) {
+extern "C" int wctb_debug_set_h2_resident(int on) { g_h2_resident = on ? 1 : 0; return WCTB_OK; }
+
+extern "C" int wctb_debug_mma_rate_f16_off(long long* out_cycles, int N, int nacc, int iters, int ctas, int a_off16, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int smem = 200 * 1024;
   if (!out_cycles || nacc < 1 || nacc * N > 512 || iters < 1 || ctas < 1) return WCTB_E_BADARG;
 #define WCTB_MR(NN) case NN: WCTB_CUDA_TRY(cudaFuncSetAttribute(h2_mma_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    h2_mma_rate_kernel<NN><<<ctas, 128, smem, st>>>(out_cycles, nacc, iters); break;
+    h2_mma_rate_kernel<NN><<<ctas, 128, smem, st>>>(out_cycles, nacc, iters, a_off16); break;
   switch (N) { WCTB_MR(16) WCTB_MR(32) WCTB_MR(48) WCTB_MR(64) WCTB_MR(96) WCTB_MR(128) WCTB_MR(256) default: return WCTB_E_UNSUPPORTED; }
 #undef WCTB_MR
   WCTB_RETURN_LAUNCH();
+}
+extern "C" int wctb_debug_mma_rate_f16(long long* out_cycles, int N, int nacc, int iters, int ctas, void* stream) {
+  return wctb_debug_mma_rate_f16_off(out_cycles, N, nacc, iters, ctas, 0, stream);
 }
 /* out: [ctas][8] cycles per warp; nwarps in {4, 8}; per_iter even */
 extern "C" int wctb_debug_ldtm_rate(long long* out_cycles, int nwarps, int per_iter, int iters, int ctas, void* stream) {

@@ -15,6 +15,8 @@ summation order.  No feature map is ever gathered.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -109,10 +111,16 @@ class StripGroup:
         self.native_halo = native_halo
         # peer_halo: let the fused tail kernel write the next stage's halo straight into the neighbours' buffers (PeerHalo);
         # WCTB_PEER_HALO=0 falls back to pack / send / recv / cat for every stage
-        import os
         self.peer_halo = os.environ.get("WCTB_PEER_HALO", "1") == "1"
         self._peer = None
         self.counters = {"peer_halo": 0, "nccl_halo": 0}     # halo exchanges by mechanism (bench.py reports them)
+        # use_graph: capture the whole sharded step of one input shape (two streams, ~1500 launches, the NCCL statistic
+        # all-reduces, the first halo exchange and the peer-halo barriers) in ONE CUDA graph per rank and replay it.  With 8
+        # ranks on one host the eager schedule is bound by the host (Python launches at ~8 us each, 8 processes sharing the
+        # cores); a replay needs one launch.  Every rank captures the same program, so the NCCL order is identical everywhere.
+        self.use_graph = os.environ.get("WCTB_SHARD_GRAPH", "1") == "1"
+        self.max_graphs = 3
+        self._graphs = {}
 
     # ---- collectives used by WCT._moments
     def allreduce_(self, t: torch.Tensor):
@@ -185,7 +193,75 @@ class StripGroup:
         return full[..., cuts[rank]:cuts[rank + 1]].contiguous()
 
     def stylize(self, stage_fn, mode: str, content_own: torch.Tensor, style_own: torch.Tensor, alpha: float = 1.0,
-                stages=(5, 4, 3, 2, 1), num_run: int = 1, content_width: int = None, style_width: int = None) -> torch.Tensor:
+                stages=(5, 4, 3, 2, 1), num_run: int = 1, content_width: int = None, style_width: int = None,
+                use_graph: bool = None) -> torch.Tensor:
+        """Sharded stylization; see `_stylize_eager` for the arguments.  With `use_graph` (default: self.use_graph) and a `WCT`
+        executor on CUDA strips whose whole-image widths are given, the step is captured once per input shape in a CUDA graph
+        (after one eager pass that packs weights and opens the peer buffers) and replayed afterwards."""
+        use_graph = self.use_graph if use_graph is None else use_graph
+        if (use_graph and content_own.is_cuda and style_own.is_cuda and content_width is not None and style_width is not None
+                and hasattr(stage_fn, "style_part") and hasattr(stage_fn, "content_part") and getattr(stage_fn, "timeline", None) is None):
+            return self._stylize_graph(stage_fn, mode, content_own, style_own, alpha, tuple(stages), num_run, content_width, style_width)
+        return self._stylize_eager(stage_fn, mode, content_own, style_own, alpha, stages, num_run, content_width, style_width)
+
+    def pipeline(self, wct, mode: str, content_width: int, style_width: int, alpha: float = 1.0, stages=(5, 4, 3, 2, 1),
+                 num_run: int = 1, depth: int = 2):
+        """per-rank `pipeline.StylizePipeline` around the sharded step: each rank uploads its strips of pair i+1 and downloads its
+        strip of result i-1 while pair i is being computed"""
+        from .pipeline import StylizePipeline
+        return StylizePipeline(lambda c, s: self.stylize(wct, mode, c, s, alpha=alpha, stages=stages, num_run=num_run,
+                                                         content_width=content_width, style_width=style_width), depth=depth)
+
+    def _stylize_graph(self, wct, mode, content_own, style_own, alpha, stages, num_run, content_width, style_width):
+        from . import nets, ops
+        fp = wct._weights_fingerprint(stages) if hasattr(wct, "_weights_fingerprint") else 0
+        key = (mode, tuple(content_own.shape), tuple(style_own.shape), float(alpha), stages, int(num_run), int(content_width), int(style_width),
+               nets.get_precision(), bool(self.peer_halo), bool(self.native_halo), torch.cuda.current_device(), fp,
+               bool(getattr(wct, "fold_into_decoder", True)), float(getattr(wct, "tau", 0.0)))
+        ent = self._graphs.get(key)
+        if ent is None:
+            sc = torch.empty_like(content_own, memory_format=torch.contiguous_format)
+            ss = torch.empty_like(style_own, memory_format=torch.contiguous_format)
+            sc.copy_(content_own)
+            ss.copy_(style_own)
+            args = (wct, mode, sc, ss, alpha, stages, num_run, content_width, style_width)
+            self._stylize_eager(*args)               # eager pass: packs weights, sets kernel attributes, opens the peer buffers
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            graph, out, nl, cnt, ok = torch.cuda.CUDAGraph(), None, 0, {}, 1
+            c0 = dict(self.counters)
+            try:
+                n0 = ops.launches()
+                # thread_local: the NCCL watchdog thread polls its events while this thread captures
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = self._stylize_eager(*args)
+                nl = ops.launches() - n0
+                cnt = {k: self.counters[k] - c0[k] for k in c0}
+            except Exception as e:  # noqa: BLE001
+                print("wct-b200: CUDA graph capture of the sharded step failed on rank %d (%s); running eagerly" % (self.rank, e))
+                ok = 0
+            torch.cuda.synchronize()
+            t = torch.tensor([ok], dtype=torch.int32, device=content_own.device)      # every rank replays, or none does
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            if int(t.item()) == 0:
+                graph = None
+            ent = (graph, sc, ss, out, nl, cnt)
+            self._graphs[key] = ent
+            while len(self._graphs) > max(1, int(self.max_graphs)):
+                self._graphs.pop(next(iter(self._graphs)))
+        graph, sc, ss, out, nl, cnt = ent
+        if graph is None:
+            return self._stylize_eager(wct, mode, content_own, style_own, alpha, stages, num_run, content_width, style_width)
+        sc.copy_(content_own, non_blocking=True)
+        ss.copy_(style_own, non_blocking=True)
+        graph.replay()
+        ops.add_launches(nl)
+        for k, v in cnt.items():
+            self.counters[k] += v
+        return out.clone()
+
+    def _stylize_eager(self, stage_fn, mode: str, content_own: torch.Tensor, style_own: torch.Tensor, alpha: float = 1.0,
+                       stages=(5, 4, 3, 2, 1), num_run: int = 1, content_width: int = None, style_width: int = None) -> torch.Tensor:
         """content_own / style_own: this rank's strips [1,3,H,w].  Returns this rank's strip of the stylized image.
         `stage_fn` is either a callable `fn(stage, content_ext, style_ext, alpha, c_region, s_region, c_count, s_count)`
         (one fused stage) or an executor with `style_part(stage, style_ext, s_region, s_count)` and
@@ -232,8 +308,9 @@ class StripGroup:
                     res = stage_fn.style_part(s, st, s_region, s_count)
                     ev = torch.cuda.Event()
                     ev.record(side)
-                    for t in res:
-                        t.record_stream(main)
+                    if not torch.cuda.is_current_stream_capturing():
+                        for t in res:
+                            t.record_stream(main)
                     style_res[s] = (res, ev)
             todo = list(dict.fromkeys(stages))
             launch_style(todo[0])
@@ -343,7 +420,8 @@ class StripGroup:
         if split and cuda:
             with torch.cuda.stream(main):
                 img = content_chain(img, Wc_tot)
-                img.record_stream(cur)
+                if not torch.cuda.is_current_stream_capturing():
+                    img.record_stream(cur)
             cur.wait_stream(main)
             cur.wait_stream(side)
             return img

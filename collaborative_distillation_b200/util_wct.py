@@ -439,6 +439,12 @@ class WCT(nn.Module):
         ops.add_launches(nlaunch)
         return out.clone()
 
+    def pipeline(self, alpha=1.0, num_run=1, stages=(5, 4, 3, 2, 1), depth=2):
+        """Throughput mode for a sequence of pinned host pairs: `pipeline.StylizePipeline` around stylize() -- the upload of pair
+        i+1 and the download of result i-1 overlap the five stages of pair i (WCT.py:109-131 runs them back to back)."""
+        from .pipeline import StylizePipeline
+        return StylizePipeline(lambda c, s: self.stylize(c, s, alpha=alpha, num_run=num_run, stages=stages), depth=depth)
+
     @torch.no_grad()
     def stylize(self, content, style, alpha=1.0, num_run=1, stages=(5, 4, 3, 2, 1), style_cache=None):
         """content, style: [1,3,H,W] fp32 (CUDA, or CPU -> copied up).  Returns the stylized image on the GPU,

@@ -326,7 +326,13 @@ int wctb_debug_set_trace(long long* buf);
 /* debug: cycles for iters*4*nacc tcgen05.mma (M=128,K=8 tf32) per CTA; layout 0 = planes (SWIZZLE_NONE), 1 = SWIZZLE_128B, 2 = LBO 16 */
 int wctb_debug_mma_rate(long long* out_cycles, int N, int layout, int nacc, int iters, int ctas, void* stream);
 /* cycles per tcgen05.mma.kind::f16 (M=128, K=16) vs N / number of independent accumulators; tcgen05.ld throughput */
+/* debug: 1 (default) = h2 conv layers with Cout <= 64 and Cin <= 64 keep their packed weights resident in shared memory (and the
+   64-channel ones stack the weight halves along N); 0 = weights streamed with every pipeline stage (A/B timing) */
+int wctb_debug_set_h2_resident(int on);
 int wctb_debug_mma_rate_f16(long long* out_cycles, int N, int nacc, int iters, int ctas, void* stream);
+/* same, the A descriptor of MMA k starts (k % 3) * a_off16 sixteen-byte units past a 1024-byte boundary (the dx taps of the
+   linear-pitch convolution: does a start address off the 128-byte core-matrix grid slow the operand fetch?) */
+int wctb_debug_mma_rate_f16_off(long long* out_cycles, int N, int nacc, int iters, int ctas, int a_off16, void* stream);
 int wctb_debug_ldtm_rate(long long* out_cycles, int nwarps, int per_iter, int iters, int ctas, void* stream);
 
 /* ---- self tests (device-side descriptor / pipeline checks used by tests and smoke) ------- */

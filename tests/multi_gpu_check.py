@@ -49,8 +49,16 @@ def main():
         grp = parallel.StripGroup(native_halo="--native-halo" in sys.argv)
         grp.peer_halo = "--no-peer" not in sys.argv       # fused tail writes the neighbours' halos over NVLink (default) vs NCCL exchange
         wct.dist = grp
-        own = grp.stylize(wct, "16x", grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev),
-                          grp.own_slice(style, parallel.strip_cuts(Ws, world), rank).to(dev), content_width=Wc, style_width=Ws)
+        c_own = grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev)
+        s_own = grp.own_slice(style, parallel.strip_cuts(Ws, world), rank).to(dev)
+        # default: the step is captured in a CUDA graph (eager pass, capture, replay); a second replay and the eager schedule
+        # must reproduce it (up to the summation order of the statistics' atomics)
+        own = grp.stylize(wct, "16x", c_own, s_own, content_width=Wc, style_width=Ws)
+        own_r = grp.stylize(wct, "16x", c_own, s_own, content_width=Wc, style_width=Ws)
+        own_e = grp.stylize(wct, "16x", c_own, s_own, content_width=Wc, style_width=Ws, use_graph=False)
+        graphed = any(e[0] is not None for e in grp._graphs.values())
+        dg = torch.tensor([(own_r - own).abs().max().item(), (own_e - own).abs().max().item()], dtype=torch.float64, device=dev)
+        dist.all_reduce(dg, op=dist.ReduceOp.MAX)
         # the legacy one-call-per-stage executor must agree with the overlapped one
         own2 = grp.stylize(wct.style_transfer_stage, "16x", grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev),
                            grp.own_slice(style, parallel.strip_cuts(Ws, world), rank).to(dev))
@@ -66,11 +74,13 @@ def main():
             tol_d, tol_rms = BOUNDS[precision]
             dl = (full2.cpu() - ref).abs().max().item()
             line = ("multi_gpu_check[%s%s%s]: world=%d shape=%s max|sharded - single| = %.3g (tol %g)  overlapped vs per-stage executor %.3g  "
-                    "(per-stage executor vs single %.3g)  sharded vs oracle rms %.3g max %.3g (rms tol %g)"
-                    % (precision, " big" if big else "", "" if grp.peer_halo else " no-peer", world, tuple(got.shape), d, tol_d, d2, dl, rms, mx, tol_rms))
+                    "(per-stage executor vs single %.3g)  sharded vs oracle rms %.3g max %.3g (rms tol %g)  graph=%s replay vs replay %.3g  "
+                    "replay vs eager %.3g"
+                    % (precision, " big" if big else "", "" if grp.peer_halo else " no-peer", world, tuple(got.shape), d, tol_d, d2, dl, rms, mx, tol_rms,
+                       graphed, dg[0].item(), dg[1].item()))
             print(line, flush=True)
             report.append(line)
-            ok = ok and d <= tol_d and rms <= tol_rms and d2 <= tol_d
+            ok = ok and d <= tol_d and rms <= tol_rms and d2 <= tol_d and dg.max().item() <= tol_d
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

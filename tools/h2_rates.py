@@ -27,3 +27,12 @@ for ctas in (1, 148):
         cyc = out.view(-1, 8)[:ctas, :nw].float().max().item()
         per_load = cyc / (iters * per)
         print("%d  %3d   %7.1f   %7.1f" % (nw, ctas, per_load, nw * 2048.0 / per_load))
+print("kind::f16 M=128 K=16, A start address off the 128-byte grid (dx taps: +0, +off, +2*off units of 16 B):  N nacc off  cycles/MMA")
+for N in (32, 64, 128):
+    na = min(8, 512 // N)
+    for off in (0, 1, 2, 4, 8):
+        iters = 200
+        _lib.check(lib.wctb_debug_mma_rate_f16_off(out.data_ptr(), N, na, iters, 1, off, st), "mma_rate_f16_off")
+        torch.cuda.synchronize()
+        c = out[:1].float().mean().item() / (iters * 4 * na)
+        print("%3d  %d  %d   %7.1f" % (N, na, off, c))
