@@ -20,9 +20,9 @@
 // 64 pixels, the two rightmost positions of a row are masked garbage).
 //
 // Kernel structure (persistent, one CTA per SM, 320 threads):
-//   warp 0   producer: per 16-channel K group ONE tensor-map TMA box (cp.async.bulk.tensor.4d, 4 planes x (TH+2) rows x
-//            64 px) + one bulk copy of the weight slab; tiles touching a true image border use per-row bulk copies with
-//            the reflection resolved in the source address instead (5 % of the tiles at UHD).
+//   warp 0   producer: per 16-channel K group ONE tensor-map TMA box (cp.async.bulk.tensor.3d, 4 planes x (TH+2) rows x
+//            1 KB = 64 px) + one bulk copy of the weight slab (or the whole layer's weights once, H2Cfg::RESW); tiles touching a
+//            true image border are copied by the 32 lanes with the reflection resolved in the source index.
 //   warp 1   single-thread tcgen05.mma issuer; accumulators double-buffered in TMEM (2 x NB blocks of 128 px), so the
 //            MMAs of tile t+1 overlap the epilogue of tile t inside the CTA.
 //   warps 2-9 epilogue (two groups of four, alternating accumulator blocks): tcgen05.ld -> (main + minor) * 1/s + bias -> ReLU
@@ -30,6 +30,8 @@
 //            public API).
 #include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <type_traits>
 
 #include "h2.cuh"
 
@@ -275,37 +277,34 @@ __device__ __forceinline__ void h2_epilogue_tile(const H2Args& a, uint32_t tmem_
 }
 
 // ---------------------------------------------------------------------------------- producer helpers
-// border tile: (TH+2) rows x 4 planes by bulk row copies, reflection resolved in the source address
+// Border tile (one that touches a true image edge): the whole producer warp copies the (TH+2) rows x 4 planes x 64 px halo
+// tile with 16-byte cp.async (all of them in flight at once), the reflection resolved per pixel in the source index (columns
+// and rows beyond the image are clamped: they only feed masked outputs).  The stage is handed to the MMA issuer one stage
+// later (cp.async.wait_group + proxy fence + arrive), so consecutive border stages overlap.  Round 2a issued one cp.async.bulk per row and per reflected
+// 16-byte column from a single thread -- 50-70 small bulk copies per stage, ~7 us, six times an interior stage; with 14 %
+// (960x540) to 56 % (240x135) of the tiles on a border that, not the MMAs, set the kernel time (tools/profile_h2_generic.py:
+// interior tile 4.6 us, border tile 28.8 us).
 template <class C>
-__device__ __forceinline__ void h2_load_border(const H2Args& a, uint8_t* st, uint64_t* bar, int kg, int x0, int y0,
-                                               const __half* wsrc) {
+__device__ __forceinline__ void h2_load_border_warp(const H2Args& a, uint8_t* st, int kg, int x0, int y0, int lane) {
   const int H = a.H, W = a.W;
   const long long HW = (long long)H * W;
-  const int jlo = (x0 == 0) ? 1 : 0;                 // tile col j <-> gx = x0 - 1 + j
-  const int jhi = min(PW, W - x0 + 1);
-  const int ncols = jhi - jlo;
-  const bool left = (x0 == 0);
-  const int jr = W - x0 + 1;                         // tile col of gx == W
-  const bool right = jr < PW;
-  const uint32_t row_bytes = (uint32_t)(ncols + (left ? 1 : 0) + (right ? 1 : 0)) * 16u;
-  mbar_expect_tx(bar, (C::RESW ? 0u : (uint32_t)C::W_BYTES) + 4u * C::ROWS * row_bytes);
-  if (!C::RESW) bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, bar);
   const uint4* xb = reinterpret_cast<const uint4*>(a.x);
+  const int gxa = wctb_reflect(x0 - 1 + lane, W), gxb = wctb_reflect(x0 - 1 + 32 + lane, W);
+  const uint32_t sbase = smem_u32(st) + (uint32_t)lane * 16u;
 #pragma unroll 1
   for (int pl = 0; pl < 4; ++pl) {
     int gp = 4 * kg + pl;
     if (gp >= a.planes_in) gp -= 2;                  // Cin % 16 == 8: the missing chunk has zero weights; feed finite data
     const uint4* plane = xb + (long long)gp * HW;
-#pragma unroll 1
+    const uint32_t sp = sbase + (uint32_t)(pl * C::ROWS) * (PW * 16u);
+#pragma unroll
     for (int i = 0; i < C::ROWS; ++i) {
-      const int gy = wctb_reflect(y0 - 1 + i, H);
-      const uint4* src = plane + (long long)gy * W;
-      const uint32_t dst = smem_u32(st + ((size_t)pl * C::ROWS + i) * PW * 16);
-      bulk_g2s(dst + jlo * 16, src + (x0 - 1 + jlo), (uint32_t)ncols * 16u, bar);
-      if (left) bulk_g2s(dst, src + 1, 16u, bar);                           // gx = -1 -> 1
-      if (right) bulk_g2s(dst + jr * 16, src + (W - 2), 16u, bar);          // gx = W  -> W-2
+      const uint4* src = plane + (long long)wctb_reflect(y0 - 1 + i, H) * W;
+      cpa16(sp + (uint32_t)i * (PW * 16u), src + gxa);
+      cpa16(sp + (uint32_t)i * (PW * 16u) + 512u, src + gxb);
     }
   }
+  cpa_commit();                                      // one group per stage: the caller completes it one stage later
 }
 
 template <class C, int EPI>
@@ -341,37 +340,63 @@ __global__ void __launch_bounds__(H2_THREADS, 1) conv_h2_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =========================== producer ===========================
-    if (elect_one()) {
-      if (C::RESW) {                       // the layer's weights, once per CTA (K group by K group: the first MMAs need only slab 0)
+    // =========================== producer (whole warp; one elected lane drives the TMA unit) ===========================
+    if (C::RESW) {                         // the layer's weights, once per CTA (K group by K group: the first MMAs need only slab 0)
+      if (elect_one()) {
         for (int kg = 0; kg < nkg; ++kg) {
           mbar_expect_tx(wfull + kg, (uint32_t)C::W_BYTES);
           bulk_g2s(smem_u32(resw + (size_t)kg * C::W_BYTES), a.w + (size_t)kg * (C::W_BYTES / 2), C::W_BYTES, wfull + kg);
         }
       }
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const int nblk = tile / tiles_xy, rem = tile - nblk * tiles_xy;
-        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        const int x0 = tx * TW, y0 = ty * C::TH;
-        const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= a.W) || (y0 + C::TH >= a.H);
-        const __half* wblk = a.w + (size_t)nblk * nkg * (C::W_BYTES / 2);
-        for (int kg = 0; kg < nkg; ++kg, ++it) {
-          const int slot = it % L::NSTAGE;
-          mbar_wait(empty + slot, ((it / L::NSTAGE) & 1) ^ 1);
-          uint8_t* st = stages + slot * C::STAGE_BYTES;
-          const __half* wsrc = wblk + (size_t)kg * (C::W_BYTES / 2);
-          if (!border) {
+      __syncwarp();
+    }
+    uint32_t it = 0;
+    int pend = -1;                         // slot of a border stage whose cp.async group has not been handed over yet
+    auto hand_over = [&](auto keep) {      // complete all but the `keep` most recent cp.async groups and publish the pending stage
+      if (pend >= 0) {
+        cpa_wait<decltype(keep)::value>();
+        fence_async_smem();                // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (elect_one()) mbar_arrive(full + pend);
+        __syncwarp();
+        pend = -1;
+      }
+    };
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const int nblk = tile / tiles_xy, rem = tile - nblk * tiles_xy;
+      const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+      const int x0 = tx * TW, y0 = ty * C::TH;
+      const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= a.W) || (y0 + C::TH >= a.H);
+      const __half* wblk = a.w + (size_t)nblk * nkg * (C::W_BYTES / 2);
+      for (int kg = 0; kg < nkg; ++kg, ++it) {
+        const int slot = it % L::NSTAGE;
+        uint8_t* st = stages + slot * C::STAGE_BYTES;
+        const __half* wsrc = wblk + (size_t)kg * (C::W_BYTES / 2);
+        if (!border) {
+          hand_over(std::integral_constant<int, 0>{});
+          if (elect_one()) {
+            mbar_wait(empty + slot, ((it / L::NSTAGE) & 1) ^ 1);
             mbar_expect_tx(full + slot, (uint32_t)C::STAGE_BYTES);
-            tma_load_4d(smem_u32(st), &tmap, 0, x0 - 1, y0 - 1, 4 * kg, full + slot);   // planes beyond the tensor: zero fill
+            tma_load_3d(smem_u32(st), &tmap, 4 * (x0 - 1), y0 - 1, 4 * kg, full + slot);   // planes beyond the tensor: zero fill
             if (!C::RESW) bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, full + slot);
-          } else {
-            h2_load_border<C>(a, st, full + slot, kg, x0, y0, wsrc);
           }
+          __syncwarp();
+        } else {
+          mbar_wait(empty + slot, ((it / L::NSTAGE) & 1) ^ 1);
+          if (!C::RESW) {
+            if (elect_one()) {
+              mbar_expect_tx_only(full + slot, (uint32_t)C::W_BYTES);
+              bulk_g2s(smem_u32(st + C::IN_BYTES), wsrc, C::W_BYTES, full + slot);
+            }
+            __syncwarp();
+          }
+          h2_load_border_warp<C>(a, st, kg, x0, y0, lane);
+          hand_over(std::integral_constant<int, 1>{});      // the previous border stage (this one stays in flight)
+          pend = slot;
         }
       }
     }
-    __syncwarp();
+    hand_over(std::integral_constant<int, 0>{});
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
@@ -433,15 +458,19 @@ EncodeTiledFn get_encode_tiled() {
   }
   return fn;
 }
-// H8 tensor [planes][H][W][8] fp16 as a 4-D tensor map; box = 8 x 64 px x rows x 4 planes
+// H8 tensor [planes][H][W][8] fp16 as a 3-D tensor map of 32-bit words: {W*4 words, H, planes}, box = 256 words (64 px x 16 B) x
+// rows x 4 planes.  The innermost box extent is what the TMA unit moves per request: described as {8 halves, W, H, planes} (the
+// natural 4-D view, inner extent 16 bytes) a 24 KB box became 1536 sixteen-byte requests and took ~4.2 us to land whatever
+// its size -- that latency, not the MMAs or the epilogue, set the tile time of every layer up to 64 channels.  As rows of 1 KB
+// it is 24 requests.
 int make_h8_tmap(CUtensorMap* m, const void* base, int planes, int H, int W, int rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return WCTB_E_CUDA;
-  cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-  cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  cuuint32_t box[4] = {8, (cuuint32_t)PW, (cuuint32_t)rows, 4};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  cuuint64_t dims[3] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[3] = {(cuuint32_t)PW * 4, (cuuint32_t)rows, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_wctb_last_cuda_error = (int)r; return WCTB_E_CUDA; }

@@ -116,6 +116,21 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tmap,
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
+// mbarrier: add to the expected transaction bytes WITHOUT arriving (the arrival follows later, from the same thread)
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Ampere-style asynchronous 16-byte copies (LDGSTS): no register staging, so one warp keeps a whole halo tile in flight
+__device__ __forceinline__ void cpa16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 // mbarrier wait for long waits (persistent pipelines): try_wait with a suspend-time hint, so a waiting warp sleeps in the
 // barrier unit instead of spinning through the issue slots its SM sub-partition shares with the epilogue warps
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
