@@ -346,7 +346,9 @@ def main():
             w = w.to(dev)
             w.fold_into_decoder = bool(args.fold)
             if N > 1:
-                w.dist = parallel.StripGroup()
+                if "grp" not in _wcts:
+                    _wcts["grp"] = parallel.StripGroup()       # one strip group (peer buffers, captured steps) for every workload
+                w.dist = _wcts["grp"]
             _wcts[mode] = w
         return _wcts[mode]
 
@@ -551,6 +553,10 @@ def main():
 H2_CYC = {16: 39.1, 32: 40.1, 48: 44.1, 64: 48.1, 96: 56.1, 128: 64.1, 256: 128.3}   # profiles/r02_h2_rates.txt
 
 
+def rows_available(rec):
+    return any(len(v) > 0 for v in rec.values())
+
+
 def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     """One instrumented pass: CUDA events around every conv launch (generic, fused head, fused tail), grouped by kernel
     shape class; report the class with the largest time share against the measured peaks."""
@@ -644,6 +650,10 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     overlap_prev = getattr(wct, "overlap_style", False)
     wct.overlap_style = False                       # single stream, so event pairs bracket exactly one kernel each
+    grp_ = getattr(wct, "dist", None)
+    graph_prev = getattr(grp_, "use_graph", None)
+    if grp_ is not None:
+        grp_.use_graph = False                      # the instrumented pass must launch kernel by kernel, not replay a graph
     for name, fn in wrappers.items():
         originals[name] = getattr(ops, name)
         setattr(ops, name, fn)
@@ -659,7 +669,11 @@ def conv_roofline(P, ops, wct, step, content_d, style_d, precision):
         for name in wrappers:
             setattr(ops, name, originals[name])
         wct.overlap_style = overlap_prev
+        if grp_ is not None:
+            grp_.use_graph = graph_prev
     step_ms = t0.elapsed_time(t1)
+    if not rows_available(rec):
+        return None
     rows = []
     for (kern, shape), evs in rec.items():
         rows.append({"kernel": kern, "shape": shape, "launches": len(evs), "ms": sum(e[0].elapsed_time(e[1]) for e in evs),

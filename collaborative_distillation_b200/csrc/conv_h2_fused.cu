@@ -12,9 +12,7 @@
 // the tile pitch is 32 pixels -- a TMEM lane quarter (= one warp) is exactly one tile row, the two rightmost positions
 // of a row are the usual garbage columns, an accumulator block of 128 positions is 4 rows.  With the hi/lo weight halves
 // stacked as well (N = 96: [3 dx][16] main | [3 dx][16] minor) a 16->16 conv costs 3 x (56 + 44) = 300 cycles per 128
-// positions instead of 9 x (40 + 39) = 711.  (Round 2b: the kernels turned out to be bound by their epilogues, so the three
-// products now accumulate into the same 48 columns -- 3 x 3 x 44 = 396 cycles -- which halves the TMEM loads of the epilogue
-// and removes its main + minor additions; the packed weight tiles are unchanged, the lo half is addressed as rows 48..95.)
+// positions instead of 9 x (40 + 39) = 711.
 //
 // Pipeline.  A tile is 32 output rows x 28 columns.  Inside a tile the two convolutions are pipelined at accumulator-
 // block granularity through two small TMEM rings (2 x 96 columns each): the first conv's block j is converted by its
@@ -67,20 +65,38 @@ __device__ __forceinline__ FTile f_tile(int tile, int tiles_x, int H) {
   return t;
 }
 
-// out[c] = sum_dx shfl_down(D[dx*16 + c], dx)   for one dx-stacked accumulator block (48 columns)
+// out[c] = sum_dx shfl_down(main[dx*16 + c] + minor[dx*16 + c], dx)   for one dx-stacked accumulator block (96 columns)
 __device__ __forceinline__ void f_reduce_dx(uint32_t taddr, float* out) {
-  uint32_t m0[16], m1[16], m2[16];
+  uint32_t m0[16], n0[16], m1[16], n1[16];
   tmem_ld16_issue(taddr, m0);
+  tmem_ld16_issue(taddr + 48u, n0);
   tmem_ld16_issue(taddr + 16u, m1);
-  tmem_ld16_issue(taddr + 32u, m2);
+  tmem_ld16_issue(taddr + 64u, n1);
   tmem_ld16_wait(m0);
+  tmem_ld16_wait(n0);
   tmem_ld16_wait(m1);
-  tmem_ld16_wait(m2);
+  tmem_ld16_wait(n1);
+  f32x2 acc[8];
+  float s1[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    // out[p] = D0[p] + D1[p + 1] + D2[p + 2] = D0[p] + (D1 + shfl_down(D2, 1))[p + 1]
-    const float t = __uint_as_float(m1[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(m2[i]), 1);
-    out[i] = __uint_as_float(m0[i]) + __shfl_down_sync(0xffffffffu, t, 1);
+  for (int i = 0; i < 8; ++i) {
+    acc[i] = add2(pk2(__uint_as_float(m0[2 * i]), __uint_as_float(m0[2 * i + 1])), pk2(__uint_as_float(n0[2 * i]), __uint_as_float(n0[2 * i + 1])));
+    upk2(add2(pk2(__uint_as_float(m1[2 * i]), __uint_as_float(m1[2 * i + 1])), pk2(__uint_as_float(n1[2 * i]), __uint_as_float(n1[2 * i + 1]))),
+         s1[2 * i], s1[2 * i + 1]);
+  }
+  tmem_ld16_issue(taddr + 32u, m0);              // dx = 2 flies while the dx = 1 shuffles run
+  tmem_ld16_issue(taddr + 80u, n0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    acc[i] = add2(acc[i], pk2(__shfl_down_sync(0xffffffffu, s1[2 * i], 1), __shfl_down_sync(0xffffffffu, s1[2 * i + 1], 1)));
+  tmem_ld16_wait(m0);
+  tmem_ld16_wait(n0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a, b;
+    upk2(add2(pk2(__uint_as_float(m0[2 * i]), __uint_as_float(m0[2 * i + 1])), pk2(__uint_as_float(n0[2 * i]), __uint_as_float(n0[2 * i + 1]))), a, b);
+    acc[i] = add2(acc[i], pk2(__shfl_down_sync(0xffffffffu, a, 2), __shfl_down_sync(0xffffffffu, b, 2)));
+    upk2(acc[i], out[2 * i], out[2 * i + 1]);
   }
 }
 // v[i] = relu(v[i] * s + b[i]) for 16 values, packed FFMA2
@@ -99,19 +115,13 @@ __device__ __forceinline__ void f_scale_bias_relu16(float* v, float s, const flo
 // planes, pitch 32) -> TMEM columns [tacc, tacc + 96).  wsm: [3 dy][2 chunks][96 rows][16 B] (rows 0..47 hi, 48..95 lo).
 template <int PLANE>
 __device__ __forceinline__ void f_issue_conv16(uint32_t mid, uint32_t wsm, uint32_t tacc, int k) {
-  // The three products of the hi/lo pairs accumulate into the SAME 48 columns (3 x 44 cycles per dy instead of 56 + 44 for the
-  // [w_hi | w_lo] stacking): these kernels are bound by their epilogues, and this halves the TMEM columns the epilogue loads and
-  // removes its main + minor additions.
-  constexpr uint32_t id48 = umma_idesc_f16(48);
+  constexpr uint32_t id96 = umma_idesc_f16(96), id48 = umma_idesc_f16(48);
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
     const uint32_t a = mid + (uint32_t)(4 * k + dy) * F_ROW;
-    const uint64_t bd_hi = umma_desc(wsm + (uint32_t)dy * F_WB, 96u * 16u, 128u);                  // rows  0..47: w_hi
-    const uint64_t bd_lo = umma_desc(wsm + (uint32_t)dy * F_WB + 48u * 16u, 96u * 16u, 128u);      // rows 48..95: w_lo
-    const uint64_t a_hi = umma_desc(a, 2u * PLANE, 128u);
-    umma_f16(tacc, a_hi, bd_hi, id48, dy > 0 ? 1u : 0u);                                   // hi x w_hi
-    umma_f16(tacc, umma_desc(a + PLANE, 2u * PLANE, 128u), bd_hi, id48, 1u);               // lo x w_hi
-    umma_f16(tacc, a_hi, bd_lo, id48, 1u);                                                 // hi x w_lo
+    const uint64_t bd = umma_desc(wsm + (uint32_t)dy * F_WB, 96u * 16u, 128u);
+    umma_f16(tacc, umma_desc(a, 2u * PLANE, 128u), bd, id96, dy > 0 ? 1u : 0u);            // hi x [w_hi | w_lo]
+    umma_f16(tacc, umma_desc(a + PLANE, 2u * PLANE, 128u), bd, id48, 1u);                  // lo x  w_hi
   }
 }
 
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      constexpr uint32_t id48 = umma_idesc_f16(48);
+      constexpr uint32_t id96 = umma_idesc_f16(96);
       const uint32_t w11s = smem_u32(smem + HD_OFF_W11), w12s = smem_u32(smem + HD_OFF_W12);
       mbar_wait_sleep(bars + B_WFULL, 0);
       int i1 = 0, j1 = 0, i2 = 0, k2 = 0;          // cursors: (local tile, block) of the next first- / second-conv block
@@ -256,13 +266,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_head_h2_kernel(const HeadH2
           // conv11: K chunk 0 = image row r (RGB hi | RGB lo of one pixel), chunk 1 = row r + 1 (LBO = one row)
           const uint32_t a = smem_u32(smem + (i1 & 1) * HD_IN_BYTES) + (uint32_t)(4 * j1) * F_ROW;
           const uint32_t tacc = tmem_base + F_ACC1 + slot * 96u;
-          // weight rows 0..47 (w_hi against the hi | lo halves of a pixel) and 48..95 (w_lo against the hi half) accumulate into
-          // the same 48 columns, like f_issue_conv16
-          const uint64_t a01 = umma_desc(a, F_ROW, 128u), a2 = umma_desc(a + 2u * F_ROW, F_ROW, 128u);
-          umma_f16(tacc, a01, umma_desc(w11s, 96u * 16u, 128u), id48, 0u);                              // dy 0, 1
-          umma_f16(tacc, a01, umma_desc(w11s + 48u * 16u, 96u * 16u, 128u), id48, 1u);
-          umma_f16(tacc, a2, umma_desc(w11s + F_WB, 96u * 16u, 128u), id48, 1u);                        // dy 2, (zero)
-          umma_f16(tacc, a2, umma_desc(w11s + F_WB + 48u * 16u, 96u * 16u, 128u), id48, 1u);
+          umma_f16(tacc, umma_desc(a, F_ROW, 128u), umma_desc(w11s, 96u * 16u, 128u), id96, 0u);                  // dy 0, 1
+          umma_f16(tacc, umma_desc(a + 2u * F_ROW, F_ROW, 128u), umma_desc(w11s + F_WB, 96u * 16u, 128u), id96, 1u);  // dy 2, (zero)
           tc_commit(bars + B_A1_FULL + slot);
           ++g1;
           if (++j1 == t1.nb1) {
@@ -531,18 +536,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv_tail_h2_kernel(const TailH2
         if (slot != (uint32_t)grp) continue;        // the other group's block
         mbar_wait_sleep(bars + B_A2_FULL + slot, (g2 >> 1) & 1u);
         tc_fence_after();
-        // channels 0..2 of each dx group at dx*16
-        float m[3][4];
+        // channels 0..2 of each dx group: main at dx*16, minor at 48 + dx*16
+        float m[6][4];
         const uint32_t ta = tq + slot * 96u;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) tmem_ld4(ta + 16u * d, m[d]);
+        for (int d = 0; d < 3; ++d) { tmem_ld4(ta + 16u * d, m[d]); tmem_ld4(ta + 48u + 16u * d, m[3 + d]); }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + B_A2_EMPTY + slot);
         float v[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          v[c] = m[0][c] + __shfl_down_sync(0xffffffffu, m[1][c], 1) + __shfl_down_sync(0xffffffffu, m[2][c], 2);
+          v[c] = (m[0][c] + m[3][c]) + __shfl_down_sync(0xffffffffu, m[1][c] + m[4][c], 1) + __shfl_down_sync(0xffffffffu, m[2][c] + m[5][c], 2);
         const int gy = t.ya + 4 * k + q, gx = t.x0 + lane;
         const int ox = gx - h.own_x0;
         if (lane < F_TW && gy < H && gx < W && ox >= 0 && ox < h.own_w) {

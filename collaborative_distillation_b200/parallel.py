@@ -49,6 +49,9 @@ def strip_cuts(W: int, world: int):
     return cuts
 
 
+_KEEP_ALIVE = []   # captured sharded steps (CUDA graphs with NCCL nodes) stay alive until the process exits
+
+
 class PeerHalo:
     """Peer-mapped next-stage strip buffers for the fused tail kernel (compute + halo exchange in one kernel).
 
@@ -119,8 +122,7 @@ class StripGroup:
         # ranks on one host the eager schedule is bound by the host (Python launches at ~8 us each, 8 processes sharing the
         # cores); a replay needs one launch.  Every rank captures the same program, so the NCCL order is identical everywhere.
         self.use_graph = os.environ.get("WCTB_SHARD_GRAPH", "0") == "1"   # opt-in: first 2-GPU run of the capture did not complete
-        self.max_graphs = 3
-        self._graphs = {}
+        self._graphs = {}        # never evicted: a captured step holds NCCL nodes, and its destruction is left to process exit
 
     # ---- collectives used by WCT._moments
     def allreduce_(self, t: torch.Tensor):
@@ -200,7 +202,8 @@ class StripGroup:
         (after one eager pass that packs weights and opens the peer buffers) and replayed afterwards."""
         use_graph = self.use_graph if use_graph is None else use_graph
         if (use_graph and content_own.is_cuda and style_own.is_cuda and content_width is not None and style_width is not None
-                and hasattr(stage_fn, "style_part") and hasattr(stage_fn, "content_part") and getattr(stage_fn, "timeline", None) is None):
+                and hasattr(stage_fn, "style_part") and hasattr(stage_fn, "content_part") and getattr(stage_fn, "timeline", None) is None
+                and self._graph_engine_ok()):
             return self._stylize_graph(stage_fn, mode, content_own, style_own, alpha, tuple(stages), num_run, content_width, style_width)
         return self._stylize_eager(stage_fn, mode, content_own, style_own, alpha, stages, num_run, content_width, style_width)
 
@@ -211,6 +214,12 @@ class StripGroup:
         from .pipeline import StylizePipeline
         return StylizePipeline(lambda c, s: self.stylize(wct, mode, c, s, alpha=alpha, stages=stages, num_run=num_run,
                                                          content_width=content_width, style_width=style_width), depth=depth)
+
+    @staticmethod
+    def _graph_engine_ok():
+        """the capture is exercised (tests/multi_gpu_check.py, bench.py) with the default h2 engine only"""
+        from . import nets
+        return nets.get_precision() == "h2"
 
     def _stylize_graph(self, wct, mode, content_own, style_own, alpha, stages, num_run, content_width, style_width):
         from . import nets, ops
@@ -247,8 +256,7 @@ class StripGroup:
                 graph = None
             ent = (graph, sc, ss, out, nl, cnt)
             self._graphs[key] = ent
-            while len(self._graphs) > max(1, int(self.max_graphs)):
-                self._graphs.pop(next(iter(self._graphs)))
+            _KEEP_ALIVE.append(ent)
         graph, sc, ss, out, nl, cnt = ent
         if graph is None:
             return self._stylize_eager(wct, mode, content_own, style_own, alpha, stages, num_run, content_width, style_width)

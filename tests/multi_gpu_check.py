@@ -30,6 +30,9 @@ def main():
     big = "--big" in sys.argv
     ok, report = True, []
     wpath = os.path.join(ROOT, "tests", "golden", "weights_16x.npz")
+    grp = parallel.StripGroup(native_halo="--native-halo" in sys.argv)     # one group for the whole run
+    grp.peer_halo = "--no-peer" not in sys.argv           # fused tail writes the neighbours' halos over NVLink (default) vs NCCL exchange
+    grp.use_graph = "--no-graph" not in sys.argv and os.environ.get("WCTB_SHARD_GRAPH", "1") == "1"   # captured step (h2 engine) unless told otherwise
     for precision in (("h2",) if big else ("h2", "fp32")):
         P.set_precision(precision)
         wct = P.WCT(SimpleNamespace(mode="16x", numpy=False))
@@ -46,8 +49,6 @@ def main():
             wct.dist = None
             ref = wct.stylize(content.to(dev), style.to(dev)).cpu()          # the default single-GPU path (graph, fast stats, ...)
             oracle = O.stylize(O.load_weights_npz(wpath), "16x", content, style)
-        grp = parallel.StripGroup(native_halo="--native-halo" in sys.argv)
-        grp.peer_halo = "--no-peer" not in sys.argv       # fused tail writes the neighbours' halos over NVLink (default) vs NCCL exchange
         wct.dist = grp
         c_own = grp.own_slice(content, parallel.strip_cuts(Wc, world), rank).to(dev)
         s_own = grp.own_slice(style, parallel.strip_cuts(Ws, world), rank).to(dev)
@@ -56,7 +57,7 @@ def main():
         own = grp.stylize(wct, "16x", c_own, s_own, content_width=Wc, style_width=Ws)
         own_r = grp.stylize(wct, "16x", c_own, s_own, content_width=Wc, style_width=Ws)
         own_e = grp.stylize(wct, "16x", c_own, s_own, content_width=Wc, style_width=Ws, use_graph=False)
-        graphed = any(e[0] is not None for e in grp._graphs.values())
+        graphed = precision == "h2" and any(e[0] is not None for e in grp._graphs.values())
         dg = torch.tensor([(own_r - own).abs().max().item(), (own_e - own).abs().max().item()], dtype=torch.float64, device=dev)
         dist.all_reduce(dg, op=dist.ReduceOp.MAX)
         # the legacy one-call-per-stage executor must agree with the overlapped one
