@@ -545,7 +545,7 @@ def main():
             line[k] = v
         print(json.dumps(line))
     if N > 1:
-        dist.destroy_process_group()
+        parallel.shutdown(0)        # destroy_process_group(), or a hard exit when sharded steps were captured (see parallel.shutdown)
 
 
 # cycles per tcgen05.mma.kind::f16 (M=128, K=16) by N, measured by tools/h2_rates.py (same A-fetch bound as the TF32 K=8

@@ -52,6 +52,28 @@ def strip_cuts(W: int, world: int):
 _KEEP_ALIVE = []   # captured sharded steps (CUDA graphs with NCCL nodes) stay alive until the process exits
 
 
+def shutdown(code: int = 0):
+    """End a multi-GPU process that captured sharded steps.  Measured on 2 B200s (profiles/r02_multi_gpu_graph.txt): with CUDA
+    graphs holding NCCL nodes alive, `dist.destroy_process_group()` / interpreter teardown does not return (the communicator
+    waits for the graphs, the graphs for the communicator).  So: synchronize, agree that every rank is done, flush, and leave
+    without running destructors.  Without captured steps this is an ordinary destroy_process_group()."""
+    import sys
+    if dist.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if not _KEEP_ALIVE:
+            dist.destroy_process_group()
+            return
+    elif not _KEEP_ALIVE:
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
+
+
 class PeerHalo:
     """Peer-mapped next-stage strip buffers for the fused tail kernel (compute + halo exchange in one kernel).
 
@@ -121,7 +143,7 @@ class StripGroup:
         # all-reduces, the first halo exchange and the peer-halo barriers) in ONE CUDA graph per rank and replay it.  With 8
         # ranks on one host the eager schedule is bound by the host (Python launches at ~8 us each, 8 processes sharing the
         # cores); a replay needs one launch.  Every rank captures the same program, so the NCCL order is identical everywhere.
-        self.use_graph = os.environ.get("WCTB_SHARD_GRAPH", "0") == "1"   # opt-in: first 2-GPU run of the capture did not complete
+        self.use_graph = os.environ.get("WCTB_SHARD_GRAPH", "1") == "1"   # processes that captured a step must end with parallel.shutdown()
         self._graphs = {}        # never evicted: a captured step holds NCCL nodes, and its destruction is left to process exit
 
     # ---- collectives used by WCT._moments

@@ -82,14 +82,14 @@ def main():
             print(line, flush=True)
             report.append(line)
             ok = ok and d <= tol_d and rms <= tol_rms and d2 <= tol_d and dg.max().item() <= tol_d
-    dist.barrier()
-    dist.destroy_process_group()
     if rank == 0:
         out = os.environ.get("WCTB_CHECK_OUT")
         if out:
-            json.dump({"ok": ok, "lines": report}, open(out, "w"))
-        if not ok:
-            sys.exit(1)
+            with open(out, "w") as f:
+                json.dump({"ok": ok, "lines": report}, f)
+    parallel.shutdown(0 if ok else 1)      # captured steps hold NCCL nodes: leave without destructors (see parallel.shutdown)
+    if not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":
