@@ -125,8 +125,11 @@ def _worker(rank, world, port, content, style, stages, out_path, split=False):
         dist.all_gather_object(parts, own.numpy())
         if rank == 0:
             np.save(out_path, np.concatenate(parts, axis=-1))
+        # CPU strips never take the captured-step path (there is nothing to capture), whatever the group's default says
+        assert grp.use_graph in (True, False) and not grp._graphs and not parallel._KEEP_ALIVE
     finally:
-        dist.destroy_process_group()
+        parallel.shutdown()          # no captured steps -> an ordinary destroy_process_group()
+        assert not dist.is_initialized()
 
 
 def _free_port():
