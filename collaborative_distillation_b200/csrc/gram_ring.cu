@@ -148,11 +148,12 @@ static int launch_gram_ring(const float* x, int H, int W, int y0, int y1, int x0
   const unsigned iters = (unsigned)((npix + stride - 1) / stride);   // (iters-1)*stride < npix: only the last tile is partial
   const unsigned wreg = (unsigned)(x1 - x0);
   const size_t smem = (size_t)RING * NCH * PIX * sizeof(float4);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[WCTB_MAX_DEVICES] = {};      // per device: one process may drive several GPUs
+  const int dev_slot = wctb_device_slot();
+  if (!attr_done[dev_slot]) {
     WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, true, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WCTB_CUDA_TRY(cudaFuncSetAttribute(gram_ring_kernel<NCH, SPLIT, PIX, RING, false, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[dev_slot] = true;
   }
   if (x0 == 0 && x1 == W)
     gram_ring_kernel<NCH, SPLIT, PIX, RING, true, PEEL><<<(unsigned)ctas, PIX * SPLIT, smem, st>>>((const float4*)x, H, W, y0, x0, wreg,

@@ -175,10 +175,11 @@ static int launch_gram(const float* x, int C, int H, int W, int y0, int y1, int 
   constexpr int GB = SIDE * TR;
   constexpr int GP = (SIDE == 16) ? 64 : 128;
   const size_t smem = (size_t)2 * GP * (GB + 2) * sizeof(T);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[WCTB_MAX_DEVICES] = {};      // per device: one process may drive several GPUs
+  const int dev_slot = wctb_device_slot();
+  if (!attr_done[dev_slot]) {
     WCTB_CUDA_TRY(cudaFuncSetAttribute(centered_gram_kernel<TR, SIDE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[dev_slot] = true;
   }
   const int nb = (C + GB - 1) / GB, nblk = nb * (nb + 1) / 2;
   const long long npix = (long long)(y1 - y0) * (x1 - x0);
