@@ -7,14 +7,18 @@
 One "step" = one full pass of the hot path over one synthetic content/style pair: 5 coarse-to-fine stages of
 encoder(style), encoder(content), whiten-and-colour transform, decoder (WCT.py:120-125).
   value : content megapixels / second with inputs already resident in HBM (CUDA events, max over ranks)
-  e2e   : the same through the public API from pinned HOST buffers, H2D + D2H inside the timed region
+  e2e   : the same from pinned HOST buffers through the public throughput API (WCT.pipeline() / StripGroup.pipeline(): every pair
+          uploaded, computed and downloaded inside the timed region; upload of pair i+1 / download of result i-1 overlap pair i);
+          e2e.serial = one blocking stylize(host tensors) call after another
   e2e_u8 : (extra key, N=1) the same step fed with 8-bit interleaved RGB host buffers through the image-I/O row
            (ToTensor / save_image quantisation on the device): what `WCT.py --gpu_io` moves over PCIe
   roofline : the dominant kernel (by time) measured live with CUDA events on the launch stream
   cpu_baseline : the CPU oracle (port of the reference path, torch-cpu fp32 convs + fp64 transform) on a bounded sample
 Default workload (N=1): BASELINE.json configs[2] = 3840x2160 content / 2000x2000 style, --mode 16x --UHD
 (the config the UHD metric is quoted on; it fits one GPU).  N>1: weak scaling, content 2160 x (3840*N) cut into
-N strips along W (halo exchange + statistic all-reduces per stage), style 2000x2000 sharded the same way.
+N strips along W (halo exchange + statistic all-reduces per stage), style 2000x2000 sharded the same way; the sharded step is
+replayed from one CUDA graph per rank (WCTB_SHARD_GRAPH=0: eager schedule).  The N=2 line carries BASELINE configs[4] (cfg5,
+original mode on 2 GPUs) and the N=8 line configs[3] (cfg4, 10240x4096 on 8 GPUs) as extra keys.
 """
 import argparse
 import json
